@@ -1,0 +1,112 @@
+"""Shared host-side behaviour of the two drop-in classes (restore, dict ordering, dtype rules)."""
+import os
+
+import numpy as np
+
+from . import _engine, _loader
+
+
+class _EmulatorBase:
+    _FIELDS = ()
+    _IS_PCA = False
+
+    # -- construction -------------------------------------------------------------------------
+    def _init_runtime(self, device, precision, verbose):
+        self._device = device
+        self._precision = precision
+        self._engines = {}
+        self.verbose = verbose
+
+    def restore(self, filename):
+        """Load a pre-trained model from `filename + ".pkl"` (reference layout; TF-free reader),
+        or from `filename + ".npz"` (flat container) when no pickle exists."""
+        if os.path.isfile(filename + ".pkl") or not os.path.isfile(filename + ".npz"):
+            # open() raises FileNotFoundError exactly like the reference when the pickle is missing
+            items = _loader.load_pickle_list(filename + ".pkl")
+            attrs = _loader.attributes_from_list(items, self._FIELDS)
+        else:
+            attrs = _loader.load_npz(filename + ".npz", self._FIELDS)
+        for k, v in attrs.items():
+            setattr(self, k, v)
+        self._validate()
+        self._engines = {}
+
+    def _validate(self):
+        arch = [int(self.W_[0].shape[0])] + [int(w.shape[1]) for w in self.W_]
+        if list(self.architecture) != arch:
+            raise ValueError("architecture %s does not match the weight shapes %s" % (list(self.architecture), arch))
+        if int(self.n_layers) != len(self.W_):
+            raise ValueError("n_layers %s != number of weight matrices %d" % (self.n_layers, len(self.W_)))
+
+    def _attrs(self):
+        return {k: getattr(self, k) for k in self._FIELDS}
+
+    def engine(self, device=None):
+        """The device-resident engine for this model (created on first use; one per device)."""
+        dev = self._device if device is None else device
+        if dev is None:
+            dev = 0
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    dev = torch.cuda.current_device()
+            except Exception:
+                pass
+        if dev not in self._engines:
+            self._engines[dev] = _engine.Engine(self._attrs(), device=dev, precision=self._precision)
+        return self._engines[dev]
+
+    def close(self):
+        for e in self._engines.values():
+            e.close()
+        self._engines = {}
+
+    # -- reference API: NumPy in, NumPy out -----------------------------------------------------------
+    def dict_to_ordered_arr_np(self, input_dict):
+        """Sort input parameters (reference cosmopower_NN.py:333-350 / cosmopower_PCAplusNN.py:330-347)."""
+        if self.parameters is not None:
+            return np.stack([input_dict[k] for k in self.parameters], axis=1)
+        return np.stack([input_dict[k] for k in input_dict], axis=1)
+
+    def forward_pass_np(self, parameters_arr):
+        """Forward pass on the B200 (reference cosmopower_NN.py:354-384 / cosmopower_PCAplusNN.py:351-381).
+        The contraction runs in split-fp16/fp32 on the device; the returned dtype follows the
+        reference's promotion rule (float32 inputs -> float32, anything else -> float64)."""
+        return self._forward_np(parameters_arr, ten_to=False)
+
+    def _forward_np(self, parameters_arr, ten_to):
+        x = np.asarray(parameters_arr)
+        if x.ndim != 2 or x.shape[1] != int(self.n_parameters):
+            raise ValueError("parameters array must have shape (N, %d), got %s" % (self.n_parameters, x.shape))
+        out_dtype = np.float32 if x.dtype == np.float32 else np.float64
+        y = self.engine().forward_host(np.ascontiguousarray(x, dtype=np.float32), ten_to=ten_to)
+        return y if out_dtype == np.float32 else y.astype(np.float64)
+
+    def predictions_np(self, parameters_dict):
+        """reference cosmopower_NN.py:388-405 / cosmopower_PCAplusNN.py:384-401."""
+        return self._forward_np(self.dict_to_ordered_arr_np(parameters_dict), ten_to=False)
+
+    def ten_to_predictions_np(self, parameters_dict):
+        """reference cosmopower_NN.py:409-425 / cosmopower_PCAplusNN.py:405-421 (10**x fused in the kernel)."""
+        return self._forward_np(self.dict_to_ordered_arr_np(parameters_dict), ten_to=True)
+
+    # -- batched device-resident twins of predictions_tf / ten_to_predictions_tf ---------------------------
+    def predictions_tf(self, parameters_tensor):
+        """Array-in/array-out twin (reference cosmopower_NN.py:160-190 / cosmopower_PCAplusNN.py:197-218):
+        takes an already ordered CUDA float32 torch tensor (N, n_parameters), returns a CUDA tensor."""
+        return self.engine(parameters_tensor.device.index).forward_torch(parameters_tensor, ten_to=False)
+
+    def ten_to_predictions_tf(self, parameters_tensor):
+        """reference cosmopower_NN.py:194-211 / cosmopower_PCAplusNN.py:222-239."""
+        return self.engine(parameters_tensor.device.index).forward_torch(parameters_tensor, ten_to=True)
+
+    predictions_device = predictions_tf
+    ten_to_predictions_device = ten_to_predictions_tf
+
+    # -- out of scope, named so that callers get a clear message ---------------------------------------
+    def train(self, *a, **k):
+        raise NotImplementedError("cosmopower_b200 is an inference engine; training is out of scope")
+
+    def save(self, filename):
+        """Write the flat .npz container (not the pickle) for this model."""
+        _loader.save_npz(filename + ".npz", self._attrs(), self._FIELDS)

@@ -1,0 +1,230 @@
+"""ctypes binding of the C ABI declared in include/cpb200.h (csrc/libcpb200.so).
+
+There is deliberately no fallback: if the shared library is missing or no sm_100 device is
+visible, creating an engine raises.  Nothing here computes on the CPU.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcpb200.so")
+
+PREC_FP32_SIMT = 0
+PREC_F16X3 = 1
+FLAG_TEN_TO = 1
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "f16x3": PREC_F16X3}
+
+_fp = ctypes.POINTER(ctypes.c_float)
+_fpp = ctypes.POINTER(_fp)
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("n_parameters", ctypes.c_int32), ("n_modes", ctypes.c_int32),
+                ("n_dense", ctypes.c_int32), ("n_pcas", ctypes.c_int32),
+                ("dims", ctypes.POINTER(ctypes.c_int32)),
+                ("W", _fpp), ("b", _fpp), ("alphas", _fpp), ("betas", _fpp),
+                ("parameters_mean", _fp), ("parameters_std", _fp),
+                ("features_mean", _fp), ("features_std", _fp),
+                ("pca_mean", _fp), ("pca_std", _fp), ("pca_transform_matrix", _fp)]
+
+
+# every symbol include/cpb200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("cpb200_abi_version", ctypes.c_int, []),
+    ("cpb200_device_count", ctypes.c_int, []),
+    ("cpb200_create", ctypes.c_int, [ctypes.POINTER(ModelDesc), ctypes.c_int, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_void_p)]),
+    ("cpb200_destroy", ctypes.c_int, [ctypes.c_void_p]),
+    ("cpb200_forward_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                             ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
+    ("cpb200_forward_host", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    ("cpb200_host_alloc", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
+    ("cpb200_host_free", ctypes.c_int, [ctypes.c_void_p]),
+    ("cpb200_engine_info", ctypes.c_int, [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 4),
+    ("cpb200_engine_launch_count", ctypes.c_int64, [ctypes.c_void_p]),
+    ("cpb200_engine_last_kernel_ms", ctypes.c_float, [ctypes.c_void_p]),
+    ("cpb200_engine_set_timing", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    ("cpb200_last_error", ctypes.c_char_p, []),
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library():
+    """Load csrc/libcpb200.so and bind every declared symbol; raises if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError(
+                    "cosmopower_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; "
+                    "g.build()'` or `make -C cosmopower_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, res, args in SYMBOLS:
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load_library().cpb200_last_error().decode("utf-8", "replace")
+        raise RuntimeError("cpb200 error %d: %s" % (rc, msg))
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_fp)
+
+
+class PinnedArray:
+    """A float32 host array in page-locked memory (cpb200_host_alloc); `.array` is the numpy view."""
+
+    def __init__(self, shape):
+        lib = load_library()
+        self._shape = tuple(int(s) for s in shape)
+        n = int(np.prod(self._shape)) if self._shape else 1
+        p = ctypes.c_void_p()
+        _check(lib.cpb200_host_alloc(ctypes.byref(p), ctypes.c_uint64(max(n, 1) * 4)))
+        self._ptr = p
+        buf = (ctypes.c_float * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=np.float32, count=n).reshape(self._shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            load_library().cpb200_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One restored emulator resident on one B200 (opaque cpb200_engine handle)."""
+
+    def __init__(self, attrs, device=0, precision="f16x3"):
+        lib = load_library()
+        self._lib = lib
+        self._h = None
+        n_dense = len(attrs["W_"])
+        dims = [int(attrs["W_"][0].shape[0])] + [int(w.shape[1]) for w in attrs["W_"]]
+        keep = []
+
+        def arr_list(items):
+            arrs = [_f32(a) for a in items]
+            keep.extend(arrs)
+            c = (_fp * max(len(arrs), 1))(*[_ptr(a) for a in arrs])
+            keep.append(c)
+            return c
+
+        def arr(a):
+            a = _f32(a)
+            keep.append(a)
+            return _ptr(a)
+
+        d = ModelDesc()
+        d.n_parameters = int(attrs["n_parameters"])
+        d.n_modes = int(attrs["n_modes"])
+        d.n_dense = n_dense
+        d.n_pcas = int(attrs.get("n_pcas", 0) or 0)
+        cdims = (ctypes.c_int32 * len(dims))(*dims)
+        keep.append(cdims)
+        d.dims = cdims
+        for i, w in enumerate(attrs["W_"]):
+            if tuple(w.shape) != (dims[i], dims[i + 1]):
+                raise ValueError("W_[%d] has shape %s, expected %s" % (i, w.shape, (dims[i], dims[i + 1])))
+        d.W = arr_list(attrs["W_"])
+        d.b = arr_list(attrs["b_"])
+        d.alphas = arr_list(attrs["alphas_"])
+        d.betas = arr_list(attrs["betas_"])
+        d.parameters_mean = arr(attrs["parameters_mean_"])
+        d.parameters_std = arr(attrs["parameters_std_"])
+        d.features_mean = arr(attrs["features_mean_"])
+        d.features_std = arr(attrs["features_std_"])
+        if d.n_pcas:
+            d.pca_mean = arr(attrs["pca_mean_"])
+            d.pca_std = arr(attrs["pca_std_"])
+            d.pca_transform_matrix = arr(attrs["pca_transform_matrix_"])
+        prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        h = ctypes.c_void_p()
+        _check(lib.cpb200_create(ctypes.byref(d), int(device), prec, ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.precision = prec
+        self.n_parameters = d.n_parameters
+        self.n_modes = d.n_modes
+
+    def close(self):
+        if self._h is not None:
+            self._lib.cpb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- device-resident path -------------------------------------------------------------
+    def forward_device_ptr(self, params_ptr, n_rows, out_ptr, out_pitch, ten_to=False, stream=0):
+        _check(self._lib.cpb200_forward_device(self._h, ctypes.c_void_p(params_ptr), int(n_rows),
+                                               ctypes.c_void_p(out_ptr), int(out_pitch),
+                                               FLAG_TEN_TO if ten_to else 0, ctypes.c_void_p(stream)))
+
+    def forward_torch(self, params, out=None, ten_to=False):
+        """params: CUDA float32 tensor (N, P) on this engine's device -> CUDA float32 (N, n_modes)."""
+        import torch
+        if not (params.is_cuda and params.dtype == torch.float32 and params.dim() == 2
+                and params.shape[1] == self.n_parameters):
+            raise ValueError("expected a CUDA float32 tensor of shape (N, %d)" % self.n_parameters)
+        if params.device.index != self.device:
+            raise ValueError("tensor is on cuda:%s, engine on cuda:%d" % (params.device.index, self.device))
+        params = params.contiguous()
+        n = params.shape[0]
+        if out is None:
+            out = torch.empty((n, self.n_modes), dtype=torch.float32, device=params.device)
+        elif not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.shape[0] == n
+                  and out.shape[1] == self.n_modes and out.stride(1) == 1 and out.stride(0) >= self.n_modes):
+            raise ValueError("bad output tensor")
+        stream = torch.cuda.current_stream(params.device).cuda_stream
+        self.forward_device_ptr(params.data_ptr(), n, out.data_ptr(), out.stride(0) if n > 1 else self.n_modes,
+                                ten_to, stream)
+        return out
+
+    # -- host path --------------------------------------------------------------------------
+    def forward_host(self, params, out=None, ten_to=False):
+        """params: float32 C-contiguous (N, P) host array -> float32 (N, n_modes) host array."""
+        params = np.ascontiguousarray(params, dtype=np.float32)
+        if params.ndim != 2 or params.shape[1] != self.n_parameters:
+            raise ValueError("expected an array of shape (N, %d), got %s" % (self.n_parameters, params.shape))
+        n = params.shape[0]
+        if out is None:
+            out = np.empty((n, self.n_modes), dtype=np.float32)
+        _check(self._lib.cpb200_forward_host(self._h, ctypes.c_void_p(params.ctypes.data), n,
+                                             ctypes.c_void_p(out.ctypes.data), out.strides[0] // 4 if n > 1 else self.n_modes,
+                                             FLAG_TEN_TO if ten_to else 0))
+        return out
+
+    # -- introspection ---------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._lib.cpb200_engine_launch_count(self._h))
+
+    def set_timing(self, enabled):
+        _check(self._lib.cpb200_engine_set_timing(self._h, 1 if enabled else 0))
+
+    def last_kernel_ms(self):
+        return float(self._lib.cpb200_engine_last_kernel_ms(self._h))

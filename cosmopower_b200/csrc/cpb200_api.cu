@@ -1,0 +1,528 @@
+// C ABI of the B200 CosmoPower engine (see include/cpb200.h).  Host-side logic only:
+// model validation, weight packing/upload, scratch management, kernel launches and the pipelined
+// host<->device path.  No CPU compute fallback exists: without an sm_100 device every entry point
+// that would compute returns CPB200_E_NO_DEVICE.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cpb200.h"
+#include "simt_kernels.cuh"
+#include "umma_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(CPB200_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),   \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// One dense contraction of the network with its fused epilogue.
+struct Gemm {
+    int K = 0, N = 0;              // logical sizes
+    int epi = cpb::EPI_ACT;
+    std::vector<float> W;          // (K, N) row-major, host copy
+    std::vector<float> p0, p1, p2; // epilogue constants (see build_gemms)
+    // device, SIMT path
+    float *dW = nullptr, *dp0 = nullptr, *dp1 = nullptr, *dp2 = nullptr;
+    // device, UMMA path
+    int k_pad = 0, k_stages = 0, nc = 0, n_chunks = 0;
+    __half* dwpack = nullptr;
+    float4* depi = nullptr;
+};
+
+constexpr int64_t HOST_CHUNK_BYTES = 64ll << 20;   // output bytes per pipelined host chunk
+
+}  // namespace
+
+struct cpb200_engine {
+    int device = 0, precision = 0;
+    int P = 0, n_modes = 0, n_pcas = 0, num_sms = 0;
+    std::vector<Gemm> gemms;
+    float *d_pmean = nullptr, *d_pstd = nullptr;
+    // SIMT scratch (two ping-pong activation buffers)
+    float* simt_buf[2] = {nullptr, nullptr};
+    int64_t simt_rows = 0;
+    int simt_width = 0;
+    // UMMA scratch
+    uint8_t* um_scratch = nullptr;
+    unsigned long long um_scratch_cta = 0;
+    unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
+    int* d_error_flag = nullptr;
+    // host pipeline
+    cudaStream_t hstream[2] = {nullptr, nullptr};
+    float* h_in[2] = {nullptr, nullptr};
+    float* h_out[2] = {nullptr, nullptr};
+    float* d_in[2] = {nullptr, nullptr};
+    float* d_out[2] = {nullptr, nullptr};
+    int64_t chunk_rows = 0;
+    cudaEvent_t kdone[2] = {nullptr, nullptr};   // serialises the two slots' kernels (they share the scratch)
+    // bookkeeping
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+namespace {
+
+template <class T>
+int upload(T** dptr, const T* h, size_t n) {
+    CU(cudaMalloc(reinterpret_cast<void**>(dptr), std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CU(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Turn the reference attributes into the list of contractions + folded epilogue constants.
+int build_gemms(const cpb200_model_desc* d, std::vector<Gemm>& out) {
+    const int nd = d->n_dense;
+    const bool pca = d->n_pcas > 0;
+    for (int i = 0; i < nd; ++i) {
+        Gemm g;
+        g.K = d->dims[i];
+        g.N = d->dims[i + 1];
+        g.W.assign(d->W[i], d->W[i] + static_cast<size_t>(g.K) * g.N);
+        const float* b = d->b[i];
+        g.p0.resize(g.N); g.p1.resize(g.N); g.p2.assign(g.N, 0.f);
+        if (i < nd - 1) {                       // hidden layer: NN.py:375-378
+            g.epi = cpb::EPI_ACT;
+            for (int n = 0; n < g.N; ++n) { g.p0[n] = b[n]; g.p1[n] = d->alphas[i][n]; g.p2[n] = d->betas[i][n]; }
+        } else if (pca) {                       // PCA coefficients: (acc + b) * pca_std + pca_mean
+            g.epi = cpb::EPI_AFFINE;
+            for (int n = 0; n < g.N; ++n) {
+                g.p0[n] = d->pca_std[n];
+                g.p1[n] = static_cast<float>(static_cast<double>(b[n]) * d->pca_std[n] + d->pca_mean[n]);
+            }
+        } else {                                // NN output: (acc + b) * features_std + features_mean
+            g.epi = cpb::EPI_OUT;
+            for (int n = 0; n < g.N; ++n) {
+                g.p0[n] = d->features_std[n];
+                g.p1[n] = static_cast<float>(static_cast<double>(b[n]) * d->features_std[n] + d->features_mean[n]);
+            }
+        }
+        out.push_back(std::move(g));
+    }
+    if (pca) {                                  // basis contraction: PCAplusNN.py:381
+        Gemm g;
+        g.K = d->n_pcas;
+        g.N = d->n_modes;
+        g.epi = cpb::EPI_OUT;
+        g.W.assign(d->pca_transform_matrix, d->pca_transform_matrix + static_cast<size_t>(g.K) * g.N);
+        g.p0.assign(d->features_std, d->features_std + g.N);
+        g.p1.assign(d->features_mean, d->features_mean + g.N);
+        g.p2.assign(g.N, 0.f);
+        out.push_back(std::move(g));
+    }
+    return 0;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Pack one contraction for the tensor-core path: fp16 hi/lo split, chunked along N, staged along
+// K, each (chunk, stage, hi|lo) tile stored in the UMMA K-major core-matrix order
+//   byte offset of element (n, k) inside a tile = (n/8)*512 + (k/8)*128 + (n%8)*16 + (k%8)*2.
+int pack_umma(Gemm& g, int k_pad) {
+    g.k_pad = k_pad;
+    g.k_stages = k_pad / cpb::UM_KS;
+    g.n_chunks = (g.N + cpb::UM_MAX_NC - 1) / cpb::UM_MAX_NC;
+    g.nc = round_up((g.N + g.n_chunks - 1) / g.n_chunks, 32);
+    const size_t tile = static_cast<size_t>(g.nc) * cpb::UM_KS;            // elements per hi or lo tile
+    std::vector<__half> pack(static_cast<size_t>(g.n_chunks) * g.k_stages * 2 * tile, __float2half(0.f));
+    for (int k = 0; k < g.K; ++k) {
+        for (int n = 0; n < g.N; ++n) {
+            const float w = g.W[static_cast<size_t>(k) * g.N + n];
+            if (!std::isfinite(w) || std::fabs(w) > 65000.f)
+                return fail(CPB200_E_RANGE, "weight %g outside the fp16 split range", static_cast<double>(w));
+            const __half hi = __float2half_rn(w);
+            const __half lo = __float2half_rn(w - __half2float(hi));
+            const int c = n / g.nc, nn = n % g.nc, s = k / cpb::UM_KS, kk = k % cpb::UM_KS;
+            const size_t base = (static_cast<size_t>(c) * g.k_stages + s) * 2 * tile;
+            const size_t off = static_cast<size_t>(nn / 8) * 256 + (kk / 8) * 64 + (nn % 8) * 8 + (kk % 8);
+            pack[base + off] = hi;
+            pack[base + tile + off] = lo;
+        }
+    }
+    std::vector<float4> epi(static_cast<size_t>(g.n_chunks) * g.nc, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int n = 0; n < g.N; ++n) {
+        if (g.epi == cpb::EPI_ACT) {
+            const float alpha = g.p1[n], beta = g.p2[n];
+            epi[n] = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
+                                 beta, 1.f - beta);
+        } else {
+            epi[n] = make_float4(g.p0[n], g.p1[n], 0.f, 0.f);
+        }
+    }
+    if (int rc = upload(&g.dwpack, pack.data(), pack.size())) return rc;
+    if (int rc = upload(&g.depi, epi.data(), epi.size())) return rc;
+    return 0;
+}
+
+int launch_simt(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
+                cudaStream_t st) {
+    const int G = static_cast<int>(e->gemms.size());
+    for (int64_t r0 = 0; r0 < n; r0 += e->simt_rows) {
+        const int64_t m = std::min<int64_t>(e->simt_rows, n - r0);
+        const float* A = params + r0 * e->P;
+        int64_t lda = e->P;
+        for (int gi = 0; gi < G; ++gi) {
+            const Gemm& g = e->gemms[gi];
+            const bool last = gi == G - 1;
+            float* C = last ? out + r0 * pitch : e->simt_buf[gi & 1];
+            const int64_t ldc = last ? pitch : e->simt_width;
+            dim3 grid((g.N + cpb::SIMT_BN - 1) / cpb::SIMT_BN, static_cast<unsigned>((m + cpb::SIMT_BM - 1) / cpb::SIMT_BM));
+            const float* im = gi == 0 ? e->d_pmean : nullptr;
+            const float* is = gi == 0 ? e->d_pstd : nullptr;
+            const int ten = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
+            if (g.epi == cpb::EPI_ACT)
+                cpb::dense_simt_kernel<cpb::EPI_ACT><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, im, is);
+            else if (g.epi == cpb::EPI_AFFINE)
+                cpb::dense_simt_kernel<cpb::EPI_AFFINE><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, im, is);
+            else
+                cpb::dense_simt_kernel<cpb::EPI_OUT><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, ten, im, is);
+            ++e->launches;
+            A = C;
+            lda = ldc;
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
+                cudaStream_t st) {
+    cpb::UmmaParams p;
+    memset(&p, 0, sizeof p);
+    p.n_gemms = static_cast<int>(e->gemms.size());
+    for (int i = 0; i < p.n_gemms; ++i) {
+        const Gemm& g = e->gemms[i];
+        p.g[i].wpack = g.dwpack;
+        p.g[i].epi = g.depi;
+        p.g[i].k_stages = g.k_stages;
+        p.g[i].nc = g.nc;
+        p.g[i].n_chunks = g.n_chunks;
+        p.g[i].epi_kind = g.epi;
+    }
+    p.n_parameters = e->P;
+    p.n_modes = e->n_modes;
+    p.ten_to = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
+    p.params = params;
+    p.pmean = e->d_pmean;
+    p.pstd = e->d_pstd;
+    p.out = out;
+    p.out_pitch = pitch;
+    p.n_rows = n;
+    const int64_t n_tiles = (n + cpb::UM_TILE_M - 1) / cpb::UM_TILE_M;
+    p.n_pairs = (n_tiles + 1) / 2;
+    p.scratch = e->um_scratch;
+    p.scratch_cta_bytes = e->um_scratch_cta;
+    p.a0_bytes = e->um_a0_bytes;
+    p.abuf_bytes = e->um_abuf_bytes;
+    p.error_flag = e->d_error_flag;
+    const int grid = static_cast<int>(std::min<int64_t>(p.n_pairs, e->num_sms));
+    cpb::fused_mlp_umma_kernel<<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+    ++e->launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int forward_async(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
+                  cudaStream_t st) {
+    if (n == 0) return 0;
+    if (e->precision == CPB200_PREC_FP32_SIMT) return launch_simt(e, params, n, out, pitch, flags, st);
+    return launch_umma(e, params, n, out, pitch, flags, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpb200_abi_version(void) { return CPB200_ABI_VERSION; }
+
+const char* cpb200_last_error(void) { return g_err.c_str(); }
+
+int cpb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_engine** out) {
+    if (!d || !out) return fail(CPB200_E_INVALID, "null argument");
+    *out = nullptr;
+    if (precision != CPB200_PREC_FP32_SIMT && precision != CPB200_PREC_F16X3)
+        return fail(CPB200_E_INVALID, "unknown precision %d", precision);
+    if (d->n_dense < 1 || d->n_parameters < 1 || d->n_modes < 1 || !d->dims || !d->W || !d->b ||
+        !d->parameters_mean || !d->parameters_std || !d->features_mean || !d->features_std)
+        return fail(CPB200_E_INVALID, "incomplete model description");
+    if (d->n_dense > 1 && (!d->alphas || !d->betas)) return fail(CPB200_E_INVALID, "missing activation parameters");
+    if (d->dims[0] != d->n_parameters) return fail(CPB200_E_INVALID, "architecture[0] != n_parameters");
+    if (d->n_pcas > 0) {
+        if (!d->pca_mean || !d->pca_std || !d->pca_transform_matrix) return fail(CPB200_E_INVALID, "missing PCA arrays");
+        if (d->dims[d->n_dense] != d->n_pcas) return fail(CPB200_E_INVALID, "architecture[-1] != n_pcas");
+    } else if (d->dims[d->n_dense] != d->n_modes) {
+        return fail(CPB200_E_INVALID, "architecture[-1] != n_modes");
+    }
+    for (int i = 0; i <= d->n_dense; ++i)
+        if (d->dims[i] < 1) return fail(CPB200_E_INVALID, "non-positive layer width");
+    if (d->n_dense + (d->n_pcas > 0 ? 1 : 0) > cpb::UM_MAX_GEMMS)
+        return fail(CPB200_E_UNSUPPORTED, "more than %d dense contractions", cpb::UM_MAX_GEMMS);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CPB200_E_NO_DEVICE, "no CUDA device visible; this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(CPB200_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CPB200_E_NO_DEVICE, "device %d is sm_%d%d; this engine is built for sm_100a only", device, prop.major, prop.minor);
+
+    DeviceGuard guard(device);
+    cpb200_engine* e = new cpb200_engine();
+    e->device = device;
+    e->precision = precision;
+    e->P = d->n_parameters;
+    e->n_modes = d->n_modes;
+    e->n_pcas = d->n_pcas;
+    e->num_sms = prop.multiProcessorCount;
+    int rc = build_gemms(d, e->gemms);
+    auto bail = [&](int code) { cpb200_destroy(e); return code; };
+    if (rc) return bail(rc);
+    if ((rc = upload(&e->d_pmean, d->parameters_mean, e->P))) return bail(rc);
+    if ((rc = upload(&e->d_pstd, d->parameters_std, e->P))) return bail(rc);
+
+    if (precision == CPB200_PREC_FP32_SIMT) {
+        int width = 1;
+        for (auto& g : e->gemms) {
+            if ((rc = upload(&g.dW, g.W.data(), g.W.size()))) return bail(rc);
+            if ((rc = upload(&g.dp0, g.p0.data(), g.p0.size()))) return bail(rc);
+            if ((rc = upload(&g.dp1, g.p1.data(), g.p1.size()))) return bail(rc);
+            if ((rc = upload(&g.dp2, g.p2.data(), g.p2.size()))) return bail(rc);
+            if (&g != &e->gemms.back()) width = std::max(width, g.N);
+        }
+        e->simt_width = width;
+        e->simt_rows = 32768;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(reinterpret_cast<void**>(&e->simt_buf[i]), sizeof(float) * e->simt_rows * width) != cudaSuccess)
+                return bail(fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    } else {
+        int k_pad = round_up(e->P, cpb::UM_KS);
+        unsigned max_stages = 1;
+        for (size_t i = 0; i < e->gemms.size(); ++i) {
+            Gemm& g = e->gemms[i];
+            if ((rc = pack_umma(g, k_pad))) return bail(rc);
+            if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
+            k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
+        }
+        e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
+        e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
+        e->um_scratch_cta = 2ull * e->um_a0_bytes + 4ull * e->um_abuf_bytes;
+        const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
+        if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
+            return bail(fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+        if (cudaMemset(e->um_scratch, 0, total) != cudaSuccess) return bail(fail(CPB200_E_CUDA, "memset failed"));
+        if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
+            cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess)
+            return bail(fail(CPB200_E_CUDA, "error flag allocation failed"));
+        if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 cpb::UM_SMEM_BYTES) != cudaSuccess)
+            return bail(fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
+                             cudaGetErrorString(cudaGetLastError())));
+    }
+    for (auto& g : e->gemms) { g.W.clear(); g.W.shrink_to_fit(); }
+    if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess)
+        return bail(fail(CPB200_E_CUDA, "event creation failed"));
+    if (cudaDeviceSynchronize() != cudaSuccess)
+        return bail(fail(CPB200_E_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = e;
+    return 0;
+}
+
+int cpb200_destroy(cpb200_engine* e) {
+    if (!e) return 0;
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    for (auto& g : e->gemms) {
+        cudaFree(g.dW); cudaFree(g.dp0); cudaFree(g.dp1); cudaFree(g.dp2);
+        cudaFree(g.dwpack); cudaFree(g.depi);
+    }
+    cudaFree(e->d_pmean); cudaFree(e->d_pstd);
+    cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
+    cudaFree(e->um_scratch); cudaFree(e->d_error_flag);
+    for (int i = 0; i < 2; ++i) {
+        if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
+        if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);
+        if (e->h_in[i]) cudaFreeHost(e->h_in[i]);
+        if (e->h_out[i]) cudaFreeHost(e->h_out[i]);
+        cudaFree(e->d_in[i]); cudaFree(e->d_out[i]);
+    }
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    cudaGetLastError();
+    delete e;
+    return 0;
+}
+
+int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_rows, float* out_dev,
+                          int64_t out_pitch, int flags, void* stream) {
+    if (!e) return fail(CPB200_E_INVALID, "null engine");
+    if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
+    if (n_rows == 0) return 0;
+    if (!params_dev || !out_dev) return fail(CPB200_E_INVALID, "null buffer");
+    if (out_pitch < e->n_modes) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d", static_cast<long long>(out_pitch), e->n_modes);
+    DeviceGuard guard(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->timing) CU(cudaEventRecord(e->ev0, st));
+    int rc = forward_async(e, params_dev, n_rows, out_dev, out_pitch, flags, st);
+    if (rc) return rc;
+    if (e->timing) { CU(cudaEventRecord(e->ev1, st)); e->ev_valid = true; }
+    return 0;
+}
+
+static int ensure_host_pipeline(cpb200_engine* e) {
+    if (e->hstream[0]) return 0;
+    e->chunk_rows = std::max<int64_t>(256, HOST_CHUNK_BYTES / (static_cast<int64_t>(e->n_modes) * 4) / 256 * 256);
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaStreamCreateWithFlags(&e->hstream[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->kdone[i], cudaEventDisableTiming));
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[i]), sizeof(float) * e->chunk_rows * e->P));
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[i]), sizeof(float) * e->chunk_rows * e->n_modes));
+    }
+    return 0;
+}
+
+static int ensure_bounce(cpb200_engine* e) {
+    if (e->h_in[0]) return 0;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_in[i]), sizeof(float) * e->chunk_rows * e->P));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_out[i]), sizeof(float) * e->chunk_rows * e->n_modes));
+    }
+    return 0;
+}
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_rows, float* out_host,
+                        int64_t out_pitch, int flags) {
+    if (!e) return fail(CPB200_E_INVALID, "null engine");
+    if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
+    if (n_rows == 0) return 0;
+    if (!params_host || !out_host) return fail(CPB200_E_INVALID, "null buffer");
+    if (out_pitch < e->n_modes) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d", static_cast<long long>(out_pitch), e->n_modes);
+    DeviceGuard guard(e->device);
+    if (int rc = ensure_host_pipeline(e)) return rc;
+    const bool pin_in = is_pinned(params_host), pin_out = is_pinned(out_host);
+    if (!(pin_in && pin_out)) if (int rc = ensure_bounce(e)) return rc;
+    const int64_t R = e->chunk_rows;
+    const int64_t n_chunks = (n_rows + R - 1) / R;
+    const size_t row_bytes = sizeof(float) * e->n_modes;
+    // two slots, each with its own stream: H2D -> kernel -> D2H; slot reuse waits for its stream
+    for (int64_t c = 0; c < n_chunks + 2; ++c) {
+        const int slot = static_cast<int>(c & 1);
+        if (c >= 2) {   // retire chunk c-2 of this slot
+            CU(cudaStreamSynchronize(e->hstream[slot]));
+            const int64_t r0 = (c - 2) * R, m = std::min<int64_t>(R, n_rows - r0);
+            if (!pin_out) {
+                if (out_pitch == e->n_modes) memcpy(out_host + r0 * out_pitch, e->h_out[slot], m * row_bytes);
+                else for (int64_t r = 0; r < m; ++r) memcpy(out_host + (r0 + r) * out_pitch, e->h_out[slot] + r * e->n_modes, row_bytes);
+            }
+        }
+        if (c < n_chunks) {
+            const int64_t r0 = c * R, m = std::min<int64_t>(R, n_rows - r0);
+            const float* src = params_host + r0 * e->P;
+            if (!pin_in) { memcpy(e->h_in[slot], src, sizeof(float) * m * e->P); src = e->h_in[slot]; }
+            CU(cudaMemcpyAsync(e->d_in[slot], src, sizeof(float) * m * e->P, cudaMemcpyHostToDevice, e->hstream[slot]));
+            if (c > 0) CU(cudaStreamWaitEvent(e->hstream[slot], e->kdone[slot ^ 1], 0));
+            if (int rc = forward_async(e, e->d_in[slot], m, e->d_out[slot], e->n_modes, flags, e->hstream[slot])) return rc;
+            CU(cudaEventRecord(e->kdone[slot], e->hstream[slot]));
+            if (pin_out) {
+                CU(cudaMemcpy2DAsync(out_host + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot], row_bytes,
+                                     row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[slot]));
+            } else {
+                CU(cudaMemcpyAsync(e->h_out[slot], e->d_out[slot], m * row_bytes, cudaMemcpyDeviceToHost, e->hstream[slot]));
+            }
+        }
+    }
+    return 0;
+}
+
+int cpb200_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return fail(CPB200_E_INVALID, "null argument");
+    CU(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return 0;
+}
+
+int cpb200_host_free(void* ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+int cpb200_engine_info(const cpb200_engine* e, int32_t* n_parameters, int32_t* n_modes, int32_t* precision,
+                       int32_t* device) {
+    if (!e) return fail(CPB200_E_INVALID, "null engine");
+    if (n_parameters) *n_parameters = e->P;
+    if (n_modes) *n_modes = e->n_modes;
+    if (precision) *precision = e->precision;
+    if (device) *device = e->device;
+    return 0;
+}
+
+int64_t cpb200_engine_launch_count(const cpb200_engine* e) { return e ? e->launches : 0; }
+
+int cpb200_engine_set_timing(cpb200_engine* e, int enabled) {
+    if (!e) return fail(CPB200_E_INVALID, "null engine");
+    e->timing = enabled != 0;
+    e->ev_valid = false;
+    return 0;
+}
+
+float cpb200_engine_last_kernel_ms(cpb200_engine* e) {
+    if (!e || !e->ev_valid) return -1.f;
+    DeviceGuard guard(e->device);
+    float ms = -1.f;
+    if (cudaEventSynchronize(e->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.f;
+    }
+    return ms;
+}
+
+}  // extern "C"

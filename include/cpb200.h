@@ -1,0 +1,135 @@
+/*
+ * cpb200.h — C ABI of the B200 engine for CosmoPower's batched emulator forward pass.
+ *
+ * The reference (alessiospuriomancini/cosmopower) is pure Python and has no FFI layer: its
+ * boundary for this path is the Python class API.  Each entry point below names the reference
+ * interface it stands in for; cosmopower_b200/cosmopower_NN.py and cosmopower_PCAplusNN.py bind
+ * these symbols with ctypes and expose the reference's method names on top of them
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * CPB200_E_* code and never throws or aborts; cpb200_last_error() gives the message of the last
+ * failure on the calling thread.  One engine per (model, device).  Calls on different engines
+ * may run concurrently; calls on one engine must be serialised by the caller.
+ */
+#ifndef CPB200_H
+#define CPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPB200_ABI_VERSION 1
+
+/* error codes */
+#define CPB200_OK            0
+#define CPB200_E_INVALID    -1   /* bad argument / inconsistent model description        */
+#define CPB200_E_CUDA       -2   /* a CUDA runtime call failed (message has the detail)  */
+#define CPB200_E_NO_DEVICE  -3   /* no sm_100 device visible: there is NO CPU fallback   */
+#define CPB200_E_UNSUPPORTED -4  /* layer shape outside what the kernels were built for  */
+#define CPB200_E_RANGE      -5   /* weights overflow the fp16 split (use CPB200_PREC_FP32) */
+
+/* numeric formats of the dense contractions (one kernel family, not back-ends) */
+#define CPB200_PREC_FP32_SIMT  0  /* CUDA-core fp32 FMA: on-GPU fp32 truth, slow               */
+#define CPB200_PREC_F16X3      1  /* tcgen05 kind::f16, 2-way fp16 split, 3 products, fp32 acc */
+
+/* flags for cpb200_forward_* */
+#define CPB200_FLAG_TEN_TO     1  /* apply 10**x to the output (ten_to_predictions_np)         */
+
+typedef struct cpb200_engine cpb200_engine;
+
+/*
+ * Host-side description of one restored emulator: exactly the attributes the reference's
+ * `restore` sets (cosmopower/cosmopower_NN.py:310-327; cosmopower/cosmopower_PCAplusNN.py:306-326).
+ * All arrays are float32, C-contiguous, owned by the caller and only read during cpb200_create.
+ *   dims[0..n_dense]  = `architecture`   (n_parameters, hidden..., n_modes or n_pcas)
+ *   W[i]              = `W_[i]`  (dims[i], dims[i+1]) row-major, applied as x @ W (no transpose)
+ *   b[i]              = `b_[i]`  (dims[i+1])
+ *   alphas[i]/betas[i]= `alphas_[i]` / `betas_[i]` (dims[i+1]),  i < n_dense-1
+ * For cosmopower_PCAplusNN set n_pcas > 0 and the three pca_* arrays
+ * (`pca_mean_`, `pca_std_` (n_pcas), `pca_transform_matrix_` (n_pcas, n_modes) row-major).
+ */
+typedef struct cpb200_model_desc {
+    int32_t n_parameters;
+    int32_t n_modes;
+    int32_t n_dense;              /* == reference n_layers: number of W matrices */
+    int32_t n_pcas;               /* 0 for cosmopower_NN */
+    const int32_t* dims;
+    const float* const* W;
+    const float* const* b;
+    const float* const* alphas;
+    const float* const* betas;
+    const float* parameters_mean;
+    const float* parameters_std;
+    const float* features_mean;
+    const float* features_std;
+    const float* pca_mean;
+    const float* pca_std;
+    const float* pca_transform_matrix;
+} cpb200_model_desc;
+
+/* Library identity: returns CPB200_ABI_VERSION. */
+int cpb200_abi_version(void);
+
+/* Number of visible CUDA devices with compute capability 10.x (0 if none / no driver). */
+int cpb200_device_count(void);
+
+/*
+ * Replaces: constructor with restore=True followed by the TF variable set-up
+ * (cosmopower_NN.py:46-68,92-118; cosmopower_PCAplusNN.py:37-54,80-126).
+ * Uploads and packs the weights once on `device` (split into fp16 hi/lo, tiled for the tensor
+ * cores).  `precision` is one of CPB200_PREC_*.
+ */
+int cpb200_create(const cpb200_model_desc* desc, int device, int precision, cpb200_engine** out);
+
+/* Replaces: garbage collection of the reference object. Safe on NULL. */
+int cpb200_destroy(cpb200_engine* e);
+
+/*
+ * Replaces: predictions_tf / ten_to_predictions_tf — array in, array out, both resident on the
+ * device (cosmopower_NN.py:160-211; cosmopower_PCAplusNN.py:164-239), i.e. forward_pass_np
+ * (cosmopower_NN.py:354-384; cosmopower_PCAplusNN.py:351-381) without the host round trip.
+ *   params_dev : (n_rows, n_parameters) float32 row-major, already in the model's column order
+ *   out_dev    : n_rows rows of n_modes float32, row pitch `out_pitch` elements (>= n_modes)
+ *   stream     : cudaStream_t (NULL = legacy default stream); the call is asynchronous on it
+ * No allocation happens inside when n_rows fits the engine's scratch (it always does: the engine
+ * walks the batch in row tiles).  Caller owns both buffers.
+ */
+int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_rows,
+                          float* out_dev, int64_t out_pitch, int flags, void* stream);
+
+/*
+ * Replaces: forward_pass_np / predictions_np / ten_to_predictions_np on host arrays
+ * (cosmopower_NN.py:354-425; cosmopower_PCAplusNN.py:351-421).  Host float32 in, host float32
+ * out; the copies host->device and device->host are pipelined with the kernel in row chunks.
+ * Buffers from cpb200_host_alloc (pinned) are DMA'd directly; pageable buffers go through the
+ * engine's pinned bounce buffers.  Synchronous: returns when `out_host` is complete.
+ */
+int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_rows,
+                        float* out_host, int64_t out_pitch, int flags);
+
+/* Pinned host memory for zero-bounce cpb200_forward_host calls. */
+int cpb200_host_alloc(void** ptr, uint64_t bytes);
+int cpb200_host_free(void* ptr);
+
+/* Introspection used by bench.py / tests. */
+int cpb200_engine_info(const cpb200_engine* e, int32_t* n_parameters, int32_t* n_modes,
+                       int32_t* precision, int32_t* device);
+/* Kernels launched by this engine since creation (each grid launch counts once). */
+int64_t cpb200_engine_launch_count(const cpb200_engine* e);
+/* Device time of the most recent cpb200_forward_device/_host kernel section, in ms
+ * (CUDA events recorded on the launching stream); < 0 if none. Synchronises on those events. */
+float cpb200_engine_last_kernel_ms(cpb200_engine* e);
+/* Turn per-call kernel timing events on/off (off by default: they serialise nothing but cost two
+ * event records per call). */
+int cpb200_engine_set_timing(cpb200_engine* e, int enabled);
+
+/* Message for the most recent failure on this thread ("" if none). */
+const char* cpb200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPB200_H */

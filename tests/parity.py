@@ -1,0 +1,43 @@
+"""Tolerance definitions shared by the parity tests (DESIGN.md "Tolerance").
+
+Log-spectrum models (TT, EE, PP, PKLIN, PKNLBOOST): err = max |y - y_ref| / max(|y_ref|, 1) on the
+log10 output of predictions_np against the float64 oracle; must be <= 1e-5 (north star).
+Linear-spectrum model (TE): err = max |y - y_ref| / (row peak |y_ref|) <= 1e-4 (the reference's own
+float32 path sits at 1.6e-5 by this metric on the stand-in, see tests/golden).
+ten_to_predictions_np: relative error of 10**y <= 5e-5 (= ln10 * 1e-5 * |y| head-room for |y|<=2).
+"""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = ["cmb_TT_NN", "cmb_EE_NN", "cmb_TE_PCAplusNN", "cmb_PP_PCAplusNN", "PKLIN_NN", "PKNLBOOST_NN"]
+LINEAR_MODELS = {"cmb_TE_PCAplusNN"}
+TOL_LOG = 1e-5
+TOL_LINEAR = 1e-4
+TOL_TEN_TO_REL = 5e-5
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def log_error(y, y_ref):
+    y = np.asarray(y, np.float64)
+    y_ref = np.asarray(y_ref, np.float64)
+    return float(np.max(np.abs(y - y_ref) / np.maximum(np.abs(y_ref), 1.0)))
+
+
+def linear_error(y, y_ref):
+    y = np.asarray(y, np.float64)
+    y_ref = np.asarray(y_ref, np.float64)
+    peak = np.max(np.abs(y_ref), axis=1, keepdims=True)
+    return float(np.max(np.abs(y - y_ref) / peak))
+
+
+def model_error(name, y, y_ref):
+    return linear_error(y, y_ref) if name in LINEAR_MODELS else log_error(y, y_ref)
+
+
+def model_tol(name):
+    return TOL_LINEAR if name in LINEAR_MODELS else TOL_LOG

@@ -1,0 +1,127 @@
+"""Parity tests proper: the CUDA path (through the drop-in classes and the C ABI) against the
+oracle / golden vectors.  Tolerances: tests/parity.py."""
+import numpy as np
+import pytest
+
+import cosmopower_b200 as cp
+from cosmopower_b200 import _engine, priors, standins
+from oracle import oracle_np
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+_models = {}
+
+
+def get_model(name, precision="f16x3"):
+    key = (name, precision)
+    if key not in _models:
+        kind, path = standins.model_path(name)
+        _models[key] = (getattr(cp, kind)(restore=True, restore_filename=path, device=0, precision=precision),
+                        standins.load_attrs(kind, path))
+    return _models[key]
+
+
+def test_native_library_is_loaded_and_sees_a_b200():
+    lib = _engine.load_library()
+    assert lib.cpb200_device_count() >= 1
+
+
+@pytest.mark.parametrize("precision", ["f16x3", "fp32"])
+@pytest.mark.parametrize("name", parity.MODELS)
+def test_golden_vectors(name, precision):
+    m, _ = get_model(name, precision)
+    g = parity.golden(name)
+    d = {k: g["params"][:, i] for i, k in enumerate(m.parameters)}
+    y = m.predictions_np(d)
+    assert y.dtype == np.float64 and y.shape == g["pred"].shape
+    err = parity.model_error(name, y, g["pred"])
+    assert err <= parity.model_tol(name), (name, precision, err)
+    if name not in parity.LINEAR_MODELS:
+        t = m.ten_to_predictions_np(d)
+        rel = float(np.max(np.abs(t / 10. ** g["pred"] - 1.0)))
+        assert rel <= parity.TOL_TEN_TO_REL, (name, precision, rel)
+
+
+@pytest.mark.parametrize("name", parity.MODELS)
+def test_seeded_batch_against_oracle(name):
+    m, attrs = get_model(name)
+    x = priors.sample_prior(m.parameters, 10000, seed=20260201)
+    y_ref = oracle_np.forward_chunked(attrs, x)
+    y = m.forward_pass_np(x)
+    assert parity.model_error(name, y, y_ref) <= parity.model_tol(name)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 255, 257, 300, 1025])
+def test_ragged_row_counts(n):
+    name = "PKLIN_NN"
+    m, attrs = get_model(name)
+    x = priors.sample_prior(m.parameters, n, seed=n + 1)
+    y = m.forward_pass_np(x)
+    assert y.shape == (n, m.n_modes)
+    if n:
+        assert parity.log_error(y, oracle_np.forward_pass(attrs, x)) <= parity.TOL_LOG
+
+
+def test_float32_inputs_return_float32_like_reference():
+    m, attrs = get_model("PKNLBOOST_NN")
+    x = priors.sample_prior(m.parameters, 64, seed=9, dtype=np.float32)
+    d = {k: x[:, i] for i, k in enumerate(m.parameters)}
+    y = m.predictions_np(d)
+    assert y.dtype == np.float32
+    assert parity.log_error(y, oracle_np.forward_pass(attrs, x.astype(np.float64))) <= parity.TOL_LOG
+    y_list = m.predictions_np({k: [float(v) for v in x[:3, i]] for i, k in enumerate(m.parameters)})
+    assert y_list.dtype == np.float64 and y_list.shape == (3, m.n_modes)
+
+
+def test_device_tensor_api_matches_host_api_and_respects_pitch():
+    import torch
+    m, attrs = get_model("cmb_PP_PCAplusNN")
+    x = priors.sample_prior(m.parameters, 777, seed=12, dtype=np.float32)
+    y_host = m.engine().forward_host(x)
+    xd = torch.from_numpy(x).cuda()
+    yd = m.predictions_tf(xd)
+    assert yd.is_cuda and yd.shape == (777, m.n_modes)
+    assert np.array_equal(yd.cpu().numpy(), y_host)
+    padded = torch.full((777, 2560), -7.0, device="cuda")
+    view = padded[:, :m.n_modes]
+    m.engine().forward_torch(xd, out=view, ten_to=True)
+    torch.cuda.synchronize()
+    assert torch.all(padded[:, m.n_modes:] == -7.0)          # nothing written past n_modes
+    t = m.ten_to_predictions_tf(xd)
+    assert np.array_equal(view.cpu().numpy(), t.cpu().numpy())
+    rel = np.max(np.abs(t.cpu().numpy() / 10. ** oracle_np.forward_pass(attrs, x.astype(np.float64)) - 1.0))
+    assert rel <= parity.TOL_TEN_TO_REL
+
+
+def test_pinned_host_path_equals_pageable_path():
+    m, _ = get_model("PKLIN_NN")
+    n = 50000                                   # several pipeline chunks
+    x = priors.sample_prior(m.parameters, n, seed=5, dtype=np.float32)
+    y = m.engine().forward_host(x)
+    pin_in, pin_out = _engine.PinnedArray((n, m.n_parameters)), _engine.PinnedArray((n, m.n_modes))
+    pin_in.array[:] = x
+    m.engine().forward_host(pin_in.array, out=pin_out.array)
+    assert np.array_equal(pin_out.array, y)
+    pin_in.free(); pin_out.free()
+
+
+def test_determinism_and_row_independence():
+    m, _ = get_model("cmb_TT_NN")
+    x = priors.sample_prior(m.parameters, 1000, seed=77, dtype=np.float32)
+    y1 = m.engine().forward_host(x)
+    y2 = m.engine().forward_host(x)
+    assert np.array_equal(y1, y2)
+    perm = np.random.default_rng(0).permutation(1000)
+    y3 = m.engine().forward_host(x[perm])
+    assert np.array_equal(y3, y1[perm])          # each row's result does not depend on its neighbours
+
+
+def test_extreme_activation_has_no_nans():
+    # alpha up to 56 in cmb_PP: exp overflows in the reference (-> sigmoid 0); the kernel must agree, NaN-free
+    m, attrs = get_model("cmb_PP_PCAplusNN")
+    lo, hi = priors.prior_bounds(m.parameters)
+    corners = np.array([[lo[i] if (c >> i) & 1 else hi[i] for i in range(6)] for c in range(64)])
+    y = m.forward_pass_np(corners)
+    assert np.all(np.isfinite(y))
+    assert parity.log_error(y, oracle_np.forward_pass(attrs, corners)) <= parity.TOL_LOG
