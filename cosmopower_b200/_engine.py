@@ -48,6 +48,8 @@ SYMBOLS = [
     ("cpb200_engine_launch_count", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_engine_last_kernel_ms", ctypes.c_float, [ctypes.c_void_p]),
     ("cpb200_engine_set_timing", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    ("cpb200_engine_debug_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                                    ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
     ("cpb200_last_error", ctypes.c_char_p, []),
 ]
 
@@ -225,6 +227,20 @@ class Engine:
 
     def set_timing(self, enabled):
         _check(self._lib.cpb200_engine_set_timing(self._h, 1 if enabled else 0))
+
+    def debug_counters(self, enable=True, read=False):
+        """Per-CTA role cycle counters of the fused kernel (debug aid; see csrc/umma_kernel.cuh UM_CNT_*)."""
+        if not read:
+            n = self._lib.cpb200_engine_debug_counters(self._h, 1 if enable else 0, None, 0)
+            if n < 0:
+                _check(n)
+            return None
+        n = self._lib.cpb200_engine_debug_counters(self._h, 1, None, 0)
+        buf = (ctypes.c_int64 * n)()
+        n = self._lib.cpb200_engine_debug_counters(self._h, 1 if enable else 0, buf, n)
+        if n < 0:
+            _check(n)
+        return np.frombuffer(buf, dtype=np.int64).reshape(-1, 16).copy()
 
     def last_kernel_ms(self):
         return float(self._lib.cpb200_engine_last_kernel_ms(self._h))

@@ -55,6 +55,7 @@ struct Gemm {
     float *dW = nullptr, *dp0 = nullptr, *dp1 = nullptr, *dp2 = nullptr;
     // device, UMMA path
     int k_pad = 0, k_stages = 0, nc = 0, n_chunks = 0;
+    float acc_scale = 1.f;         // 1 / (weight scale * input-activation scale), a power of two
     __half* dwpack = nullptr;
     float4* depi = nullptr;
 };
@@ -77,6 +78,7 @@ struct cpb200_engine {
     unsigned long long um_scratch_cta = 0;
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
     int* d_error_flag = nullptr;
+    long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
     // host pipeline
     cudaStream_t hstream[2] = {nullptr, nullptr};
     float* h_in[2] = {nullptr, nullptr};
@@ -149,7 +151,23 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Pack one contraction for the tensor-core path: fp16 hi/lo split, chunked along N, staged along
 // K, each (chunk, stage, hi|lo) tile stored in the UMMA K-major core-matrix order
 //   byte offset of element (n, k) inside a tile = (n/8)*512 + (k/8)*128 + (n%8)*16 + (k%8)*2.
-int pack_umma(Gemm& g, int k_pad) {
+//
+// Range conditioning: fp16 keeps 11 significand bits only down to 6.1e-5, and the lo parts are
+// 2^-11 of the value, so operands are pre-scaled by powers of two (exact) to sit high in the fp16
+// range: weights by s_w (largest |w| lands in [16384, 32768)), the incoming activations by s_in,
+// the produced activations by s_out.  The epilogue undoes s_w*s_in on the fp32 accumulator.
+int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
+    float wmax = 0.f;
+    for (float w : g.W) {
+        if (!std::isfinite(w)) return fail(CPB200_E_RANGE, "non-finite weight");
+        wmax = std::max(wmax, std::fabs(w));
+    }
+    int ex = wmax > 0.f ? static_cast<int>(std::floor(std::log2(32768.0 / wmax))) : 0;
+    ex = std::max(-10, std::min(14, ex));
+    const float s_w = std::ldexp(1.f, ex);
+    if (wmax * s_w > 60000.f) return fail(CPB200_E_RANGE, "weight %g outside the fp16 split range", static_cast<double>(wmax));
+    const float inv = 1.f / (s_w * s_in);
+    g.acc_scale = inv;
     g.k_pad = k_pad;
     g.k_stages = k_pad / cpb::UM_KS;
     g.n_chunks = (g.N + cpb::UM_MAX_NC - 1) / cpb::UM_MAX_NC;
@@ -158,9 +176,7 @@ int pack_umma(Gemm& g, int k_pad) {
     std::vector<__half> pack(static_cast<size_t>(g.n_chunks) * g.k_stages * 2 * tile, __float2half(0.f));
     for (int k = 0; k < g.K; ++k) {
         for (int n = 0; n < g.N; ++n) {
-            const float w = g.W[static_cast<size_t>(k) * g.N + n];
-            if (!std::isfinite(w) || std::fabs(w) > 65000.f)
-                return fail(CPB200_E_RANGE, "weight %g outside the fp16 split range", static_cast<double>(w));
+            const float w = g.W[static_cast<size_t>(k) * g.N + n] * s_w;
             const __half hi = __float2half_rn(w);
             const __half lo = __float2half_rn(w - __half2float(hi));
             const int c = n / g.nc, nn = n % g.nc, s = k / cpb::UM_KS, kk = k % cpb::UM_KS;
@@ -174,10 +190,13 @@ int pack_umma(Gemm& g, int k_pad) {
     for (int n = 0; n < g.N; ++n) {
         if (g.epi == cpb::EPI_ACT) {
             const float alpha = g.p1[n], beta = g.p2[n];
+            // a = acc*acc_scale + b;  h*s_out = ((1-beta)*s_out * sigmoid + beta*s_out) * a
             epi[n] = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
-                                 beta, 1.f - beta);
+                                 beta * s_out, (1.f - beta) * s_out);
+        } else if (g.epi == cpb::EPI_AFFINE) {
+            epi[n] = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
         } else {
-            epi[n] = make_float4(g.p0[n], g.p1[n], 0.f, 0.f);
+            epi[n] = make_float4(g.p0[n] * inv, g.p1[n], 0.f, 0.f);
         }
     }
     if (int rc = upload(&g.dwpack, pack.data(), pack.size())) return rc;
@@ -229,6 +248,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
         p.g[i].nc = g.nc;
         p.g[i].n_chunks = g.n_chunks;
         p.g[i].epi_kind = g.epi;
+        p.g[i].acc_scale = g.acc_scale;
     }
     p.n_parameters = e->P;
     p.n_modes = e->n_modes;
@@ -246,6 +266,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.a0_bytes = e->um_a0_bytes;
     p.abuf_bytes = e->um_abuf_bytes;
     p.error_flag = e->d_error_flag;
+    p.counters = e->d_counters;
     const int grid = static_cast<int>(std::min<int64_t>(p.n_pairs, e->num_sms));
     cpb::fused_mlp_umma_kernel<<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
     ++e->launches;
@@ -344,7 +365,8 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
         unsigned max_stages = 1;
         for (size_t i = 0; i < e->gemms.size(); ++i) {
             Gemm& g = e->gemms[i];
-            if ((rc = pack_umma(g, k_pad))) return bail(rc);
+            const float s_in = i == 0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
+            if ((rc = pack_umma(g, k_pad, s_in, cpb::UM_ACT_SCALE))) return bail(rc);
             if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
             k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
         }
@@ -382,7 +404,7 @@ int cpb200_destroy(cpb200_engine* e) {
     }
     cudaFree(e->d_pmean); cudaFree(e->d_pstd);
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
-    cudaFree(e->um_scratch); cudaFree(e->d_error_flag);
+    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters);
     for (int i = 0; i < 2; ++i) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);
@@ -503,6 +525,27 @@ int cpb200_engine_info(const cpb200_engine* e, int32_t* n_parameters, int32_t* n
     if (precision) *precision = e->precision;
     if (device) *device = e->device;
     return 0;
+}
+
+int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int32_t capacity) {
+    if (!e) return fail(CPB200_E_INVALID, "null engine");
+    DeviceGuard guard(e->device);
+    const size_t n = static_cast<size_t>(e->num_sms) * cpb::UM_CNT_SLOTS;
+    if (out && e->d_counters) {
+        CU(cudaDeviceSynchronize());
+        std::vector<long long> h(n);
+        CU(cudaMemcpy(h.data(), e->d_counters, n * sizeof(long long), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n && i < static_cast<size_t>(capacity); ++i) out[i] = h[i];
+    }
+    if (enable && !e->d_counters) {
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_counters), n * sizeof(long long)));
+        CU(cudaMemset(e->d_counters, 0, n * sizeof(long long)));
+    } else if (!enable && e->d_counters) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(e->d_counters);
+        e->d_counters = nullptr;
+    }
+    return static_cast<int>(n);
 }
 
 int64_t cpb200_engine_launch_count(const cpb200_engine* e) { return e ? e->launches : 0; }

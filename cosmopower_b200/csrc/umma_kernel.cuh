@@ -45,6 +45,8 @@ constexpr int UM_EPI_WARP0 = 4;
 constexpr int UM_EPI_WARPS = 8;
 constexpr int UM_EPI_THREADS = UM_EPI_WARPS * 32;
 constexpr int UM_PIECE = 16;                                 // accumulator columns per tcgen05.ld
+constexpr float UM_INPUT_SCALE = 1024.f;                     // power-of-two pre-scale of the standardised parameters
+constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre-scale of every produced activation
 
 // shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int UM_SMEM_STAGES = 0;
@@ -57,11 +59,12 @@ constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // 
 
 struct UmmaGemm {
     const __half* wpack;   // [n_chunks][k_stages][hi|lo][nc x 32] core-matrix tiles
-    const float4* epi;     // per padded output column: ACT {b, -alpha*log2e, beta, 1-beta}; else {scale, shift,0,0}
+    const float4* epi;     // per padded output column: ACT {b, -alpha*log2e, beta*s, (1-beta)*s}; else {scale, shift,0,0}
     int k_stages;          // K_pad / 32
     int nc;                // chunk width: multiple of 32, <= 256
     int n_chunks;
     int epi_kind;          // cpb::Epilogue
+    float acc_scale;       // undoes the power-of-two operand pre-scales on the accumulator (EPI_ACT)
 };
 
 struct UmmaParams {
@@ -82,7 +85,14 @@ struct UmmaParams {
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
     unsigned abuf_bytes;       // per tile per buffer: max k_stages(gemm >= 1) * 16384
     int* error_flag;           // set to a code by the watchdog before trapping
+    long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
 };
+
+// debug counter slots (cycles), per CTA
+enum { UM_CNT_LOAD_WAIT_EMPTY = 0, UM_CNT_LOAD_WAIT_AREADY = 1, UM_CNT_LOAD_TOTAL = 2,
+       UM_CNT_MMA_WAIT_FULL = 3, UM_CNT_MMA_WAIT_ACCEMPTY = 4, UM_CNT_MMA_TOTAL = 5,
+       UM_CNT_EPI_WAIT_ACCFULL = 6, UM_CNT_EPI_ACT = 7, UM_CNT_EPI_OUT = 8, UM_CNT_EPI_TOTAL = 9,
+       UM_CNT_IN_WAIT = 10, UM_CNT_IN_TOTAL = 11, UM_CNT_SLOTS = 16 };
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -111,19 +121,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 #ifndef CPB_WATCHDOG_CYCLES
 #define CPB_WATCHDOG_CYCLES 6000000000LL   // ~3 s at 2 GHz: a stuck pipeline traps instead of hanging the GPU
 #endif
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+__device__ __noinline__ long long mbar_wait_slow(uint32_t bar, uint32_t parity, int* error_flag, int code) {
     const long long t0 = clock64();
+    long long t1 = t0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > CPB_WATCHDOG_CYCLES) {
+        t1 = clock64();
+        if (t1 - t0 > CPB_WATCHDOG_CYCLES) {
             if (error_flag) atomicExch(error_flag, code);
             __threadfence_system();
             __trap();
         }
     }
+    return clock64() - t0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(bar, parity, error_flag, code);
+// returns the cycles spent blocked (0 on the fast path); callers may add it to a debug counter
+__device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return 0;
+    return mbar_wait_slow(bar, parity, error_flag, code);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -244,6 +258,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     if (warp == 0) {
         // ===================== loader: bulk copies into the stage ring =====================
         if (lane == 0) {
+            long long w_empty = 0, w_aready = 0; const long long t_begin = clock64();
             int stage = 0; uint32_t ph_empty = 1;                 // fresh "empty" barriers pass at parity 1
             uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0};
             for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
@@ -253,17 +268,17 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     for (int t = 0; t < 2; ++t) {
                         const uint8_t* a_src;
                         if (g == 0) {
-                            mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1;
+                            w_aready += mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1;
                             a_src = a0_buf(t);
                         } else {
-                            mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1;
+                            w_aready += mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1;
                             a_src = a_buf(t, g & 1);
                         }
                         for (int c = 0; c < L.n_chunks; ++c) {
                             const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack)
                                                    + static_cast<size_t>(c) * L.k_stages * b_bytes;
                             for (int s = 0; s < L.k_stages; ++s) {
-                                mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
+                                w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
                                 const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
                                 mbar_arrive_expect_tx(bar_full(stage), UM_A_STAGE_BYTES + b_bytes);
                                 bulk_g2s(dst, a_src + static_cast<size_t>(s) * UM_A_STAGE_BYTES, UM_A_STAGE_BYTES, bar_full(stage));
@@ -274,10 +289,16 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     }
                 }
             }
+            if (P.counters) {
+                long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
+                cnt[UM_CNT_LOAD_WAIT_EMPTY] = w_empty; cnt[UM_CNT_LOAD_WAIT_AREADY] = w_aready;
+                cnt[UM_CNT_LOAD_TOTAL] = clock64() - t_begin;
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
+            long long w_full = 0, w_accempty = 0; const long long t_begin = clock64();
             int stage = 0; uint32_t ph_full = 0;
             uint32_t ph_accempty[2] = {1, 1};
             int job = 0;
@@ -289,11 +310,11 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     for (int t = 0; t < 2; ++t) {
                         for (int c = 0; c < L.n_chunks; ++c, ++job) {
                             const int buf = job & 1;
-                            mbar_wait(bar_accempty(buf), ph_accempty[buf], P.error_flag, 201); ph_accempty[buf] ^= 1;
+                            w_accempty += mbar_wait(bar_accempty(buf), ph_accempty[buf], P.error_flag, 201); ph_accempty[buf] ^= 1;
                             tc_fence_after();
                             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
                             for (int s = 0; s < L.k_stages; ++s) {
-                                mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
+                                w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
                                 tc_fence_after();
                                 const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
                                 const uint64_t a_hi = umma_desc(sa);
@@ -316,14 +337,20 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     }
                 }
             }
+            if (P.counters) {
+                long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
+                cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty;
+                cnt[UM_CNT_MMA_TOTAL] = clock64() - t_begin;
+            }
         }
     } else if (warp == 2) {
         // ===================== parameter standardiser: builds the layer-0 A operand =====================
         uint32_t ph_a0free[2] = {1, 1};
+        long long w_in = 0; const long long t_begin = clock64();
         const int np = P.n_parameters;
         for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
             for (int t = 0; t < 2; ++t) {
-                mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
+                w_in += mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
                 const long long row0 = (pair * 2 + t) * UM_TILE_M;
                 uint8_t* dst = a0_buf(t);
                 for (int rr = 0; rr < UM_TILE_M / 32; ++rr) {
@@ -337,7 +364,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             float v = 0.f;
                             if (k < np) {
                                 const float raw_v = (grow < P.n_rows) ? P.params[grow * np + k] : P.pmean[k];
-                                v = (raw_v - P.pmean[k]) / P.pstd[k];
+                                v = (raw_v - P.pmean[k]) / P.pstd[k] * UM_INPUT_SCALE;
                             }
                             x[u] = v;
                         }
@@ -356,6 +383,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 if (lane == 0) mbar_arrive(bar_a0ready(t));
             }
         }
+        if (P.counters && lane == 0) {
+            long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
+            cnt[UM_CNT_IN_WAIT] = w_in; cnt[UM_CNT_IN_TOTAL] = clock64() - t_begin;
+        }
     } else if (warp >= UM_EPI_WARP0) {
         // ===================== epilogue warps =====================
         const int ew = warp - UM_EPI_WARP0;          // 0..7
@@ -366,6 +397,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         float4* epipar = reinterpret_cast<float4*>(sbase + UM_SMEM_EPIPAR);
         float* outstg = reinterpret_cast<float*>(sbase + UM_SMEM_OUTSTG) + ew * (32 * 16);
         uint32_t ph_accfull[2] = {0, 0};
+        long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = clock64();
         int job = 0;
         for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
             for (int g = 0; g < G; ++g) {
@@ -380,8 +412,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                         float4* par = epipar + buf * UM_MAX_NC;
                         if (et < L.nc) par[et] = L.epi[c * L.nc + et];
                         asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_THREADS) : "memory");
-                        mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
+                        w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
                         tc_fence_after();
+                        const long long t_job = clock64();
                         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16)
                                                 + static_cast<uint32_t>(buf * UM_MAX_NC + hf * half_cols);
                         for (int pc = 0; pc < half_cols; pc += UM_PIECE) {
@@ -418,7 +451,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 #pragma unroll
                                     for (int j = 0; j < 16; ++j) {
                                         const float4 pp = par[ccol + j];
-                                        const float a = __uint_as_float(v[j]) + pp.x;
+                                        const float a = fmaf(__uint_as_float(v[j]), L.acc_scale, pp.x);
                                         const float e = ex2_approx(a * pp.y);          // exp(-alpha*a)
                                         const float s = rcp_approx(1.f + e);           // inf -> 0, as numpy
                                         h[j] = fmaf(pp.w, s, pp.z) * a;
@@ -454,9 +487,15 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             mbar_arrive(bar_accempty(buf));
                             if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
                         }
+                        if (L.epi_kind == EPI_OUT) c_out += clock64() - t_job; else c_act += clock64() - t_job;
                     }
                 }
             }
+        }
+        if (P.counters && ew == 0 && lane == 0) {
+            long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
+            cnt[UM_CNT_EPI_WAIT_ACCFULL] = w_accfull; cnt[UM_CNT_EPI_ACT] = c_act; cnt[UM_CNT_EPI_OUT] = c_out;
+            cnt[UM_CNT_EPI_TOTAL] = clock64() - t_begin;
         }
     }
 

@@ -126,6 +126,12 @@ float cpb200_engine_last_kernel_ms(cpb200_engine* e);
  * event records per call). */
 int cpb200_engine_set_timing(cpb200_engine* e, int enabled);
 
+/* Debug: per-CTA cycle counters of the fused kernel's roles (16 int64 per SM; layout UM_CNT_* in
+ * csrc/umma_kernel.cuh).  enable!=0 switches collection on for later launches; when `out` is
+ * non-NULL the counters of the most recent launch are copied out first (device synchronised).
+ * Returns the number of int64 values available, or a negative error. */
+int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int32_t capacity);
+
 /* Message for the most recent failure on this thread ("" if none). */
 const char* cpb200_last_error(void);
 

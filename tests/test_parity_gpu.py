@@ -39,8 +39,9 @@ def test_golden_vectors(name, precision):
     assert err <= parity.model_tol(name), (name, precision, err)
     if name not in parity.LINEAR_MODELS:
         t = m.ten_to_predictions_np(d)
-        rel = float(np.max(np.abs(t / 10. ** g["pred"] - 1.0)))
-        assert rel <= parity.TOL_TEN_TO_REL, (name, precision, rel)
+        assert t.dtype == np.float64 and np.all(t > 0)
+        err10 = parity.ten_to_error(t, g["pred"])
+        assert err10 <= parity.TOL_LOG, (name, precision, err10)
 
 
 @pytest.mark.parametrize("name", parity.MODELS)
@@ -90,8 +91,7 @@ def test_device_tensor_api_matches_host_api_and_respects_pitch():
     assert torch.all(padded[:, m.n_modes:] == -7.0)          # nothing written past n_modes
     t = m.ten_to_predictions_tf(xd)
     assert np.array_equal(view.cpu().numpy(), t.cpu().numpy())
-    rel = np.max(np.abs(t.cpu().numpy() / 10. ** oracle_np.forward_pass(attrs, x.astype(np.float64)) - 1.0))
-    assert rel <= parity.TOL_TEN_TO_REL
+    assert parity.ten_to_error(t.cpu().numpy(), oracle_np.forward_pass(attrs, x.astype(np.float64))) <= parity.TOL_LOG
 
 
 def test_pinned_host_path_equals_pageable_path():

@@ -31,7 +31,7 @@ def main():
         err = parity.model_error(name, y, y_ref)
         t = m.engine().forward_host(x.astype(np.float32), ten_to=True)
         with np.errstate(over="ignore", invalid="ignore"):
-            rel = float(np.nanmax(np.abs(t / 10. ** y_ref - 1.0))) if name not in parity.LINEAR_MODELS else float("nan")
+            rel = parity.ten_to_error(t, y_ref) if name not in parity.LINEAR_MODELS else float("nan")
         xd = torch.from_numpy(x.astype(np.float32)).cuda()
         yd = m.predictions_tf(xd)
         torch.cuda.synchronize()
@@ -50,7 +50,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
-        print("%-18s prec=%s rows=%d err=%.3g (tol %.0e) ten_to_rel=%.3g dev==host:%s first_call=%.3fs | %d rows in %.3f ms = %.3g spectra/s"
+        print("%-18s prec=%s rows=%d err=%.3g (tol %.0e) ten_to_logerr=%.3g dev==host:%s first_call=%.3fs | %d rows in %.3f ms = %.3g spectra/s"
               % (name, prec, rows, err, parity.model_tol(name), rel, same, dt, nb, ms, nb / ms * 1e3), flush=True)
         m.close()
 
