@@ -165,7 +165,8 @@ def run_ours(args):
         engines.append(m.engine(local))
         x = priors.sample_prior(m.parameters, batch, seed=20260101 + i + 1000 * rank, dtype=np.float32)
         xs.append(torch.from_numpy(x).to(dev))
-    out = torch.empty((batch, 2507), dtype=torch.float32, device=dev)     # 10.5 GB, reused by both models
+    # 10.5 GB, reused by both models; row pitch 2512 floats (32-byte aligned rows), (batch, 2507) view
+    out = torch.empty((batch, 2512), dtype=torch.float32, device=dev)[:, :2507]
 
     def step():
         for e, x in zip(engines, xs):

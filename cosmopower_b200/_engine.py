@@ -198,7 +198,10 @@ class Engine:
         params = params.contiguous()
         n = params.shape[0]
         if out is None:
-            out = torch.empty((n, self.n_modes), dtype=torch.float32, device=params.device)
+            # rows padded to a multiple of 8 floats (32-byte sectors) so the kernel can use aligned
+            # vector stores; the caller gets the (n, n_modes) view
+            pitch = (self.n_modes + 7) // 8 * 8
+            out = torch.empty((n, pitch), dtype=torch.float32, device=params.device)[:, :self.n_modes]
         elif not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.shape[0] == n
                   and out.shape[1] == self.n_modes and out.stride(1) == 1 and out.stride(0) >= self.n_modes):
             raise ValueError("bad output tensor")

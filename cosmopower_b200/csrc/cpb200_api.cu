@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -86,6 +87,7 @@ struct cpb200_engine {
     float* d_in[2] = {nullptr, nullptr};
     float* d_out[2] = {nullptr, nullptr};
     int64_t chunk_rows = 0;
+    int64_t dpitch = 0;                 // row pitch of d_out (n_modes rounded up to 8 floats: 32-byte rows)
     cudaEvent_t kdone[2] = {nullptr, nullptr};   // serialises the two slots' kernels (they share the scratch)
     // bookkeeping
     int64_t launches = 0;
@@ -179,7 +181,19 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
             const float w = g.W[static_cast<size_t>(k) * g.N + n] * s_w;
             const __half hi = __float2half_rn(w);
             const __half lo = __float2half_rn(w - __half2float(hi));
-            const int c = n / g.nc, nn = n % g.nc, s = k / cpb::UM_KS, kk = k % cpb::UM_KS;
+            // accumulator column order inside each 32-column block: position 8i+2t+cc holds logical
+            // column 8t+2i+cc, which hands an epilogue lane 8 consecutive logical columns
+            // (tcgen05.ld.16x256b fragment); the map is its own inverse
+            const int c = n / g.nc, nl = n % g.nc, s = k / cpb::UM_KS, kk = k % cpb::UM_KS;
+            const int nb = nl & 31;
+            int nn;
+            if (g.epi == cpb::EPI_OUT) {
+                // output layers: a lane owns logical columns 4t..4t+3 and 16+4t..16+4t+3 (two 16-byte stores)
+                const int t4 = (nb & 15) >> 2, j = (nb & 3) | ((nb >> 4) << 2);
+                nn = (nl & ~31) | ((j >> 1) << 3) | (t4 << 1) | (j & 1);
+            } else {
+                nn = (nl & ~31) | (((nb >> 1) & 3) << 3) | ((nb >> 3) << 1) | (nb & 1);
+            }
             const size_t base = (static_cast<size_t>(c) * g.k_stages + s) * 2 * tile;
             const size_t off = static_cast<size_t>(nn / 8) * 256 + (kk / 8) * 64 + (nn % 8) * 8 + (kk % 8);
             pack[base + off] = hi;
@@ -196,7 +210,10 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
         } else if (g.epi == cpb::EPI_AFFINE) {
             epi[n] = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
         } else {
-            epi[n] = make_float4(g.p0[n] * inv, g.p1[n], 0.f, 0.f);
+            // {scale, shift} for predictions; {scale, shift} * log2(10) for 10**y = 2**(y*log2 10)
+            const double l2_10 = 3.321928094887362;
+            epi[n] = make_float4(g.p0[n] * inv, g.p1[n], static_cast<float>(static_cast<double>(g.p0[n]) * inv * l2_10),
+                                 static_cast<float>(static_cast<double>(g.p1[n]) * l2_10));
         }
     }
     if (int rc = upload(&g.dwpack, pack.data(), pack.size())) return rc;
@@ -261,13 +278,15 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.n_rows = n;
     const int64_t n_tiles = (n + cpb::UM_TILE_M - 1) / cpb::UM_TILE_M;
     p.n_pairs = (n_tiles + 1) / 2;
+    p.n_pairgroups = (p.n_pairs + cpb::UM_CLUSTER - 1) / cpb::UM_CLUSTER;
     p.scratch = e->um_scratch;
     p.scratch_cta_bytes = e->um_scratch_cta;
     p.a0_bytes = e->um_a0_bytes;
     p.abuf_bytes = e->um_abuf_bytes;
     p.error_flag = e->d_error_flag;
     p.counters = e->d_counters;
-    const int grid = static_cast<int>(std::min<int64_t>(p.n_pairs, e->num_sms));
+    const int max_clusters = e->num_sms / cpb::UM_CLUSTER;
+    const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * cpb::UM_CLUSTER;
     cpb::fused_mlp_umma_kernel<<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
     ++e->launches;
     CU(cudaGetLastError());
@@ -438,11 +457,12 @@ int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_r
 static int ensure_host_pipeline(cpb200_engine* e) {
     if (e->hstream[0]) return 0;
     e->chunk_rows = std::max<int64_t>(256, HOST_CHUNK_BYTES / (static_cast<int64_t>(e->n_modes) * 4) / 256 * 256);
+    e->dpitch = (e->n_modes + 7) / 8 * 8;             // 32-byte rows: every 8-byte pair store stays inside one sector
     for (int i = 0; i < 2; ++i) {
         CU(cudaStreamCreateWithFlags(&e->hstream[i], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&e->kdone[i], cudaEventDisableTiming));
         CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[i]), sizeof(float) * e->chunk_rows * e->P));
-        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[i]), sizeof(float) * e->chunk_rows * e->n_modes));
+        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[i]), sizeof(float) * e->chunk_rows * e->dpitch));
     }
     return 0;
 }
@@ -493,13 +513,14 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
             if (!pin_in) { memcpy(e->h_in[slot], src, sizeof(float) * m * e->P); src = e->h_in[slot]; }
             CU(cudaMemcpyAsync(e->d_in[slot], src, sizeof(float) * m * e->P, cudaMemcpyHostToDevice, e->hstream[slot]));
             if (c > 0) CU(cudaStreamWaitEvent(e->hstream[slot], e->kdone[slot ^ 1], 0));
-            if (int rc = forward_async(e, e->d_in[slot], m, e->d_out[slot], e->n_modes, flags, e->hstream[slot])) return rc;
+            if (int rc = forward_async(e, e->d_in[slot], m, e->d_out[slot], e->dpitch, flags, e->hstream[slot])) return rc;
             CU(cudaEventRecord(e->kdone[slot], e->hstream[slot]));
             if (pin_out) {
-                CU(cudaMemcpy2DAsync(out_host + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot], row_bytes,
-                                     row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[slot]));
+                CU(cudaMemcpy2DAsync(out_host + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot],
+                                     sizeof(float) * e->dpitch, row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[slot]));
             } else {
-                CU(cudaMemcpyAsync(e->h_out[slot], e->d_out[slot], m * row_bytes, cudaMemcpyDeviceToHost, e->hstream[slot]));
+                CU(cudaMemcpy2DAsync(e->h_out[slot], row_bytes, e->d_out[slot], sizeof(float) * e->dpitch, row_bytes, m,
+                                     cudaMemcpyDeviceToHost, e->hstream[slot]));
             }
         }
     }

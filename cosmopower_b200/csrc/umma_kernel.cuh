@@ -18,7 +18,13 @@
 // Two row tiles are interleaved per CTA so the epilogue of one overlaps the MMAs of the other.
 //
 // Warp roles (384 threads): warp 0 loader (bulk copies), warp 1 MMA issuer (one thread),
-// warp 2 TMEM allocator + parameter standardiser, warp 3 idle, warps 4..11 epilogue.
+// warp 2 TMEM allocator + parameter standardiser, warp 3 idle, warps 4..11 epilogue
+// (2 warps per TMEM lane quarter, each owning half of the chunk's columns).
+// The epilogue reads accumulators with tcgen05.ld.16x256b, whose fragment gives a thread 2
+// adjacent columns of 2 rows: 4 neighbouring lanes then hold one 16-byte core-matrix row, so the
+// next layer's operand is written with full 128-byte lines and no shared-memory transpose (the
+// shared-memory data pipe is the scarce resource: the tensor core's operand reads and the bulk
+// copies already use most of it).
 //
 // Reference math: cosmopower/cosmopower_NN.py:371-384,425 and
 // cosmopower/cosmopower_PCAplusNN.py:368-381,421.
@@ -35,6 +41,7 @@ constexpr int UM_TILE_M = 128;
 constexpr int UM_KS = 32;                                    // k elements per pipeline stage
 constexpr int UM_MAX_NC = 256;                               // widest N chunk (one accumulator)
 constexpr int UM_STAGES = 4;
+constexpr int UM_CLUSTER = 2;                                // CTAs per cluster sharing every weight stage by multicast
 constexpr int UM_A_HALF_BYTES = UM_TILE_M * UM_KS * 2;       // 8192: one of (hi, lo)
 constexpr int UM_A_STAGE_BYTES = 2 * UM_A_HALF_BYTES;        // 16384
 constexpr int UM_B_STAGE_BYTES_MAX = 2 * UM_MAX_NC * UM_KS * 2;   // 32768
@@ -44,16 +51,15 @@ constexpr int UM_THREADS = 384;
 constexpr int UM_EPI_WARP0 = 4;
 constexpr int UM_EPI_WARPS = 8;
 constexpr int UM_EPI_THREADS = UM_EPI_WARPS * 32;
-constexpr int UM_PIECE = 16;                                 // accumulator columns per tcgen05.ld
+constexpr int UM_PIECE = 32;                                 // accumulator columns per epilogue piece
 constexpr float UM_INPUT_SCALE = 1024.f;                     // power-of-two pre-scale of the standardised parameters
 constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre-scale of every produced activation
 
 // shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int UM_SMEM_STAGES = 0;
-constexpr int UM_SMEM_OUTSTG = UM_STAGES * UM_STAGE_BYTES;                   // 8 warps x 32x16 floats
-constexpr int UM_SMEM_EPIPAR = UM_SMEM_OUTSTG + UM_EPI_WARPS * 32 * 16 * 4;  // 2 x 256 float4
+constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // 2 x 256 float4
 constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + 2 * UM_MAX_NC * 16;
-constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2;
+constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // + alignment slack
 
@@ -80,6 +86,7 @@ struct UmmaParams {
     long long out_pitch;
     long long n_rows;
     long long n_pairs;         // ceil(n_tiles / 2)
+    long long n_pairgroups;    // ceil(n_pairs / UM_CLUSTER): one pair per CTA of a cluster, processed in lockstep
     uint8_t* scratch;          // gridDim.x * scratch_cta_bytes
     unsigned long long scratch_cta_bytes;
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
@@ -143,6 +150,47 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// the same bytes land at the same CTA-relative shared-memory offset of every CTA in `mask`, and each
+// destination's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                                   uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+// L2 eviction-priority policies: the CTA-private activation scratch and the weights must stay in L2
+// (evict_last); an activation tile's final read and the spectrum output are streaming (evict_first)
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                                        uint16_t mask, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_global_v4_hint(void* ptr, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
+                 ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -157,6 +205,11 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// arrive (once the MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -164,7 +217,56 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+// 16 lanes x (2 x 256 bit): thread t gets, for column group i in {0,1}: v[4i+0..1] = (lane t/4, cols 8i+2(t%4)+{0,1}),
+// v[4i+2..3] = (lane t/4+8, same cols)
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr) : "memory");
+}
+// 16 lanes x (4 x 256 bit): thread t gets, for column group i in 0..3: v[4i+0..1] = (lane t/4, cols 8i+2(t%4)+{0,1}),
+// v[4i+2..3] = (lane t/4+8, same cols)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&a)[16], uint32_t (&b)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                   "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16x(uint32_t (&a)[8], uint32_t (&b)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+                 :: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for outstanding tcgen05.ld; the registers are listed as in/out so that no use of them can be
+// scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
+// Ordering of the epilogue's plain stores to the L2-resident scratch before the loader's bulk
+// (async-proxy) reads of the same lines by the same CTA.
+#ifndef UM_SCRATCH_FENCE
+#define UM_SCRATCH_FENCE() __threadfence()
+#endif
 
 // K-major, no-swizzle shared-memory matrix descriptor: core matrices (8 rows x 16 B) are 128 B
 // apart along K (LBO) and 512 B apart along M/N (SBO = 4 core matrices of a 32-wide stage).
@@ -175,6 +277,22 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     d |= static_cast<uint64_t>(512u >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;              // descriptor version for sm_100
     return d;
+}
+// Activation (A) tiles use the K-major SWIZZLE_64B layout instead: a stage is 128 rows x 32 k = 64-byte
+// rows, 8-row atoms of 512 B (SBO), 16-byte chunks XOR-ed with (row>>1)&3.  Rows are contiguous, so the
+// epilogue's fragment (4 lanes = one row's 64 B, 8 lanes = two rows) stores whole 128-byte lines.
+__device__ __forceinline__ uint64_t umma_desc_a(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;               // LBO unused for swizzled K-major
+    d |= static_cast<uint64_t>(512u >> 4) << 32;       // SBO: 8 rows x 64 B
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;               // SWIZZLE_64B
+    return d;
+}
+// byte offset of the 16-byte chunk holding k..k+7 (k multiple of 8, < 32) of row r inside one A tile
+__device__ __forceinline__ uint32_t a_tile_off(int r, int kchunk) {
+    return static_cast<uint32_t>(r) * 64u + static_cast<uint32_t>((kchunk ^ (r >> 1)) & 3) * 16u;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=nc
 __device__ __forceinline__ uint32_t umma_idesc(int nc) {
@@ -205,9 +323,135 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// epilogue of one accumulator chunk for one warp (templated on the layer kind so that the inner
+// loops carry exactly one code path)
+// ---------------------------------------------------------------------------------------------
+struct EpiCtx {
+    uint32_t t_addr0;        // TMEM address of this warp's first column, lanes +0
+    int my_cols;             // columns this warp handles (multiple of 32)
+    int colbase;             // first of them inside the chunk
+    int chunk_col0;          // c * nc
+    int q, tq, tr;
+    const float4* par;       // the chunk's per-column constants in shared memory (logical column order)
+};
+
+// hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
+// contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
+template <int KIND>
+__device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_scale, uint8_t* a_dst) {
+    const uint64_t pol_keep = policy_evict_last();
+    uint32_t va[16], vb[16];
+    const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
+    tmem_ld_16x256b_x4(E.t_addr0, va);                                 // software-pipelined TMEM reads
+    tmem_ld_16x256b_x4(t_addr1, vb);
+    // accumulator column 8i+2tr+cc of a 32-column piece holds logical column 8tr+2i+cc (packing order),
+    // so this lane owns 8 consecutive logical columns = one 16-byte row chunk of the next A tile
+    const int lcol0 = E.colbase + 8 * E.tr;
+    for (int pc = 0; pc < E.my_cols; pc += UM_PIECE) {
+        float4 pp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pp[j] = E.par[lcol0 + pc + j];
+        float x[32];
+        tmem_ld_wait32(va, vb);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = __uint_as_float(va[j]); x[16 + j] = __uint_as_float(vb[j]); }
+        if (pc + UM_PIECE < E.my_cols) {
+            tmem_ld_16x256b_x4(E.t_addr0 + pc + UM_PIECE, va);
+            tmem_ld_16x256b_x4(t_addr1 + pc + UM_PIECE, vb);
+        }
+        const int kk = E.chunk_col0 + lcol0 + pc;                      // next layer's k index of this lane's 8 values
+        // (kk % 32) >> 3 == tr; rows 32q + 16h + 8rr + tq share (row >> 1) & 3 == (tq >> 1) & 3
+        uint8_t* dst = a_dst + static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(E.q * 32 + E.tq, E.tr);
+        // x[16h + 4i + 2rr + cc] = (row 16h + 8rr + tq, lane value j = 2i + cc)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float hv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xv = x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)];
+                    if (KIND == EPI_ACT) {
+                        const float z = fmaf(xv, acc_scale, pp[j].x);
+                        const float e = ex2_approx(z * pp[j].y);       // exp(-alpha*z)
+                        const float sg = rcp_approx(1.f + e);          // inf -> 0, as numpy
+                        hv[j] = fmaf(pp[j].w, sg, pp[j].z) * z;
+                    } else {
+                        hv[j] = fmaf(xv, pp[j].x, pp[j].y);
+                    }
+                }
+                uint4 hi, lo;
+                split2(hv[0], hv[1], hi.x, lo.x);
+                split2(hv[2], hv[3], hi.y, lo.y);
+                split2(hv[4], hv[5], hi.z, lo.z);
+                split2(hv[6], hv[7], hi.w, lo.w);
+                // rows +16h +8rr: 64 B per row; a warp store covers 8 rows x 64 B = 4 full lines
+                st_global_v4_hint(dst + (2 * h + rr) * 512, hi, pol_keep);
+                st_global_v4_hint(dst + (2 * h + rr) * 512 + UM_A_HALF_BYTES, lo, pol_keep);
+            }
+    }
+}
+
+// output layers: de-standardise (+ 10**y) and store rows of the spectrum.
+template <bool TEN_TO>
+__device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, long long pitch, bool fast_rows,
+                                                 long long rows_left, int n_modes) {
+    uint32_t va[16], vb[16];
+    const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
+    tmem_ld_16x256b_x4(E.t_addr0, va);
+    tmem_ld_16x256b_x4(t_addr1, vb);
+    for (int pc = 0; pc < E.my_cols; pc += UM_PIECE) {
+        // output layers are packed so that lane value j is logical column 4tr + j (j < 4) or 16 + 4tr + (j - 4):
+        // each 16-byte store instruction then covers 64 contiguous bytes per row
+        const int ocol = E.colbase + pc + 4 * E.tr;
+        float2 pp[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 p0 = E.par[ocol + j], p1 = E.par[ocol + 16 + j];
+            // ten_to: 10**y = 2**(y*log2(10)); the factor is folded into .z/.w on the host
+            pp[j] = TEN_TO ? make_float2(p0.z, p0.w) : make_float2(p0.x, p0.y);
+            pp[4 + j] = TEN_TO ? make_float2(p1.z, p1.w) : make_float2(p1.x, p1.y);
+        }
+        float x[32];
+        tmem_ld_wait32(va, vb);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = __uint_as_float(va[j]); x[16 + j] = __uint_as_float(vb[j]); }
+        if (pc + UM_PIECE < E.my_cols) {
+            tmem_ld_16x256b_x4(E.t_addr0 + pc + UM_PIECE, va);
+            tmem_ld_16x256b_x4(t_addr1 + pc + UM_PIECE, vb);
+        }
+        const int gc = E.chunk_col0 + ocol;
+        const bool fast = fast_rows && gc + 20 <= n_modes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], pp[j].x, pp[j].y);
+                    y[j] = TEN_TO ? ex2_approx(v) : v;
+                }
+                const int rl = 16 * h + 8 * rr;
+                float* dst = orow0 + static_cast<long long>(rl) * pitch + gc;
+                if (fast) {
+                    __stcs(reinterpret_cast<float4*>(dst), make_float4(y[0], y[1], y[2], y[3]));
+                    __stcs(reinterpret_cast<float4*>(dst + 16), make_float4(y[4], y[5], y[6], y[7]));
+                } else if (E.q * 32 + E.tq + rl < rows_left) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (gc + j < n_modes) __stcs(dst + j, y[j]);
+                        if (gc + 16 + j < n_modes) __stcs(dst + 16 + j, y[4 + j]);
+                    }
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UM_THREADS, 1)
+__global__ void __cluster_dims__(UM_CLUSTER, 1, 1) __launch_bounds__(UM_THREADS, 1)
 fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -226,11 +470,17 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     auto bar_aready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 4 + t); };
     auto bar_a0ready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 6 + t); };
     auto bar_a0free = [&](int t) { return bars + 8u * (2 * UM_STAGES + 8 + t); };
+    auto bar_parfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + 10 + b); };
+    auto bar_parempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 12 + b); };
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbase + UM_SMEM_TMEMPTR);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_EPI_WARPS); }
+        // a stage is refilled only when every CTA of the cluster has consumed it (its weights are multicast)
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), UM_CLUSTER); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_EPI_WARPS);
+            mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS);
+        }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar_aready(t), UM_EPI_WARPS);
             mbar_init(bar_a0ready(t), 1);
@@ -245,8 +495,12 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     }
     tc_fence_before();
     __syncthreads();
+    if (UM_CLUSTER > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t cta_rank = UM_CLUSTER > 1 ? cluster_ctarank() : 0;
+    const long long pg_first = blockIdx.x / UM_CLUSTER, pg_step = gridDim.x / UM_CLUSTER;
+    constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << UM_CLUSTER) - 1);
 
     uint8_t* cta_scratch = P.scratch + static_cast<unsigned long long>(blockIdx.x) * P.scratch_cta_bytes;
     auto a0_buf = [&](int t) { return cta_scratch + static_cast<size_t>(t) * P.a0_bytes; };
@@ -260,8 +514,11 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         if (lane == 0) {
             long long w_empty = 0, w_aready = 0; const long long t_begin = clock64();
             int stage = 0; uint32_t ph_empty = 1;                 // fresh "empty" barriers pass at parity 1
-            uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0};
-            for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+            uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0}, ph_parempty[2] = {1, 1};
+            const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+            int job = 0;
+            for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
+            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
                 for (int g = 0; g < G; ++g) {
                     const UmmaGemm& L = P.g[g];
                     const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
@@ -274,15 +531,30 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             w_aready += mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1;
                             a_src = a_buf(t, g & 1);
                         }
-                        for (int c = 0; c < L.n_chunks; ++c) {
+                        for (int c = 0; c < L.n_chunks; ++c, ++job) {
+                            {   // this chunk's per-column epilogue constants -> shared memory (ring of 2 by job parity)
+                                const int pb = job & 1;
+                                w_empty += mbar_wait(bar_parempty(pb), ph_parempty[pb], P.error_flag, 104); ph_parempty[pb] ^= 1;
+                                mbar_arrive_expect_tx(bar_parfull(pb), L.nc * 16u);
+                                bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), L.epi + c * L.nc, L.nc * 16u, bar_parfull(pb));
+                            }
                             const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack)
                                                    + static_cast<size_t>(c) * L.k_stages * b_bytes;
                             for (int s = 0; s < L.k_stages; ++s) {
                                 w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
                                 const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
                                 mbar_arrive_expect_tx(bar_full(stage), UM_A_STAGE_BYTES + b_bytes);
-                                bulk_g2s(dst, a_src + static_cast<size_t>(s) * UM_A_STAGE_BYTES, UM_A_STAGE_BYTES, bar_full(stage));
-                                bulk_g2s(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes, b_bytes, bar_full(stage));
+                                // an activation tile is dead after its last chunk has streamed it
+                                bulk_g2s_hint(dst, a_src + static_cast<size_t>(s) * UM_A_STAGE_BYTES, UM_A_STAGE_BYTES, bar_full(stage),
+                                              c == L.n_chunks - 1 ? pol_stream : pol_keep);
+                                if (UM_CLUSTER > 1) {   // each CTA fetches 1/UM_CLUSTER of the weight stage and multicasts it
+                                    const uint32_t part = b_bytes / UM_CLUSTER;
+                                    bulk_g2s_multicast_hint(dst + UM_A_STAGE_BYTES + cta_rank * part,
+                                                            b_src + static_cast<size_t>(s) * b_bytes + cta_rank * part, part,
+                                                            bar_full(stage), kClusterMask, pol_keep);
+                                } else {
+                                    bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes, b_bytes, bar_full(stage), pol_keep);
+                                }
                                 if (++stage == UM_STAGES) { stage = 0; ph_empty ^= 1; }
                             }
                         }
@@ -302,7 +574,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             int stage = 0; uint32_t ph_full = 0;
             uint32_t ph_accempty[2] = {1, 1};
             int job = 0;
-            for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+            for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
+            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
                 for (int g = 0; g < G; ++g) {
                     const UmmaGemm& L = P.g[g];
                     const uint32_t idesc = umma_idesc(L.nc);
@@ -317,18 +590,20 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                                 w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
                                 tc_fence_after();
                                 const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
-                                const uint64_t a_hi = umma_desc(sa);
-                                const uint64_t a_lo = umma_desc(sa + UM_A_HALF_BYTES);
+                                const uint64_t a_hi = umma_desc_a(sa);
+                                const uint64_t a_lo = umma_desc_a(sa + UM_A_HALF_BYTES);
                                 const uint64_t b_hi = umma_desc(sa + UM_A_STAGE_BYTES);
                                 const uint64_t b_lo = umma_desc(sa + UM_A_STAGE_BYTES + b_half);
 #pragma unroll
                                 for (int kk = 0; kk < UM_KS / 16; ++kk) {
-                                    const uint64_t adv = static_cast<uint64_t>((kk * 256) >> 4);   // 2 core matrices along K
-                                    umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (s | kk) != 0);
-                                    umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-                                    umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                                    const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
+                                    const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
+                                    umma_f16(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
+                                    umma_f16(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                                    umma_f16(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                                 }
-                                umma_commit(bar_empty(stage));
+                                if (UM_CLUSTER > 1) umma_commit_multicast(bar_empty(stage), kClusterMask);
+                                else umma_commit(bar_empty(stage));
                                 if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                             }
                             umma_commit(bar_accfull(buf));
@@ -348,7 +623,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         uint32_t ph_a0free[2] = {1, 1};
         long long w_in = 0; const long long t_begin = clock64();
         const int np = P.n_parameters;
-        for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+        for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
+            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
             for (int t = 0; t < 2; ++t) {
                 w_in += mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
                 const long long row0 = (pair * 2 + t) * UM_TILE_M;
@@ -371,8 +647,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                         uint4 hi, lo;
                         split2(x[0], x[1], hi.x, lo.x); split2(x[2], x[3], hi.y, lo.y);
                         split2(x[4], x[5], hi.z, lo.z); split2(x[6], x[7], hi.w, lo.w);
-                        const size_t off = static_cast<size_t>(k0 / UM_KS) * UM_A_STAGE_BYTES
-                                           + (r >> 3) * 512 + ((k0 % UM_KS) >> 3) * 128 + (r & 7) * 16;
+                        const size_t off = static_cast<size_t>(k0 / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(r, (k0 % UM_KS) >> 3);
                         *reinterpret_cast<uint4*>(dst + off) = hi;
                         *reinterpret_cast<uint4*>(dst + off + UM_A_HALF_BYTES) = lo;
                     }
@@ -392,99 +667,54 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         const int ew = warp - UM_EPI_WARP0;          // 0..7
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int hf = ew >> 2;                      // which half of the chunk's columns
-        const int r = q * 32 + lane;                 // tile row owned by this thread
-        const int et = threadIdx.x - UM_EPI_WARP0 * 32;
-        float4* epipar = reinterpret_cast<float4*>(sbase + UM_SMEM_EPIPAR);
-        float* outstg = reinterpret_cast<float*>(sbase + UM_SMEM_OUTSTG) + ew * (32 * 16);
+        const float4* epipar = reinterpret_cast<const float4*>(sbase + UM_SMEM_EPIPAR);
+        const int tq = lane >> 2, tr = lane & 3;     // fragment coordinates: rows tq, tq+8 (+16 for the 2nd load); cols 2*tr, 2*tr+1
+        // 16-byte output stores need a 16-byte aligned base and a row pitch that is a multiple of 4 floats
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(P.out) & 15) | (static_cast<uintptr_t>(P.out_pitch) & 3)) == 0;
         uint32_t ph_accfull[2] = {0, 0};
         long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = clock64();
         int job = 0;
-        for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+        EpiCtx E;
+        E.q = q; E.tq = tq; E.tr = tr;
+        for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
+            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
             for (int g = 0; g < G; ++g) {
                 const UmmaGemm& L = P.g[g];
-                const int half_cols = L.nc >> 1;
+                // the chunk's columns are split between the two warps of a lane quarter in multiples of 32
+                const int cols0 = ((L.nc + 63) >> 6) << 5;
+                E.colbase = hf ? cols0 : 0;
+                E.my_cols = hf ? L.nc - cols0 : cols0;
                 for (int t = 0; t < 2; ++t) {
                     const long long row0 = (pair * 2 + t) * UM_TILE_M;
                     uint8_t* a_dst = a_buf(t, (g + 1) & 1);
+                    const bool rows_ok = row0 + UM_TILE_M <= P.n_rows;
+                    // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
+                    float* orow0 = P.out + (row0 + q * 32 + tq) * P.out_pitch;
                     for (int c = 0; c < L.n_chunks; ++c, ++job) {
                         const int buf = job & 1;
-                        // stage this chunk's per-column epilogue constants (double-buffered by job parity)
-                        float4* par = epipar + buf * UM_MAX_NC;
-                        if (et < L.nc) par[et] = L.epi[c * L.nc + et];
-                        asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_THREADS) : "memory");
+                        E.par = epipar + buf * UM_MAX_NC;                 // filled by the loader's bulk copy
+                        w_accfull += mbar_wait(bar_parfull(buf), ph_accfull[buf], P.error_flag, 402);
                         w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
                         tc_fence_after();
                         const long long t_job = clock64();
-                        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16)
-                                                + static_cast<uint32_t>(buf * UM_MAX_NC + hf * half_cols);
-                        for (int pc = 0; pc < half_cols; pc += UM_PIECE) {
-                            uint32_t v[16];
-                            tmem_ld16(t_addr + pc, v);
-                            tmem_ld_wait();
-                            const int ccol = hf * half_cols + pc;          // column within the chunk
-                            if (L.epi_kind == EPI_OUT) {
-                                // transpose 32 rows x 16 cols through shared memory, then row-contiguous stores
-                                float4* srow = reinterpret_cast<float4*>(outstg + lane * 16);
-                                const int sw = (lane >> 1) & 3;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    srow[j ^ sw] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                                __syncwarp();
-                                const int cl = lane & 15;
-                                const float4 pp = par[ccol + cl];
-                                const long long gcol = static_cast<long long>(c) * L.nc + ccol + cl;
-#pragma unroll 4
-                                for (int it = 0; it < 16; ++it) {
-                                    const int rl = 2 * it + (lane >> 4);
-                                    const float a = outstg[rl * 16 + (((cl >> 2) ^ ((rl >> 1) & 3)) << 2) + (cl & 3)];
-                                    float y = fmaf(a, pp.x, pp.y);
-                                    if (P.ten_to) y = ex2_approx(y * 3.3219280948873623f);
-                                    const long long grow = row0 + q * 32 + rl;
-                                    if (grow < P.n_rows && gcol < P.n_modes)
-                                        __stcs(P.out + grow * P.out_pitch + gcol, y);
-                                }
-                                __syncwarp();
-                            } else {
-                                float h[16];
-                                if (L.epi_kind == EPI_ACT) {
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        const float4 pp = par[ccol + j];
-                                        const float a = fmaf(__uint_as_float(v[j]), L.acc_scale, pp.x);
-                                        const float e = ex2_approx(a * pp.y);          // exp(-alpha*a)
-                                        const float s = rcp_approx(1.f + e);           // inf -> 0, as numpy
-                                        h[j] = fmaf(pp.w, s, pp.z) * a;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        const float4 pp = par[ccol + j];
-                                        h[j] = fmaf(__uint_as_float(v[j]), pp.x, pp.y);
-                                    }
-                                }
-                                const int k = c * L.nc + ccol;                         // next layer's k index
-#pragma unroll
-                                for (int u = 0; u < 2; ++u) {
-                                    uint4 hi, lo;
-                                    split2(h[8 * u + 0], h[8 * u + 1], hi.x, lo.x);
-                                    split2(h[8 * u + 2], h[8 * u + 3], hi.y, lo.y);
-                                    split2(h[8 * u + 4], h[8 * u + 5], hi.z, lo.z);
-                                    split2(h[8 * u + 6], h[8 * u + 7], hi.w, lo.w);
-                                    const int kk = k + 8 * u;
-                                    const size_t off = static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES
-                                                       + (r >> 3) * 512 + ((kk % UM_KS) >> 3) * 128 + (r & 7) * 16;
-                                    *reinterpret_cast<uint4*>(a_dst + off) = hi;
-                                    *reinterpret_cast<uint4*>(a_dst + off + UM_A_HALF_BYTES) = lo;
-                                }
-                            }
+                        E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16)
+                                    + static_cast<uint32_t>(buf * UM_MAX_NC + E.colbase);
+                        E.chunk_col0 = c * L.nc;
+                        if (E.my_cols > 0) {
+                            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, a_dst);
+                            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, a_dst);
+                            else if (P.ten_to) epi_chunk_output<true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                            else epi_chunk_output<false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
                         }
                         // accumulator drained: hand the TMEM buffer back to the MMA issuer
                         tc_fence_before();
-                        if (L.epi_kind != EPI_OUT) { __threadfence(); fence_proxy_async(); }
+                        // the next layer's loader may only read the scratch once every chunk of this layer is
+                        // written: one fence per thread before the last chunk's arrive covers all its stores
+                        if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
                         __syncwarp();
                         if (lane == 0) {
                             mbar_arrive(bar_accempty(buf));
+                            mbar_arrive(bar_parempty(buf));
                             if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
                         }
                         if (L.epi_kind == EPI_OUT) c_out += clock64() - t_job; else c_act += clock64() - t_job;
@@ -501,6 +731,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 
     tc_fence_before();
     __syncthreads();
+    if (UM_CLUSTER > 1) cluster_sync_all();      // no CTA leaves while a peer can still multicast into it / arrive on it
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }

@@ -22,7 +22,8 @@ def main():
     m = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
     eng = m.engine()
     x = torch.from_numpy(priors.sample_prior(m.parameters, rows, seed=1, dtype=np.float32)).cuda()
-    out = torch.empty((rows, m.n_modes), dtype=torch.float32, device="cuda")
+    pitch = (m.n_modes + 7) // 8 * 8
+    out = torch.empty((rows, pitch), dtype=torch.float32, device="cuda")[:, :m.n_modes]
     for _ in range(2):
         eng.forward_torch(x, out=out, ten_to=True)
     torch.cuda.synchronize()
