@@ -174,8 +174,9 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
     g.k_stages = k_pad / cpb::UM_KS;
     g.n_chunks = (g.N + cpb::UM_MAX_NC - 1) / cpb::UM_MAX_NC;
     g.nc = round_up((g.N + g.n_chunks - 1) / g.n_chunks, 32);
-    const size_t tile = static_cast<size_t>(g.nc) * cpb::UM_KS;            // elements per hi or lo tile
-    std::vector<__half> pack(static_cast<size_t>(g.n_chunks) * g.k_stages * 2 * tile, __float2half(0.f));
+    // per (chunk, stage): [CTA0: hi half | lo half][CTA1: hi half | lo half], a half = nc/2 columns
+    const size_t tile = static_cast<size_t>(g.nc / 2) * cpb::UM_KS;        // elements per hi or lo half tile
+    std::vector<__half> pack(static_cast<size_t>(g.n_chunks) * g.k_stages * 4 * tile, __float2half(0.f));
     for (int k = 0; k < g.K; ++k) {
         for (int n = 0; n < g.N; ++n) {
             const float w = g.W[static_cast<size_t>(k) * g.N + n] * s_w;
@@ -194,8 +195,9 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
             } else {
                 nn = (nl & ~31) | (((nb >> 1) & 3) << 3) | ((nb >> 3) << 1) | (nb & 1);
             }
-            const size_t base = (static_cast<size_t>(c) * g.k_stages + s) * 2 * tile;
-            const size_t off = static_cast<size_t>(nn / 8) * 256 + (kk / 8) * 64 + (nn % 8) * 8 + (kk % 8);
+            const int half = g.nc / 2, r = nn / half, nh = nn % half;          // which CTA of the pair holds this column
+            const size_t base = (static_cast<size_t>(c) * g.k_stages + s) * 4 * tile + static_cast<size_t>(r) * 2 * tile;
+            const size_t off = static_cast<size_t>(nh / 8) * 256 + (kk / 8) * 64 + (nh % 8) * 8 + (kk % 8);
             pack[base + off] = hi;
             pack[base + tile + off] = lo;
         }

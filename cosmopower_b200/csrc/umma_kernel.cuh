@@ -40,12 +40,12 @@ namespace cpb {
 constexpr int UM_TILE_M = 128;
 constexpr int UM_KS = 32;                                    // k elements per pipeline stage
 constexpr int UM_MAX_NC = 256;                               // widest N chunk (one accumulator)
-constexpr int UM_STAGES = 4;
-constexpr int UM_CLUSTER = 2;                                // CTAs per cluster sharing every weight stage by multicast
+constexpr int UM_STAGES = 6;
+constexpr int UM_CLUSTER = 2;                                // CTA pair: one tcgen05.mma.cta_group::2 (M = 256) drives both SMs
 constexpr int UM_A_HALF_BYTES = UM_TILE_M * UM_KS * 2;       // 8192: one of (hi, lo)
 constexpr int UM_A_STAGE_BYTES = 2 * UM_A_HALF_BYTES;        // 16384
-constexpr int UM_B_STAGE_BYTES_MAX = 2 * UM_MAX_NC * UM_KS * 2;   // 32768
-constexpr int UM_STAGE_BYTES = UM_A_STAGE_BYTES + UM_B_STAGE_BYTES_MAX;   // 49152
+constexpr int UM_B_STAGE_BYTES_MAX = 2 * (UM_MAX_NC / 2) * UM_KS * 2;   // 16384: each CTA of the pair holds half of the chunk's columns
+constexpr int UM_STAGE_BYTES = UM_A_STAGE_BYTES + UM_B_STAGE_BYTES_MAX;   // 32768
 constexpr int UM_MAX_GEMMS = 8;
 constexpr int UM_THREADS = 384;
 constexpr int UM_EPI_WARP0 = 4;
@@ -59,7 +59,7 @@ constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre
 constexpr int UM_SMEM_STAGES = 0;
 constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // 2 x 256 float4
 constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + 2 * UM_MAX_NC * 16;
-constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
+constexpr int UM_NUM_BARS = 3 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // + alignment slack
 
@@ -143,8 +143,10 @@ __device__ __noinline__ long long mbar_wait_slow(uint32_t bar, uint32_t parity, 
 }
 // returns the cycles spent blocked (0 on the fast path); callers may add it to a debug counter
 __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
-    if (mbar_try_wait(bar, parity)) return 0;
-    return mbar_wait_slow(bar, parity, error_flag, code);
+    const long long t0 = clock64();           // try_wait itself may suspend the thread: time the whole wait
+    if (mbar_try_wait(bar, parity)) return clock64() - t0;
+    mbar_wait_slow(bar, parity, error_flag, code);
+    return clock64() - t0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -201,6 +203,56 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 2-CTA MMA: D[256 x N] (128 rows in each CTA's TMEM) += A[256 x 16] (128 rows from each CTA's smem)
+// x B[N x 16] (N/2 rows from each CTA's smem).  Issued by one thread of the leader CTA only.
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive, once all MMAs issued so far have completed, on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in another CTA of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t target_cta) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(target_cta));
+    return raddr;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t target_cta) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(bar, target_cta)) : "memory");
+}
+// pure event signal (no data of this thread is published through it): no release fence on the issue path
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t raddr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// wait on a barrier that CTAs of the cluster arrive on remotely
+__device__ __noinline__ long long mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+    if (mbar_try_wait_cluster(bar, parity)) return 0;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > CPB_WATCHDOG_CYCLES) {
+            if (error_flag) atomicExch(error_flag, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+    return clock64() - t0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -294,9 +346,9 @@ __device__ __forceinline__ uint64_t umma_desc_a(uint32_t saddr) {
 __device__ __forceinline__ uint32_t a_tile_off(int r, int kchunk) {
     return static_cast<uint32_t>(r) * 64u + static_cast<uint32_t>((kchunk ^ (r >> 1)) & 3) * 16u;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=nc
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=256 across the CTA pair, N=nc
 __device__ __forceinline__ uint32_t umma_idesc(int nc) {
-    return (1u << 4) | (static_cast<uint32_t>(nc >> 3) << 17) | (static_cast<uint32_t>(UM_TILE_M >> 4) << 24);
+    return (1u << 4) | (static_cast<uint32_t>(nc >> 3) << 17) | (static_cast<uint32_t>((UM_CLUSTER * UM_TILE_M) >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -465,20 +517,20 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const uint32_t bars = base + UM_SMEM_BARS;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (UM_STAGES + s); };
-    auto bar_accfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + b); };
-    auto bar_accempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 2 + b); };
-    auto bar_aready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 4 + t); };
-    auto bar_a0ready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 6 + t); };
-    auto bar_a0free = [&](int t) { return bars + 8u * (2 * UM_STAGES + 8 + t); };
-    auto bar_parfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + 10 + b); };
-    auto bar_parempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 12 + b); };
+    auto bar_peerfull = [&](int s) { return bars + 8u * (2 * UM_STAGES + s); };   // leader only: the peer's stage has landed
+    auto bar_accfull = [&](int b) { return bars + 8u * (3 * UM_STAGES + b); };
+    auto bar_accempty = [&](int b) { return bars + 8u * (3 * UM_STAGES + 2 + b); }; // leader only: both CTAs' epilogues arrive
+    auto bar_aready = [&](int t) { return bars + 8u * (3 * UM_STAGES + 4 + t); };
+    auto bar_a0ready = [&](int t) { return bars + 8u * (3 * UM_STAGES + 6 + t); };
+    auto bar_a0free = [&](int t) { return bars + 8u * (3 * UM_STAGES + 8 + t); };
+    auto bar_parfull = [&](int b) { return bars + 8u * (3 * UM_STAGES + 10 + b); };
+    auto bar_parempty = [&](int b) { return bars + 8u * (3 * UM_STAGES + 12 + b); };
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbase + UM_SMEM_TMEMPTR);
 
     if (threadIdx.x == 0) {
-        // a stage is refilled only when every CTA of the cluster has consumed it (its weights are multicast)
-        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), UM_CLUSTER); }
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); mbar_init(bar_peerfull(s), 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_EPI_WARPS);
+            mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS);
             mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS);
         }
         for (int t = 0; t < 2; ++t) {
@@ -489,9 +541,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+        // pair-wide allocation: the same warp of both CTAs issues it; each CTA gets the same 512 columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -543,18 +596,13 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             for (int s = 0; s < L.k_stages; ++s) {
                                 w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
                                 const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
-                                mbar_arrive_expect_tx(bar_full(stage), UM_A_STAGE_BYTES + b_bytes);
+                                mbar_arrive_expect_tx(bar_full(stage), UM_A_STAGE_BYTES + b_bytes / 2);
                                 // an activation tile is dead after its last chunk has streamed it
                                 bulk_g2s_hint(dst, a_src + static_cast<size_t>(s) * UM_A_STAGE_BYTES, UM_A_STAGE_BYTES, bar_full(stage),
                                               c == L.n_chunks - 1 ? pol_stream : pol_keep);
-                                if (UM_CLUSTER > 1) {   // each CTA fetches 1/UM_CLUSTER of the weight stage and multicasts it
-                                    const uint32_t part = b_bytes / UM_CLUSTER;
-                                    bulk_g2s_multicast_hint(dst + UM_A_STAGE_BYTES + cta_rank * part,
-                                                            b_src + static_cast<size_t>(s) * b_bytes + cta_rank * part, part,
-                                                            bar_full(stage), kClusterMask, pol_keep);
-                                } else {
-                                    bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes, b_bytes, bar_full(stage), pol_keep);
-                                }
+                                // this CTA's half of the weight stage ([hi | lo] of its nc/2 columns)
+                                bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes + cta_rank * (b_bytes / 2),
+                                              b_bytes / 2, bar_full(stage), pol_keep);
                                 if (++stage == UM_STAGES) { stage = 0; ph_empty ^= 1; }
                             }
                         }
@@ -568,26 +616,41 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (leader CTA) / stage relay (peer CTA) =====================
+        if (lane == 0 && cta_rank != 0) {
+            // the peer's operands live in its own shared memory: tell the leader when each stage has landed
+            int stage = 0; uint32_t ph_full = 0;
+            const uint32_t peerfull0 = map_to_cta(bar_peerfull(0), 0);
+            for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step)
+                for (int g = 0; g < G; ++g) {
+                    const int n_stage_total = 2 * P.g[g].n_chunks * P.g[g].k_stages;
+                    for (int i = 0; i < n_stage_total; ++i) {
+                        mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
+                        mbar_arrive_remote_relaxed(peerfull0 + 8u * stage);
+                        if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
+                    }
+                }
+        } else if (lane == 0) {
             long long w_full = 0, w_accempty = 0; const long long t_begin = clock64();
             int stage = 0; uint32_t ph_full = 0;
             uint32_t ph_accempty[2] = {1, 1};
             int job = 0;
             for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
-            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
                 for (int g = 0; g < G; ++g) {
                     const UmmaGemm& L = P.g[g];
                     const uint32_t idesc = umma_idesc(L.nc);
-                    const uint32_t b_half = static_cast<uint32_t>(L.nc) * UM_KS * 2u;
+                    const uint32_t b_half = static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u;     // bytes of one (hi or lo) half tile
                     for (int t = 0; t < 2; ++t) {
                         for (int c = 0; c < L.n_chunks; ++c, ++job) {
                             const int buf = job & 1;
+                            // (a cluster-scope acquire would cost an L1 invalidate per wait on the issue path; the peer
+                            // only hands back TMEM it has finished reading - tcgen05.wait::ld precedes its arrive)
                             w_accempty += mbar_wait(bar_accempty(buf), ph_accempty[buf], P.error_flag, 201); ph_accempty[buf] ^= 1;
                             tc_fence_after();
                             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
                             for (int s = 0; s < L.k_stages; ++s) {
                                 w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
+                                w_accempty += mbar_wait(bar_peerfull(stage), ph_full, P.error_flag, 204);   // (counted with accempty: debug split)
                                 tc_fence_after();
                                 const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
                                 const uint64_t a_hi = umma_desc_a(sa);
@@ -598,17 +661,16 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                                 for (int kk = 0; kk < UM_KS / 16; ++kk) {
                                     const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
                                     const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
-                                    umma_f16(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
-                                    umma_f16(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
-                                    umma_f16(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                                    umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
+                                    umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                                    umma_f16_2cta(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                                 }
-                                if (UM_CLUSTER > 1) umma_commit_multicast(bar_empty(stage), kClusterMask);
-                                else umma_commit(bar_empty(stage));
+                                umma_commit_2cta(bar_empty(stage));           // frees the stage in both CTAs
                                 if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                             }
-                            umma_commit(bar_accfull(buf));
+                            umma_commit_2cta(bar_accfull(buf));               // both CTAs' epilogues may drain their 128 rows
                         }
-                        if (g == 0) umma_commit(bar_a0free(t));
+                        if (g == 0) umma_commit_2cta(bar_a0free(t));
                     }
                 }
             }
@@ -713,7 +775,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                         if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
                         __syncwarp();
                         if (lane == 0) {
-                            mbar_arrive(bar_accempty(buf));
+                            if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
+                            else mbar_arrive_remote(bar_accempty(buf), 0);
                             mbar_arrive(bar_parempty(buf));
                             if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
                         }
@@ -733,7 +796,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     __syncthreads();
     if (UM_CLUSTER > 1) cluster_sync_all();      // no CTA leaves while a peer can still multicast into it / arrive on it
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
