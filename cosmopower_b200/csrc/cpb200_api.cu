@@ -286,6 +286,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.a0_bytes = e->um_a0_bytes;
     p.abuf_bytes = e->um_abuf_bytes;
     p.error_flag = e->d_error_flag;
+    if (const char* dbg = getenv("CPB200_DEBUG_FLAGS")) p.debug_flags = atoi(dbg);   // timing ablations only
     p.counters = e->d_counters;
     const int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * cpb::UM_CLUSTER;

@@ -47,10 +47,11 @@ constexpr int UM_A_STAGE_BYTES = 2 * UM_A_HALF_BYTES;        // 16384
 constexpr int UM_B_STAGE_BYTES_MAX = 2 * (UM_MAX_NC / 2) * UM_KS * 2;   // 16384: each CTA of the pair holds half of the chunk's columns
 constexpr int UM_STAGE_BYTES = UM_A_STAGE_BYTES + UM_B_STAGE_BYTES_MAX;   // 32768
 constexpr int UM_MAX_GEMMS = 8;
-constexpr int UM_THREADS = 384;
+constexpr int UM_THREADS = 640;
 constexpr int UM_EPI_WARP0 = 4;
-constexpr int UM_EPI_WARPS = 8;
+constexpr int UM_EPI_WARPS = 16;
 constexpr int UM_EPI_THREADS = UM_EPI_WARPS * 32;
+constexpr bool UM_EPI_PREFETCH = false;                          // software-pipeline the TMEM reads (needs > 96 registers)
 constexpr int UM_PIECE = 32;                                 // accumulator columns per epilogue piece
 constexpr float UM_INPUT_SCALE = 1024.f;                     // power-of-two pre-scale of the standardised parameters
 constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre-scale of every produced activation
@@ -91,6 +92,7 @@ struct UmmaParams {
     unsigned long long scratch_cta_bytes;
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
     unsigned abuf_bytes;       // per tile per buffer: max k_stages(gemm >= 1) * 16384
+    int debug_flags;           // timing ablations only (results are wrong when set): 1 no MUFU, 2 no scratch stores, 4 no output stores, 8 no fence
     int* error_flag;           // set to a code by the watchdog before trapping
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
 };
@@ -99,7 +101,7 @@ struct UmmaParams {
 enum { UM_CNT_LOAD_WAIT_EMPTY = 0, UM_CNT_LOAD_WAIT_AREADY = 1, UM_CNT_LOAD_TOTAL = 2,
        UM_CNT_MMA_WAIT_FULL = 3, UM_CNT_MMA_WAIT_ACCEMPTY = 4, UM_CNT_MMA_TOTAL = 5,
        UM_CNT_EPI_WAIT_ACCFULL = 6, UM_CNT_EPI_ACT = 7, UM_CNT_EPI_OUT = 8, UM_CNT_EPI_TOTAL = 9,
-       UM_CNT_IN_WAIT = 10, UM_CNT_IN_TOTAL = 11, UM_CNT_SLOTS = 16 };
+       UM_CNT_IN_WAIT = 10, UM_CNT_IN_TOTAL = 11, UM_CNT_MMA_WAIT_PEERFULL = 12, UM_CNT_SLOTS = 16 };
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -317,7 +319,7 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
 // Ordering of the epilogue's plain stores to the L2-resident scratch before the loader's bulk
 // (async-proxy) reads of the same lines by the same CTA.
 #ifndef UM_SCRATCH_FENCE
-#define UM_SCRATCH_FENCE() __threadfence()
+#define UM_SCRATCH_FENCE() ((void)0)   /* fence.proxy.async alone orders them; validated by the 1M-row cross-check tests */
 #endif
 
 // K-major, no-swizzle shared-memory matrix descriptor: core matrices (8 rows x 16 B) are 128 B
@@ -380,8 +382,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // ---------------------------------------------------------------------------------------------
 struct EpiCtx {
     uint32_t t_addr0;        // TMEM address of this warp's first column, lanes +0
-    int my_cols;             // columns this warp handles (multiple of 32)
-    int colbase;             // first of them inside the chunk
+    int nc;                  // chunk width (multiple of 32)
+    int cw;                  // this warp takes the 32-column pieces cw, cw + UM_EPI_WARPS/4, ...
+    int dbg;
     int chunk_col0;          // c * nc
     int q, tq, tr;
     const float4* par;       // the chunk's per-column constants in shared memory (logical column order)
@@ -392,24 +395,31 @@ struct EpiCtx {
 template <int KIND>
 __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_scale, uint8_t* a_dst) {
     const uint64_t pol_keep = policy_evict_last();
-    uint32_t va[16], vb[16];
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
-    tmem_ld_16x256b_x4(E.t_addr0, va);                                 // software-pipelined TMEM reads
-    tmem_ld_16x256b_x4(t_addr1, vb);
     // accumulator column 8i+2tr+cc of a 32-column piece holds logical column 8tr+2i+cc (packing order),
     // so this lane owns 8 consecutive logical columns = one 16-byte row chunk of the next A tile
-    const int lcol0 = E.colbase + 8 * E.tr;
-    for (int pc = 0; pc < E.my_cols; pc += UM_PIECE) {
+    const int lcol0 = 8 * E.tr;
+    constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
+    uint32_t va[16], vb[16];
+    if (UM_EPI_PREFETCH && E.cw * UM_PIECE < E.nc) {                   // software-pipelined TMEM reads
+        tmem_ld_16x256b_x4(E.t_addr0 + E.cw * UM_PIECE, va);
+        tmem_ld_16x256b_x4(t_addr1 + E.cw * UM_PIECE, vb);
+    }
+    for (int pc = E.cw * UM_PIECE; pc < E.nc; pc += kStep) {
         float4 pp[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) pp[j] = E.par[lcol0 + pc + j];
+        if (!UM_EPI_PREFETCH) {
+            tmem_ld_16x256b_x4(E.t_addr0 + pc, va);
+            tmem_ld_16x256b_x4(t_addr1 + pc, vb);
+        }
         float x[32];
         tmem_ld_wait32(va, vb);
 #pragma unroll
         for (int j = 0; j < 16; ++j) { x[j] = __uint_as_float(va[j]); x[16 + j] = __uint_as_float(vb[j]); }
-        if (pc + UM_PIECE < E.my_cols) {
-            tmem_ld_16x256b_x4(E.t_addr0 + pc + UM_PIECE, va);
-            tmem_ld_16x256b_x4(t_addr1 + pc + UM_PIECE, vb);
+        if (UM_EPI_PREFETCH && pc + kStep < E.nc) {
+            tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
+            tmem_ld_16x256b_x4(t_addr1 + pc + kStep, vb);
         }
         const int kk = E.chunk_col0 + lcol0 + pc;                      // next layer's k index of this lane's 8 values
         // (kk % 32) >> 3 == tr; rows 32q + 16h + 8rr + tq share (row >> 1) & 3 == (tq >> 1) & 3
@@ -419,18 +429,22 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
+                // written stage by stage (all 8 values through each step) so that the MUFU latencies of the
+                // 8 independent chains overlap instead of being serialised value after value
                 float hv[8];
+                if (KIND == EPI_ACT) {
+                    float z[8], e[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float xv = x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)];
-                    if (KIND == EPI_ACT) {
-                        const float z = fmaf(xv, acc_scale, pp[j].x);
-                        const float e = ex2_approx(z * pp[j].y);       // exp(-alpha*z)
-                        const float sg = rcp_approx(1.f + e);          // inf -> 0, as numpy
-                        hv[j] = fmaf(pp[j].w, sg, pp[j].z) * z;
-                    } else {
-                        hv[j] = fmaf(xv, pp[j].x, pp[j].y);
-                    }
+                    for (int j = 0; j < 8; ++j) z[j] = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], acc_scale, pp[j].x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e[j] = ex2_approx(z[j] * pp[j].y);         // exp(-alpha*z)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e[j] = rcp_approx(1.f + e[j]);            // sigmoid; inf -> 0, as numpy
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) hv[j] = fmaf(pp[j].w, e[j], pp[j].z) * z[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) hv[j] = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], pp[j].x, pp[j].y);
                 }
                 uint4 hi, lo;
                 split2(hv[0], hv[1], hi.x, lo.x);
@@ -448,14 +462,17 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
 template <bool TEN_TO>
 __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, long long pitch, bool fast_rows,
                                                  long long rows_left, int n_modes) {
-    uint32_t va[16], vb[16];
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
-    tmem_ld_16x256b_x4(E.t_addr0, va);
-    tmem_ld_16x256b_x4(t_addr1, vb);
-    for (int pc = 0; pc < E.my_cols; pc += UM_PIECE) {
+    constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
+    uint32_t va[16], vb[16];
+    if (UM_EPI_PREFETCH && E.cw * UM_PIECE < E.nc) {                   // software-pipelined TMEM reads
+        tmem_ld_16x256b_x4(E.t_addr0 + E.cw * UM_PIECE, va);
+        tmem_ld_16x256b_x4(t_addr1 + E.cw * UM_PIECE, vb);
+    }
+    for (int pc = E.cw * UM_PIECE; pc < E.nc; pc += kStep) {
         // output layers are packed so that lane value j is logical column 4tr + j (j < 4) or 16 + 4tr + (j - 4):
         // each 16-byte store instruction then covers 64 contiguous bytes per row
-        const int ocol = E.colbase + pc + 4 * E.tr;
+        const int ocol = pc + 4 * E.tr;
         float2 pp[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -464,13 +481,17 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
             pp[j] = TEN_TO ? make_float2(p0.z, p0.w) : make_float2(p0.x, p0.y);
             pp[4 + j] = TEN_TO ? make_float2(p1.z, p1.w) : make_float2(p1.x, p1.y);
         }
+        if (!UM_EPI_PREFETCH) {
+            tmem_ld_16x256b_x4(E.t_addr0 + pc, va);
+            tmem_ld_16x256b_x4(t_addr1 + pc, vb);
+        }
         float x[32];
         tmem_ld_wait32(va, vb);
 #pragma unroll
         for (int j = 0; j < 16; ++j) { x[j] = __uint_as_float(va[j]); x[16 + j] = __uint_as_float(vb[j]); }
-        if (pc + UM_PIECE < E.my_cols) {
-            tmem_ld_16x256b_x4(E.t_addr0 + pc + UM_PIECE, va);
-            tmem_ld_16x256b_x4(t_addr1 + pc + UM_PIECE, vb);
+        if (UM_EPI_PREFETCH && pc + kStep < E.nc) {
+            tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
+            tmem_ld_16x256b_x4(t_addr1 + pc + kStep, vb);
         }
         const int gc = E.chunk_col0 + ocol;
         const bool fast = fast_rows && gc + 20 <= n_modes;
@@ -631,7 +652,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     }
                 }
         } else if (lane == 0) {
-            long long w_full = 0, w_accempty = 0; const long long t_begin = clock64();
+            long long w_full = 0, w_accempty = 0, w_peer = 0; const long long t_begin = clock64();
             int stage = 0; uint32_t ph_full = 0;
             uint32_t ph_accempty[2] = {1, 1};
             int job = 0;
@@ -650,7 +671,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
                             for (int s = 0; s < L.k_stages; ++s) {
                                 w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
-                                w_accempty += mbar_wait(bar_peerfull(stage), ph_full, P.error_flag, 204);   // (counted with accempty: debug split)
+                                w_peer += mbar_wait(bar_peerfull(stage), ph_full, P.error_flag, 204);
                                 tc_fence_after();
                                 const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
                                 const uint64_t a_hi = umma_desc_a(sa);
@@ -676,7 +697,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             }
             if (P.counters) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
-                cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty;
+                cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty; cnt[UM_CNT_MMA_WAIT_PEERFULL] = w_peer;
                 cnt[UM_CNT_MMA_TOTAL] = clock64() - t_begin;
             }
         }
@@ -728,7 +749,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         // ===================== epilogue warps =====================
         const int ew = warp - UM_EPI_WARP0;          // 0..7
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
-        const int hf = ew >> 2;                      // which half of the chunk's columns
+        const int cw = ew >> 2;                      // which of the lane quarter's warps: takes every (UM_EPI_WARPS/4)-th 32-column piece
         const float4* epipar = reinterpret_cast<const float4*>(sbase + UM_SMEM_EPIPAR);
         const int tq = lane >> 2, tr = lane & 3;     // fragment coordinates: rows tq, tq+8 (+16 for the 2nd load); cols 2*tr, 2*tr+1
         // 16-byte output stores need a 16-byte aligned base and a row pitch that is a multiple of 4 floats
@@ -737,15 +758,13 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = clock64();
         int job = 0;
         EpiCtx E;
-        E.q = q; E.tq = tq; E.tr = tr;
+        E.q = q; E.tq = tq; E.tr = tr; E.cw = cw; E.dbg = P.debug_flags;
+        const uint32_t accempty_leader0 = map_to_cta(bar_accempty(0), 0);
         for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
             const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
             for (int g = 0; g < G; ++g) {
                 const UmmaGemm& L = P.g[g];
-                // the chunk's columns are split between the two warps of a lane quarter in multiples of 32
-                const int cols0 = ((L.nc + 63) >> 6) << 5;
-                E.colbase = hf ? cols0 : 0;
-                E.my_cols = hf ? L.nc - cols0 : cols0;
+                E.nc = L.nc;
                 for (int t = 0; t < 2; ++t) {
                     const long long row0 = (pair * 2 + t) * UM_TILE_M;
                     uint8_t* a_dst = a_buf(t, (g + 1) & 1);
@@ -759,10 +778,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                         w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
                         tc_fence_after();
                         const long long t_job = clock64();
-                        E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16)
-                                    + static_cast<uint32_t>(buf * UM_MAX_NC + E.colbase);
+                        E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * UM_MAX_NC);
                         E.chunk_col0 = c * L.nc;
-                        if (E.my_cols > 0) {
+                        {
                             if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, a_dst);
                             else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, a_dst);
                             else if (P.ten_to) epi_chunk_output<true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
@@ -772,11 +790,11 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                         tc_fence_before();
                         // the next layer's loader may only read the scratch once every chunk of this layer is
                         // written: one fence per thread before the last chunk's arrive covers all its stores
-                        if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
+                        if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1 && !(P.debug_flags & 8)) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
                         __syncwarp();
                         if (lane == 0) {
                             if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
-                            else mbar_arrive_remote(bar_accempty(buf), 0);
+                            else mbar_arrive_remote_relaxed(accempty_leader0 + 8u * buf);   // TMEM reads are complete (wait::ld)
                             mbar_arrive(bar_parempty(buf));
                             if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
                         }
