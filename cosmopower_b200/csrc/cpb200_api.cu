@@ -168,7 +168,11 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
     ex = std::max(-10, std::min(14, ex));
     const float s_w = std::ldexp(1.f, ex);
     if (wmax * s_w > 60000.f) return fail(CPB200_E_RANGE, "weight %g outside the fp16 split range", static_cast<double>(wmax));
-    const float inv = 1.f / (s_w * s_in);
+    // The tensor core truncates (does not round) the fp32 accumulator after each of the 3*K/16 MMA steps,
+    // which shrinks |acc| by about half an ulp per step; (1 + bias_ulps * 2^-24) undoes the mean of that.
+    float bias_ulps = cpb::UM_TRUNC_BIAS_ULPS_PER_STEP * 3.f * static_cast<float>(k_pad / 16);
+    if (const char* envb = getenv("CPB200_BIAS_ULPS_PER_STEP")) bias_ulps = static_cast<float>(atof(envb)) * 3.f * static_cast<float>(k_pad / 16);
+    const float inv = (1.f / (s_w * s_in)) * (1.f + bias_ulps * 5.9604645e-8f);
     g.acc_scale = inv;
     g.k_pad = k_pad;
     g.k_stages = k_pad / cpb::UM_KS;

@@ -54,6 +54,7 @@ constexpr int UM_EPI_THREADS = UM_EPI_WARPS * 32;
 constexpr bool UM_EPI_PREFETCH = false;                          // software-pipeline the TMEM reads (needs > 96 registers)
 constexpr int UM_PIECE = 32;                                 // accumulator columns per epilogue piece
 constexpr float UM_INPUT_SCALE = 1024.f;                     // power-of-two pre-scale of the standardised parameters
+constexpr float UM_TRUNC_BIAS_ULPS_PER_STEP = 0.16f;               // mean accumulator loss per MMA step, in ulps (calibrated on B200)
 constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre-scale of every produced activation
 
 // shared memory carve-up (bytes from the 1024-aligned base)
