@@ -79,6 +79,8 @@ struct cpb200_engine {
     unsigned long long um_scratch_cta = 0;
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
     int* d_error_flag = nullptr;
+    unsigned* d_jobs = nullptr;         // job table of the fused kernel (build_jobs)
+    int n_jobs = 0, n_bufs = 2, l0_out_buf = 1;
     long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
     // host pipeline
     cudaStream_t hstream[2] = {nullptr, nullptr};
@@ -227,6 +229,29 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
     return 0;
 }
 
+// Job sequence of one iteration of the fused kernel: all chunks of contractions 1..G-1 for the
+// current pair of tiles, with the NEXT pair's layer-0 chunks merged into the last contraction's
+// (output) phase, so that their epilogues overlap MMAs that do not depend on them.
+std::vector<unsigned> build_jobs(const std::vector<Gemm>& gemms) {
+    const int G = static_cast<int>(gemms.size());
+    std::vector<unsigned> cur_head, cur_out, next0, jobs;
+    auto enc = [](int g, int t, int c, int next) { return static_cast<unsigned>(g | (t << 8) | (c << 16) | (next << 24)); };
+    for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < gemms[0].n_chunks; ++c) next0.push_back(enc(0, t, c, 1));
+    if (G == 1) return next0;       // a single contraction: nothing to overlap (its chunks are both layer 0 and output)
+    for (int g = 1; g < G; ++g)
+        for (int t = 0; t < 2; ++t)
+            for (int c = 0; c < gemms[g].n_chunks; ++c) (g == G - 1 ? cur_out : cur_head).push_back(enc(g, t, c, 0));
+    jobs = cur_head;
+    size_t k = 0;
+    for (size_t i = 0; i < cur_out.size(); ++i) {
+        jobs.push_back(cur_out[i]);
+        while (k < next0.size() && (k + 1) * cur_out.size() <= (i + 1) * (next0.size() + 1)) jobs.push_back(next0[k++]);
+    }
+    while (k < next0.size()) jobs.push_back(next0[k++]);
+    return jobs;
+}
+
 int launch_simt(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
                 cudaStream_t st) {
     const int G = static_cast<int>(e->gemms.size());
@@ -289,6 +314,10 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.scratch_cta_bytes = e->um_scratch_cta;
     p.a0_bytes = e->um_a0_bytes;
     p.abuf_bytes = e->um_abuf_bytes;
+    p.n_bufs = e->n_bufs;
+    p.l0_out_buf = e->l0_out_buf;
+    p.jobs = e->d_jobs;
+    p.n_jobs = e->n_jobs;
     p.error_flag = e->d_error_flag;
     if (const char* dbg = getenv("CPB200_DEBUG_FLAGS")) p.debug_flags = atoi(dbg);   // timing ablations only
     p.counters = e->d_counters;
@@ -398,7 +427,20 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
         }
         e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
         e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
-        e->um_scratch_cta = 2ull * e->um_a0_bytes + 4ull * e->um_abuf_bytes;
+        // layer 0 of the next pair is written while the current pair's last contraction still streams its
+        // operand: with an even number of contractions that is the buffer contraction 1 would read, so a
+        // third buffer takes the layer-0 output
+        const int G = static_cast<int>(e->gemms.size());
+        e->n_bufs = (G % 2 == 0 && G > 1) ? 3 : 2;
+        e->l0_out_buf = e->n_bufs == 3 ? 2 : 1;
+        e->um_scratch_cta = 2ull * e->um_a0_bytes + 2ull * e->n_bufs * e->um_abuf_bytes;
+        {
+            std::vector<unsigned> jobs = build_jobs(e->gemms);
+            if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
+                return bail(fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
+            e->n_jobs = static_cast<int>(jobs.size());
+            if ((rc = upload(&e->d_jobs, jobs.data(), jobs.size()))) return bail(rc);
+        }
         const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
         if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
             return bail(fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -430,7 +472,7 @@ int cpb200_destroy(cpb200_engine* e) {
     }
     cudaFree(e->d_pmean); cudaFree(e->d_pstd);
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
-    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters);
+    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters); cudaFree(e->d_jobs);
     for (int i = 0; i < 2; ++i) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);

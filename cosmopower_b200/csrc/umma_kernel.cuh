@@ -63,7 +63,9 @@ constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // 
 constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + 2 * UM_MAX_NC * 16;
 constexpr int UM_NUM_BARS = 3 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
-constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // + alignment slack
+constexpr int UM_MAX_JOBS = 96;
+constexpr int UM_SMEM_JOBS = UM_SMEM_TMEMPTR + 16;
+constexpr int UM_SMEM_BYTES = UM_SMEM_JOBS + UM_MAX_JOBS * 4 + 1024;         // + alignment slack
 
 struct UmmaGemm {
     const __half* wpack;   // [n_chunks][k_stages][hi|lo][nc x 32] core-matrix tiles
@@ -93,6 +95,10 @@ struct UmmaParams {
     unsigned long long scratch_cta_bytes;
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
     unsigned abuf_bytes;       // per tile per buffer: max k_stages(gemm >= 1) * 16384
+    int n_bufs;                // activation buffers per tile: 2, or 3 when the number of contractions is even
+    int l0_out_buf;            // buffer layer 0 writes (read by contraction 1): 1, or 2 when n_bufs == 3
+    const unsigned* jobs;      // job table: g | t << 8 | c << 16 | next << 24 (see cpb200_api.cu build_jobs)
+    int n_jobs;
     int debug_flags;           // timing ablations only (results are wrong when set): 1 no MUFU, 2 no scratch stores, 4 no output stores, 8 no fence
     int* error_flag;           // set to a code by the watchdog before trapping
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
@@ -562,6 +568,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < P.n_jobs) reinterpret_cast<uint32_t*>(sbase + UM_SMEM_JOBS)[threadIdx.x] = P.jobs[threadIdx.x];
     if (warp == 2) {
         // pair-wide allocation: the same warp of both CTAs issues it; each CTA gets the same 512 columns
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -575,14 +582,37 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t cta_rank = UM_CLUSTER > 1 ? cluster_ctarank() : 0;
     const long long pg_first = blockIdx.x / UM_CLUSTER, pg_step = gridDim.x / UM_CLUSTER;
-    constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << UM_CLUSTER) - 1);
+    // pair-groups this cluster walks; iteration `it` runs the table's "cur" jobs (contractions >= 1) for
+    // pair-group it-1 and its "next" jobs (layer 0) for pair-group it, so a pair's layer-0 epilogues hide
+    // behind the previous pair's output phase instead of stalling the tensor pipe at every pair start
+    const long long n_my_pg = P.n_pairgroups > pg_first ? (P.n_pairgroups - pg_first + pg_step - 1) / pg_step : 0;
+    const uint32_t* jobtab = reinterpret_cast<const uint32_t*>(sbase + UM_SMEM_JOBS);
+    const int n_jobs = P.n_jobs;
 
     uint8_t* cta_scratch = P.scratch + static_cast<unsigned long long>(blockIdx.x) * P.scratch_cta_bytes;
     auto a0_buf = [&](int t) { return cta_scratch + static_cast<size_t>(t) * P.a0_bytes; };
     auto a_buf = [&](int t, int b) {
-        return cta_scratch + 2ull * P.a0_bytes + (static_cast<size_t>(t) * 2 + b) * P.abuf_bytes;
+        return cta_scratch + 2ull * P.a0_bytes + (static_cast<size_t>(t) * P.n_bufs + b) * P.abuf_bytes;
     };
+    // activation buffer read by contraction g (g >= 1) = written by contraction g-1
+    auto in_buf = [&](int g, int t) { return a_buf(t, g == 1 ? P.l0_out_buf : (g & 1)); };
     const int G = P.n_gemms;
+
+// every role walks the same job sequence
+#define UM_FOR_EACH_JOB(BODY)                                                                          \
+    for (long long it = 0; it <= n_my_pg; ++it) {                                                      \
+        const bool has_cur = it >= 1, has_next = it < n_my_pg;                                         \
+        for (int ji = 0; ji < n_jobs; ++ji) {                                                          \
+            const uint32_t jw = jobtab[ji];                                                            \
+            const int g = jw & 0xff, t = (jw >> 8) & 0xff, c = (jw >> 16) & 0xff;                      \
+            const bool is_next = (jw >> 24) != 0;                                                      \
+            if (is_next ? !has_next : !has_cur) continue;                                              \
+            /* rows beyond n_rows are padding (computed, never stored) */                              \
+            const long long pair = (pg_first + (is_next ? it : it - 1) * pg_step) * UM_CLUSTER + cta_rank; \
+            (void)pair; (void)c;                                                                       \
+            BODY                                                                                       \
+        }                                                                                              \
+    }
 
     if (warp == 0) {
         // ===================== loader: bulk copies into the stage ring =====================
@@ -592,45 +622,35 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0}, ph_parempty[2] = {1, 1};
             const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
             int job = 0;
-            for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
-            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
-                for (int g = 0; g < G; ++g) {
-                    const UmmaGemm& L = P.g[g];
-                    const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
-                    for (int t = 0; t < 2; ++t) {
-                        const uint8_t* a_src;
-                        if (g == 0) {
-                            w_aready += mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1;
-                            a_src = a0_buf(t);
-                        } else {
-                            w_aready += mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1;
-                            a_src = a_buf(t, g & 1);
-                        }
-                        for (int c = 0; c < L.n_chunks; ++c, ++job) {
-                            {   // this chunk's per-column epilogue constants -> shared memory (ring of 2 by job parity)
-                                const int pb = job & 1;
-                                w_empty += mbar_wait(bar_parempty(pb), ph_parempty[pb], P.error_flag, 104); ph_parempty[pb] ^= 1;
-                                mbar_arrive_expect_tx(bar_parfull(pb), L.nc * 16u);
-                                bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), L.epi + c * L.nc, L.nc * 16u, bar_parfull(pb));
-                            }
-                            const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack)
-                                                   + static_cast<size_t>(c) * L.k_stages * b_bytes;
-                            for (int s = 0; s < L.k_stages; ++s) {
-                                w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
-                                const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
-                                mbar_arrive_expect_tx(bar_full(stage), UM_A_STAGE_BYTES + b_bytes / 2);
-                                // an activation tile is dead after its last chunk has streamed it
-                                bulk_g2s_hint(dst, a_src + static_cast<size_t>(s) * UM_A_STAGE_BYTES, UM_A_STAGE_BYTES, bar_full(stage),
-                                              c == L.n_chunks - 1 ? pol_stream : pol_keep);
-                                // this CTA's half of the weight stage ([hi | lo] of its nc/2 columns)
-                                bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes + cta_rank * (b_bytes / 2),
-                                              b_bytes / 2, bar_full(stage), pol_keep);
-                                if (++stage == UM_STAGES) { stage = 0; ph_empty ^= 1; }
-                            }
-                        }
-                    }
+            UM_FOR_EACH_JOB({
+                const UmmaGemm& L = P.g[g];
+                const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
+                if (c == 0) {                                     // the whole K extent of this tile's operand must be written
+                    if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1; }
+                    else { w_aready += mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1; }
                 }
-            }
+                const uint8_t* a_src = g == 0 ? a0_buf(t) : in_buf(g, t);
+                {   // this chunk's per-column epilogue constants -> shared memory (ring of 2 by job parity)
+                    const int pb = job & 1;
+                    w_empty += mbar_wait(bar_parempty(pb), ph_parempty[pb], P.error_flag, 104); ph_parempty[pb] ^= 1;
+                    mbar_arrive_expect_tx(bar_parfull(pb), L.nc * 16u);
+                    bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), L.epi + c * L.nc, L.nc * 16u, bar_parfull(pb));
+                }
+                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack) + static_cast<size_t>(c) * L.k_stages * b_bytes;
+                for (int s = 0; s < L.k_stages; ++s) {
+                    w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
+                    const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
+                    mbar_arrive_expect_tx(bar_full(stage), UM_A_STAGE_BYTES + b_bytes / 2);
+                    // an activation tile is dead after its last chunk has streamed it
+                    bulk_g2s_hint(dst, a_src + static_cast<size_t>(s) * UM_A_STAGE_BYTES, UM_A_STAGE_BYTES, bar_full(stage),
+                                  c == L.n_chunks - 1 ? pol_stream : pol_keep);
+                    // this CTA's half of the weight stage ([hi | lo] of its nc/2 columns)
+                    bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes + cta_rank * (b_bytes / 2),
+                                  b_bytes / 2, bar_full(stage), pol_keep);
+                    if (++stage == UM_STAGES) { stage = 0; ph_empty ^= 1; }
+                }
+                ++job;
+            })
             if (P.counters) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
                 cnt[UM_CNT_LOAD_WAIT_EMPTY] = w_empty; cnt[UM_CNT_LOAD_WAIT_AREADY] = w_aready;
@@ -643,59 +663,54 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             // the peer's operands live in its own shared memory: tell the leader when each stage has landed
             int stage = 0; uint32_t ph_full = 0;
             const uint32_t peerfull0 = map_to_cta(bar_peerfull(0), 0);
-            for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step)
-                for (int g = 0; g < G; ++g) {
-                    const int n_stage_total = 2 * P.g[g].n_chunks * P.g[g].k_stages;
-                    for (int i = 0; i < n_stage_total; ++i) {
-                        mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
-                        mbar_arrive_remote_relaxed(peerfull0 + 8u * stage);
-                        if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
-                    }
+            UM_FOR_EACH_JOB({
+                (void)t;
+                const int ks = P.g[g].k_stages;
+                for (int i = 0; i < ks; ++i) {
+                    mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
+                    mbar_arrive_remote_relaxed(peerfull0 + 8u * stage);
+                    if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                 }
+            })
         } else if (lane == 0) {
             long long w_full = 0, w_accempty = 0, w_peer = 0; const long long t_begin = clock64();
             int stage = 0; uint32_t ph_full = 0;
             uint32_t ph_accempty[2] = {1, 1};
             int job = 0;
-            for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
-                for (int g = 0; g < G; ++g) {
-                    const UmmaGemm& L = P.g[g];
-                    const uint32_t idesc = umma_idesc(L.nc);
-                    const uint32_t b_half = static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u;     // bytes of one (hi or lo) half tile
-                    for (int t = 0; t < 2; ++t) {
-                        for (int c = 0; c < L.n_chunks; ++c, ++job) {
-                            const int buf = job & 1;
-                            // (a cluster-scope acquire would cost an L1 invalidate per wait on the issue path; the peer
-                            // only hands back TMEM it has finished reading - tcgen05.wait::ld precedes its arrive)
-                            w_accempty += mbar_wait(bar_accempty(buf), ph_accempty[buf], P.error_flag, 201); ph_accempty[buf] ^= 1;
-                            tc_fence_after();
-                            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
-                            for (int s = 0; s < L.k_stages; ++s) {
-                                w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
-                                w_peer += mbar_wait(bar_peerfull(stage), ph_full, P.error_flag, 204);
-                                tc_fence_after();
-                                const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
-                                const uint64_t a_hi = umma_desc_a(sa);
-                                const uint64_t a_lo = umma_desc_a(sa + UM_A_HALF_BYTES);
-                                const uint64_t b_hi = umma_desc(sa + UM_A_STAGE_BYTES);
-                                const uint64_t b_lo = umma_desc(sa + UM_A_STAGE_BYTES + b_half);
+            UM_FOR_EACH_JOB({
+                const UmmaGemm& L = P.g[g];
+                const uint32_t idesc = umma_idesc(L.nc);
+                const uint32_t b_half = static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u;     // bytes of one (hi or lo) half tile
+                const int buf = job & 1;
+                // (a cluster-scope acquire would cost an L1 invalidate per wait on the issue path; the peer
+                // only hands back TMEM it has finished reading - tcgen05.wait::ld precedes its arrive)
+                w_accempty += mbar_wait(bar_accempty(buf), ph_accempty[buf], P.error_flag, 201); ph_accempty[buf] ^= 1;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
+                for (int s = 0; s < L.k_stages; ++s) {
+                    w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
+                    w_peer += mbar_wait(bar_peerfull(stage), ph_full, P.error_flag, 204);
+                    tc_fence_after();
+                    const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc_a(sa);
+                    const uint64_t a_lo = umma_desc_a(sa + UM_A_HALF_BYTES);
+                    const uint64_t b_hi = umma_desc(sa + UM_A_STAGE_BYTES);
+                    const uint64_t b_lo = umma_desc(sa + UM_A_STAGE_BYTES + b_half);
 #pragma unroll
-                                for (int kk = 0; kk < UM_KS / 16; ++kk) {
-                                    const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
-                                    const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
-                                    umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
-                                    umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
-                                    umma_f16_2cta(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
-                                }
-                                umma_commit_2cta(bar_empty(stage));           // frees the stage in both CTAs
-                                if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
-                            }
-                            umma_commit_2cta(bar_accfull(buf));               // both CTAs' epilogues may drain their 128 rows
-                        }
-                        if (g == 0) umma_commit_2cta(bar_a0free(t));
+                    for (int kk = 0; kk < UM_KS / 16; ++kk) {
+                        const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
+                        const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
+                        umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
+                        umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                        umma_f16_2cta(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                     }
+                    umma_commit_2cta(bar_empty(stage));           // frees the stage in both CTAs
+                    if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                 }
-            }
+                umma_commit_2cta(bar_accfull(buf));               // both CTAs' epilogues may drain their 128 rows
+                if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
+                ++job;
+            })
             if (P.counters) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
                 cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty; cnt[UM_CNT_MMA_WAIT_PEERFULL] = w_peer;
@@ -707,8 +722,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         uint32_t ph_a0free[2] = {1, 1};
         long long w_in = 0; const long long t_begin = clock64();
         const int np = P.n_parameters;
-        for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
-            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
+        for (long long pgi = 0; pgi < n_my_pg; ++pgi) {
+            const long long pair = (pg_first + pgi * pg_step) * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding
             for (int t = 0; t < 2; ++t) {
                 w_in += mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
                 const long long row0 = (pair * 2 + t) * UM_TILE_M;
@@ -748,7 +763,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
     } else if (warp >= UM_EPI_WARP0) {
         // ===================== epilogue warps =====================
-        const int ew = warp - UM_EPI_WARP0;          // 0..7
+        const int ew = warp - UM_EPI_WARP0;          // 0..15
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int cw = ew >> 2;                      // which of the lane quarter's warps: takes every (UM_EPI_WARPS/4)-th 32-column piece
         const float4* epipar = reinterpret_cast<const float4*>(sbase + UM_SMEM_EPIPAR);
@@ -761,55 +776,49 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         EpiCtx E;
         E.q = q; E.tq = tq; E.tr = tr; E.cw = cw; E.dbg = P.debug_flags;
         const uint32_t accempty_leader0 = map_to_cta(bar_accempty(0), 0);
-        for (long long pg = pg_first; pg < P.n_pairgroups; pg += pg_step) {
-            const long long pair = pg * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding (computed, never stored)
-            for (int g = 0; g < G; ++g) {
-                const UmmaGemm& L = P.g[g];
-                E.nc = L.nc;
-                for (int t = 0; t < 2; ++t) {
-                    const long long row0 = (pair * 2 + t) * UM_TILE_M;
-                    uint8_t* a_dst = a_buf(t, (g + 1) & 1);
-                    const bool rows_ok = row0 + UM_TILE_M <= P.n_rows;
-                    // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
-                    float* orow0 = P.out + (row0 + q * 32 + tq) * P.out_pitch;
-                    for (int c = 0; c < L.n_chunks; ++c, ++job) {
-                        const int buf = job & 1;
-                        E.par = epipar + buf * UM_MAX_NC;                 // filled by the loader's bulk copy
-                        w_accfull += mbar_wait(bar_parfull(buf), ph_accfull[buf], P.error_flag, 402);
-                        w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
-                        tc_fence_after();
-                        const long long t_job = clock64();
-                        E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * UM_MAX_NC);
-                        E.chunk_col0 = c * L.nc;
-                        {
-                            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, a_dst);
-                            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, a_dst);
-                            else if (P.ten_to) epi_chunk_output<true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
-                            else epi_chunk_output<false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
-                        }
-                        // accumulator drained: hand the TMEM buffer back to the MMA issuer
-                        tc_fence_before();
-                        // the next layer's loader may only read the scratch once every chunk of this layer is
-                        // written: one fence per thread before the last chunk's arrive covers all its stores
-                        if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1 && !(P.debug_flags & 8)) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
-                            else mbar_arrive_remote_relaxed(accempty_leader0 + 8u * buf);   // TMEM reads are complete (wait::ld)
-                            mbar_arrive(bar_parempty(buf));
-                            if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
-                        }
-                        if (L.epi_kind == EPI_OUT) c_out += clock64() - t_job; else c_act += clock64() - t_job;
-                    }
-                }
+        UM_FOR_EACH_JOB({
+            const UmmaGemm& L = P.g[g];
+            E.nc = L.nc;
+            const long long row0 = (pair * 2 + t) * UM_TILE_M;
+            const int buf = job & 1;
+            E.par = epipar + buf * UM_MAX_NC;                 // filled by the loader's bulk copy
+            w_accfull += mbar_wait(bar_parfull(buf), ph_accfull[buf], P.error_flag, 402);
+            w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
+            tc_fence_after();
+            const long long t_job = clock64();
+            E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * UM_MAX_NC);
+            E.chunk_col0 = c * L.nc;
+            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, in_buf(g + 1, t));
+            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, in_buf(g + 1, t));
+            else {
+                const bool rows_ok = row0 + UM_TILE_M <= P.n_rows;
+                // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
+                float* orow0 = P.out + (row0 + q * 32 + tq) * P.out_pitch;
+                if (P.ten_to) epi_chunk_output<true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                else epi_chunk_output<false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
             }
-        }
+            // accumulator drained: hand the TMEM buffer back to the MMA issuer
+            tc_fence_before();
+            // the next layer's loader may only read the scratch once every chunk of this layer is
+            // written: one fence per thread before the last chunk's arrive covers all its stores
+            if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1 && !(P.debug_flags & 8)) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
+            __syncwarp();
+            if (lane == 0) {
+                if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
+                else mbar_arrive_remote_relaxed(accempty_leader0 + 8u * buf);   // TMEM reads are complete (wait::ld)
+                mbar_arrive(bar_parempty(buf));
+                if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
+            }
+            if (L.epi_kind == EPI_OUT) c_out += clock64() - t_job; else c_act += clock64() - t_job;
+            ++job;
+        })
         if (P.counters && ew == 0 && lane == 0) {
             long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
             cnt[UM_CNT_EPI_WAIT_ACCFULL] = w_accfull; cnt[UM_CNT_EPI_ACT] = c_act; cnt[UM_CNT_EPI_OUT] = c_out;
             cnt[UM_CNT_EPI_TOTAL] = clock64() - t_begin;
         }
     }
+#undef UM_FOR_EACH_JOB
 
     tc_fence_before();
     __syncthreads();
