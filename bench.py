@@ -44,6 +44,16 @@ def load_peaks():
     return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def load_traffic():
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed ncu --set full capture."""
+    p = os.path.join(REPO, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -247,11 +257,12 @@ def run_ours(args):
         peak = peaks["bf16_tflops_sustained"]
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None,
+            "traffic": load_traffic(),
             "kernel": "cpb::fused_mlp_umma_kernel", "launch_ms_avg": avg_launch_s * 1e3,
             "passes": PASSES, "executed_tflops": achieved * PASSES, "executed_frac": achieved * PASSES / peak,
             "peak_kind": "cuBLAS bf16 sustained, %s (burst %.1f)" % (peaks["source"], peaks["bf16_tflops"]),
             "hbm_achieved_gbs": BYTES_PER_SPECTRUM * batch / avg_launch_s / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
+            "algorithmic_bytes_per_launch": BYTES_PER_SPECTRUM * batch,
             "note": "algorithmic FLOP = 4,146,176 per spectrum (1 pass); the fp16x3 split executes 3 tensor passes, so frac <= 1/3 by construction and executed_frac is the tensor-pipe utilisation",
         }
         cpu = None
@@ -287,7 +298,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
