@@ -118,17 +118,23 @@ def cpu_path(sample_rows, steps, warmup):
         for attrs, d in models:
             with np.errstate(over="ignore"):
                 oracle_np.ten_to_predictions_np(attrs, d)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    try:
-        from threadpoolctl import threadpool_info
-        cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count() or 1])
+
+    def timed():
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        return time.perf_counter() - t0
+    want = os.cpu_count() or 1
+    try:   # torchrun exports OMP_NUM_THREADS=1: give BLAS every host core back for the CPU arm
+        from threadpoolctl import threadpool_info, threadpool_limits
+        with threadpool_limits(limits=want):
+            dt = timed()
+            cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
-        cores = os.cpu_count() or 1
+        dt = timed()
+        cores = int(os.environ.get("OMP_NUM_THREADS", want))
     return steps * len(MODELS) * sample_rows / dt, dt / steps, cores
 
 
