@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcpb200.so")
 PREC_FP32_SIMT = 0
 PREC_F16X3 = 1
 FLAG_TEN_TO = 1
+FLAG_ACCUMULATE = 2
 PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "f16x3": PREC_F16X3}
 
 _fp = ctypes.POINTER(ctypes.c_float)
@@ -182,12 +183,12 @@ class Engine:
             pass
 
     # -- device-resident path -------------------------------------------------------------
-    def forward_device_ptr(self, params_ptr, n_rows, out_ptr, out_pitch, ten_to=False, stream=0):
+    def forward_device_ptr(self, params_ptr, n_rows, out_ptr, out_pitch, ten_to=False, stream=0, accumulate=False):
+        flags = (FLAG_TEN_TO if ten_to else 0) | (FLAG_ACCUMULATE if accumulate else 0)
         _check(self._lib.cpb200_forward_device(self._h, ctypes.c_void_p(params_ptr), int(n_rows),
-                                               ctypes.c_void_p(out_ptr), int(out_pitch),
-                                               FLAG_TEN_TO if ten_to else 0, ctypes.c_void_p(stream)))
+                                               ctypes.c_void_p(out_ptr), int(out_pitch), flags, ctypes.c_void_p(stream)))
 
-    def forward_torch(self, params, out=None, ten_to=False):
+    def forward_torch(self, params, out=None, ten_to=False, accumulate=False):
         """params: CUDA float32 tensor (N, P) on this engine's device -> CUDA float32 (N, n_modes)."""
         import torch
         if not (params.is_cuda and params.dtype == torch.float32 and params.dim() == 2
@@ -197,6 +198,8 @@ class Engine:
             raise ValueError("tensor is on cuda:%s, engine on cuda:%d" % (params.device.index, self.device))
         params = params.contiguous()
         n = params.shape[0]
+        if accumulate and out is None:
+            raise ValueError("accumulate=True needs the `out` tensor that holds the first emulator's log-spectra")
         if out is None:
             # rows padded to a multiple of 8 floats (32-byte sectors) so the kernel can use aligned
             # vector stores; the caller gets the (n, n_modes) view
@@ -207,7 +210,7 @@ class Engine:
             raise ValueError("bad output tensor")
         stream = torch.cuda.current_stream(params.device).cuda_stream
         self.forward_device_ptr(params.data_ptr(), n, out.data_ptr(), out.stride(0) if n > 1 else self.n_modes,
-                                ten_to, stream)
+                                ten_to, stream, accumulate)
         return out
 
     # -- host path --------------------------------------------------------------------------

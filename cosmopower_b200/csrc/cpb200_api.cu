@@ -269,11 +269,11 @@ int launch_simt(cpb200_engine* e, const float* params, int64_t n, float* out, in
             const float* is = gi == 0 ? e->d_pstd : nullptr;
             const int ten = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
             if (g.epi == cpb::EPI_ACT)
-                cpb::dense_simt_kernel<cpb::EPI_ACT><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, im, is);
+                cpb::dense_simt_kernel<cpb::EPI_ACT><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, 0, im, is);
             else if (g.epi == cpb::EPI_AFFINE)
-                cpb::dense_simt_kernel<cpb::EPI_AFFINE><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, im, is);
+                cpb::dense_simt_kernel<cpb::EPI_AFFINE><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, 0, im, is);
             else
-                cpb::dense_simt_kernel<cpb::EPI_OUT><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, ten, im, is);
+                cpb::dense_simt_kernel<cpb::EPI_OUT><<<grid, 256, 0, st>>>(A, lda, g.dW, g.K, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, ten, (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0, im, is);
             ++e->launches;
             A = C;
             lda = ldc;
@@ -301,6 +301,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.n_parameters = e->P;
     p.n_modes = e->n_modes;
     p.ten_to = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
+    p.accumulate = (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0;
     p.params = params;
     p.pmean = e->d_pmean;
     p.pstd = e->d_pstd;

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256)
 dense_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
                   int K, int N, float* __restrict__ C, int64_t ldc, int64_t M,
                   const float* __restrict__ p0, const float* __restrict__ p1,
-                  const float* __restrict__ p2, int ten_to,
+                  const float* __restrict__ p2, int ten_to, int accumulate,
                   const float* __restrict__ in_mean, const float* __restrict__ in_std)
 {
     __shared__ float As[SIMT_BK][SIMT_BM + 4];
@@ -97,6 +97,7 @@ dense_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
                 v = (beta + (1.f - beta) * s) * a;
             } else {
                 v = fmaf(v, p0[gn], p1[gn]);
+                if (EPI == EPI_OUT && accumulate) v += C[gr * ldc + gn];      // fused sum of log-spectra
                 if (EPI == EPI_OUT && ten_to) v = exp10f(v);
             }
             C[gr * ldc + gn] = v;

@@ -51,6 +51,7 @@ constexpr int UM_THREADS = 640;
 constexpr int UM_EPI_WARP0 = 4;
 constexpr int UM_EPI_WARPS = 16;
 constexpr int UM_EPI_THREADS = UM_EPI_WARPS * 32;
+constexpr bool UM_DISCARD_DEAD_TILES = true;                      // discard.global.L2 on consumed activation tiles
 constexpr bool UM_EPI_PREFETCH = false;                          // software-pipeline the TMEM reads (needs > 96 registers)
 constexpr int UM_PIECE = 32;                                 // accumulator columns per epilogue piece
 constexpr float UM_INPUT_SCALE = 1024.f;                     // power-of-two pre-scale of the standardised parameters
@@ -83,6 +84,7 @@ struct UmmaParams {
     int n_parameters;
     int n_modes;
     int ten_to;
+    int accumulate;            // output layers add the log10 values already in `out` before the optional 10**
     const float* params;       // (n_rows, n_parameters)
     const float* pmean;
     const float* pstd;
@@ -192,6 +194,10 @@ __device__ __forceinline__ void bulk_g2s_multicast_hint(uint32_t dst_smem, const
 __device__ __forceinline__ void st_global_v4_hint(void* ptr, const uint4& v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
                  ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+// drop a dead 128-byte line from L2 without writing it back to HBM
+__device__ __forceinline__ void l2_discard_line(const void* ptr) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -466,7 +472,7 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
 }
 
 // output layers: de-standardise (+ 10**y) and store rows of the spectrum.
-template <bool TEN_TO>
+template <bool TEN_TO, bool ACC>
 __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, long long pitch, bool fast_rows,
                                                  long long rows_left, int n_modes) {
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
@@ -508,16 +514,33 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
             for (int rr = 0; rr < 2; ++rr) {
                 float y[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float v = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], pp[j].x, pp[j].y);
-                    y[j] = TEN_TO ? ex2_approx(v) : v;
-                }
+                for (int j = 0; j < 8; ++j) y[j] = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], pp[j].x, pp[j].y);
                 const int rl = 16 * h + 8 * rr;
                 float* dst = orow0 + static_cast<long long>(rl) * pitch + gc;
+                const bool row_ok = E.q * 32 + E.tq + rl < rows_left;
+                if (ACC) {
+                    // fused sum of log-spectra (e.g. log P_lin + log boost): add what the previous emulator left in `out`
+                    const float ks = TEN_TO ? 3.3219280948873623f : 1.f;
+                    if (fast) {
+                        const float4 p0 = *reinterpret_cast<const float4*>(dst), p1 = *reinterpret_cast<const float4*>(dst + 16);
+                        y[0] = fmaf(p0.x, ks, y[0]); y[1] = fmaf(p0.y, ks, y[1]); y[2] = fmaf(p0.z, ks, y[2]); y[3] = fmaf(p0.w, ks, y[3]);
+                        y[4] = fmaf(p1.x, ks, y[4]); y[5] = fmaf(p1.y, ks, y[5]); y[6] = fmaf(p1.z, ks, y[6]); y[7] = fmaf(p1.w, ks, y[7]);
+                    } else if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (gc + j < n_modes) y[j] = fmaf(dst[j], ks, y[j]);
+                            if (gc + 16 + j < n_modes) y[4 + j] = fmaf(dst[16 + j], ks, y[4 + j]);
+                        }
+                    }
+                }
+                if (TEN_TO) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = ex2_approx(y[j]);
+                }
                 if (fast) {
                     __stcs(reinterpret_cast<float4*>(dst), make_float4(y[0], y[1], y[2], y[3]));
                     __stcs(reinterpret_cast<float4*>(dst + 16), make_float4(y[4], y[5], y[6], y[7]));
-                } else if (E.q * 32 + E.tq + rl < rows_left) {
+                } else if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (gc + j < n_modes) __stcs(dst + j, y[j]);
@@ -599,7 +622,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const int G = P.n_gemms;
 
 // every role walks the same job sequence
-#define UM_FOR_EACH_JOB(BODY)                                                                          \
+#define UM_FOR_EACH_JOB(...)                                                                           \
     for (long long it = 0; it <= n_my_pg; ++it) {                                                      \
         const bool has_cur = it >= 1, has_next = it < n_my_pg;                                         \
         for (int ji = 0; ji < n_jobs; ++ji) {                                                          \
@@ -610,7 +633,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             /* rows beyond n_rows are padding (computed, never stored) */                              \
             const long long pair = (pg_first + (is_next ? it : it - 1) * pg_step) * UM_CLUSTER + cta_rank; \
             (void)pair; (void)c;                                                                       \
-            BODY                                                                                       \
+            __VA_ARGS__                                                                                \
         }                                                                                              \
     }
 
@@ -788,14 +811,27 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const long long t_job = clock64();
             E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * UM_MAX_NC);
             E.chunk_col0 = c * L.nc;
+            if (UM_DISCARD_DEAD_TILES && g >= 1 && c == L.n_chunks - 1) {
+                // this was the last chunk to stream the tile's operand: every copy of it has landed and been
+                // consumed (its MMAs are complete), so its L2 lines are dead - drop them instead of letting
+                // them be written back to HBM on eviction
+                const uint8_t* dead = in_buf(g, t);
+                const int n_lines = L.k_stages * (UM_A_STAGE_BYTES / 128);
+                for (int ln = threadIdx.x - UM_EPI_WARP0 * 32; ln < n_lines; ln += UM_EPI_THREADS) l2_discard_line(dead + ln * 128);
+            }
             if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, in_buf(g + 1, t));
             else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, in_buf(g + 1, t));
             else {
                 const bool rows_ok = row0 + UM_TILE_M <= P.n_rows;
                 // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
                 float* orow0 = P.out + (row0 + q * 32 + tq) * P.out_pitch;
-                if (P.ten_to) epi_chunk_output<true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
-                else epi_chunk_output<false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                if (P.accumulate) {
+                    if (P.ten_to) epi_chunk_output<true, true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                    else epi_chunk_output<false, true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                } else {
+                    if (P.ten_to) epi_chunk_output<true, false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                    else epi_chunk_output<false, false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                }
             }
             // accumulator drained: hand the TMEM buffer back to the MMA issuer
             tc_fence_before();

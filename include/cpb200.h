@@ -37,6 +37,9 @@ extern "C" {
 
 /* flags for cpb200_forward_* */
 #define CPB200_FLAG_TEN_TO     1  /* apply 10**x to the output (ten_to_predictions_np)         */
+#define CPB200_FLAG_ACCUMULATE 2  /* device path only: add the log10 values already in out_dev before the optional
+                                     10**x - fuses `10.**(lin.predictions_np(p) + boost.predictions_np(q))`
+                                     (reference cosmopower/trained_models/CP_paper/PK/README.md:62-65)        */
 
 typedef struct cpb200_engine cpb200_engine;
 
