@@ -165,3 +165,35 @@ def test_fused_linear_plus_boost_power_spectrum(precision):
     # unfused composition through the public API gives the same spectra
     y2 = 10. ** (lin.predictions_np(d_lin) + nl.predictions_np(d_nl))
     np.testing.assert_allclose(y, y2, rtol=2e-5)
+
+
+@pytest.mark.parametrize("n_hidden,n_params,n_modes", [([100, 37], 7, 333), ([64], 3, 40), ([], 5, 70), ([512, 512, 512, 512, 512, 512], 6, 2507)])
+def test_unusual_architectures_against_oracle(n_hidden, n_params, n_modes):
+    """Widths that are not multiples of the tile sizes, even/odd numbers of contractions, no hidden layer,
+    and a deeper net, built through the non-restore constructor (reference cosmopower_NN.py:71-80)."""
+    rng = np.random.default_rng(len(n_hidden) * 100 + n_modes)
+    dims = [n_params] + list(n_hidden) + [n_modes]
+    W = [(rng.standard_normal((a, b)) / np.sqrt(a)).astype(np.float32) for a, b in zip(dims[:-1], dims[1:])]
+    b = [(0.1 * rng.standard_normal(d)).astype(np.float32) for d in dims[1:]]
+    alphas = [(1.0 + rng.standard_normal(d)).astype(np.float32) for d in n_hidden]
+    betas = [(0.5 * rng.standard_normal(d)).astype(np.float32) for d in n_hidden]
+    names = ["p%d" % i for i in range(n_params)]
+    kw = dict(parameters=names, modes=np.arange(n_modes), n_hidden=list(n_hidden),
+              parameters_mean=rng.standard_normal(n_params), parameters_std=0.5 + rng.random(n_params),
+              features_mean=rng.standard_normal(n_modes), features_std=0.5 + rng.random(n_modes),
+              weights=dict(W_=W, b_=b, alphas_=alphas, betas_=betas))
+    x = rng.standard_normal((517, n_params))
+    attrs = None
+    for precision in ("f16x3", "fp32"):
+        m = cp.cosmopower_NN(device=0, precision=precision, **kw)
+        if attrs is None:
+            attrs = {k: getattr(m, k) for k in ("W_", "b_", "alphas_", "betas_", "parameters_mean_", "parameters_std_",
+                                                "features_mean_", "features_std_", "n_layers", "parameters", "n_modes")}
+            y_ref = oracle_np.forward_pass(attrs, x)
+        y = m.forward_pass_np(x)
+        assert y.shape == (517, n_modes)
+        # a deep *random* net amplifies every rounding error layer after layer (fp32 itself sits near 1e-5
+        # there), so only the shallow cases are held to the trained-model tolerance
+        tol = parity.TOL_LOG if len(n_hidden) <= 2 else 5e-5
+        assert parity.log_error(y, y_ref) <= tol, (precision, parity.log_error(y, y_ref))
+        m.close()
