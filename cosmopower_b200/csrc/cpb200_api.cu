@@ -324,7 +324,8 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.counters = e->d_counters;
     const int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * cpb::UM_CLUSTER;
-    cpb::fused_mlp_umma_kernel<<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+    if (p.counters) cpb::fused_mlp_umma_kernel<true><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+    else cpb::fused_mlp_umma_kernel<false><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
     ++e->launches;
     CU(cudaGetLastError());
     return 0;
@@ -449,7 +450,9 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
         if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
             cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess)
             return bail(fail(CPB200_E_CUDA, "error flag allocation failed"));
-        if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 cpb::UM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  cpb::UM_SMEM_BYTES) != cudaSuccess)
             return bail(fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
                              cudaGetErrorString(cudaGetLastError())));

@@ -554,9 +554,18 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+// PROF = true instantiates the per-role cycle counters (cpb200_engine_debug_counters); the production
+// instantiation carries no clock reads on the single-thread issue paths
+template <bool PROF>
 __global__ void __cluster_dims__(UM_CLUSTER, 1, 1) __launch_bounds__(UM_THREADS, 1)
 fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 {
+    auto mbar_wait = [](uint32_t bar, uint32_t parity, int* error_flag, int code) -> long long {
+        if (PROF) return cpb::mbar_wait(bar, parity, error_flag, code);
+        if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, error_flag, code);
+        return 0;
+    };
+    auto now = []() -> long long { return PROF ? clock64() : 0; };
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -579,7 +588,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbase + UM_SMEM_TMEMPTR);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); mbar_init(bar_peerfull(s), 1); }
+        // the leader's "full" barrier of a stage completes when its own copies have landed (arrive.expect_tx by
+        // its loader) AND the peer's relay has reported the peer's copies (one remote arrive): one wait per stage
+        const uint32_t full_count = (UM_CLUSTER > 1 && cluster_ctarank() == 0) ? 2 : 1;
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), full_count); mbar_init(bar_empty(s), 1); mbar_init(bar_peerfull(s), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS);
             mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS);
@@ -640,7 +652,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     if (warp == 0) {
         // ===================== loader: bulk copies into the stage ring =====================
         if (lane == 0) {
-            long long w_empty = 0, w_aready = 0; const long long t_begin = clock64();
+            long long w_empty = 0, w_aready = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_empty = 1;                 // fresh "empty" barriers pass at parity 1
             uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0}, ph_parempty[2] = {1, 1};
             const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
@@ -674,10 +686,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 }
                 ++job;
             })
-            if (P.counters) {
+            if (PROF && P.counters) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
                 cnt[UM_CNT_LOAD_WAIT_EMPTY] = w_empty; cnt[UM_CNT_LOAD_WAIT_AREADY] = w_aready;
-                cnt[UM_CNT_LOAD_TOTAL] = clock64() - t_begin;
+                cnt[UM_CNT_LOAD_TOTAL] = now() - t_begin;
             }
         }
     } else if (warp == 1) {
@@ -685,7 +697,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         if (lane == 0 && cta_rank != 0) {
             // the peer's operands live in its own shared memory: tell the leader when each stage has landed
             int stage = 0; uint32_t ph_full = 0;
-            const uint32_t peerfull0 = map_to_cta(bar_peerfull(0), 0);
+            const uint32_t peerfull0 = map_to_cta(bar_full(0), 0);        // the leader's full barriers
             UM_FOR_EACH_JOB({
                 (void)t;
                 const int ks = P.g[g].k_stages;
@@ -696,7 +708,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 }
             })
         } else if (lane == 0) {
-            long long w_full = 0, w_accempty = 0, w_peer = 0; const long long t_begin = clock64();
+            long long w_full = 0, w_accempty = 0, w_peer = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_full = 0;
             uint32_t ph_accempty[2] = {1, 1};
             int job = 0;
@@ -712,7 +724,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
                 for (int s = 0; s < L.k_stages; ++s) {
                     w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
-                    w_peer += mbar_wait(bar_peerfull(stage), ph_full, P.error_flag, 204);
                     tc_fence_after();
                     const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
                     const uint64_t a_hi = umma_desc_a(sa);
@@ -734,16 +745,16 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
                 ++job;
             })
-            if (P.counters) {
+            if (PROF && P.counters) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
                 cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty; cnt[UM_CNT_MMA_WAIT_PEERFULL] = w_peer;
-                cnt[UM_CNT_MMA_TOTAL] = clock64() - t_begin;
+                cnt[UM_CNT_MMA_TOTAL] = now() - t_begin;
             }
         }
     } else if (warp == 2) {
         // ===================== parameter standardiser: builds the layer-0 A operand =====================
         uint32_t ph_a0free[2] = {1, 1};
-        long long w_in = 0; const long long t_begin = clock64();
+        long long w_in = 0; const long long t_begin = now();
         const int np = P.n_parameters;
         for (long long pgi = 0; pgi < n_my_pg; ++pgi) {
             const long long pair = (pg_first + pgi * pg_step) * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding
@@ -780,9 +791,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 if (lane == 0) mbar_arrive(bar_a0ready(t));
             }
         }
-        if (P.counters && lane == 0) {
+        if (PROF && P.counters && lane == 0) {
             long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
-            cnt[UM_CNT_IN_WAIT] = w_in; cnt[UM_CNT_IN_TOTAL] = clock64() - t_begin;
+            cnt[UM_CNT_IN_WAIT] = w_in; cnt[UM_CNT_IN_TOTAL] = now() - t_begin;
         }
     } else if (warp >= UM_EPI_WARP0) {
         // ===================== epilogue warps =====================
@@ -794,7 +805,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         // 16-byte output stores need a 16-byte aligned base and a row pitch that is a multiple of 4 floats
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(P.out) & 15) | (static_cast<uintptr_t>(P.out_pitch) & 3)) == 0;
         uint32_t ph_accfull[2] = {0, 0};
-        long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = clock64();
+        long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = now();
         int job = 0;
         EpiCtx E;
         E.q = q; E.tq = tq; E.tr = tr; E.cw = cw; E.dbg = P.debug_flags;
@@ -808,7 +819,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             w_accfull += mbar_wait(bar_parfull(buf), ph_accfull[buf], P.error_flag, 402);
             w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
             tc_fence_after();
-            const long long t_job = clock64();
+            const long long t_job = now();
             E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * UM_MAX_NC);
             E.chunk_col0 = c * L.nc;
             if (UM_DISCARD_DEAD_TILES && g >= 1 && c == L.n_chunks - 1) {
@@ -845,13 +856,13 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 mbar_arrive(bar_parempty(buf));
                 if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
             }
-            if (L.epi_kind == EPI_OUT) c_out += clock64() - t_job; else c_act += clock64() - t_job;
+            if (L.epi_kind == EPI_OUT) c_out += now() - t_job; else c_act += now() - t_job;
             ++job;
         })
-        if (P.counters && ew == 0 && lane == 0) {
+        if (PROF && P.counters && ew == 0 && lane == 0) {
             long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
             cnt[UM_CNT_EPI_WAIT_ACCFULL] = w_accfull; cnt[UM_CNT_EPI_ACT] = c_act; cnt[UM_CNT_EPI_OUT] = c_out;
-            cnt[UM_CNT_EPI_TOTAL] = clock64() - t_begin;
+            cnt[UM_CNT_EPI_TOTAL] = now() - t_begin;
         }
     }
 #undef UM_FOR_EACH_JOB
