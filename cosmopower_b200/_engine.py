@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcpb200.so")
+LIB_PATH = os.environ.get("CPB200_LIB") or os.path.join(_HERE, "csrc", "libcpb200.so")
 
 PREC_FP32_SIMT = 0
 PREC_F16X3 = 1

@@ -1,30 +1,34 @@
 // Persistent fused-MLP kernel for sm_100a (CPB200_PREC_F16X3).
 //
-// One CTA per SM walks pairs of 128-row tiles through the WHOLE network (standardisation, every
-// dense layer, activation, PCA rescale + basis contraction, de-standardisation, 10**x).
-// Every dense contraction runs on the 5th-gen tensor cores (tcgen05.mma kind::f16, M=128,
-// N<=256, fp32 accumulators in TMEM) as a 3-product fp16 split:
+// 74 CTA pairs (cluster of 2, one CTA per SM) walk pairs of 128-row tiles through the WHOLE network
+// (standardisation, every dense layer, activation, PCA rescale + basis contraction,
+// de-standardisation, 10**x).  Every dense contraction runs on the 5th-gen tensor cores
+// (tcgen05.mma.cta_group::2 kind::f16, M = 256 across the pair, N <= 256, fp32 accumulators in each
+// CTA's TMEM) as a 3-product fp16 split:
 //     A.W  ~=  A_hi.W_hi + A_lo.W_hi + A_hi.W_lo      (x_hi = fp16(x), x_lo = fp16(x - x_hi))
 // which keeps ~22 significand bits per operand (single-pass bf16/tf32 miss the 1e-5 tolerance,
 // SURVEY 7.2).
 //
-// Data movement: operands are kept in the tensor core's canonical no-swizzle K-major
-// "core matrix" layout (8 rows x 16 bytes, contiguous 128 B) both in global memory and in shared
-// memory, so one pipeline stage is two plain bulk copies (cp.async.bulk, the TMA engine's 1-D
-// mode): 16 KB of activations (hi|lo, 128 rows x 32 k) and 2*NC*64 B of weights (hi|lo).
-// Activations between layers go through a CTA-private scratch that lives in L2 (a 128x512 tile in
-// split precision is 256 KB: more than shared memory, and TMEM holds the accumulators);
-// the epilogue warps write it with full-line 16-byte stores and the loader streams it back.
-// Two row tiles are interleaved per CTA so the epilogue of one overlaps the MMAs of the other.
+// Data movement: operands are stored in global memory already in the tensor core's shared-memory
+// layouts - weights as K-major no-swizzle core matrices (8 rows x 16 bytes), activations as K-major
+// SWIZZLE_64B tiles (64-byte rows) - so a pipeline stage is two plain bulk copies (cp.async.bulk,
+// the TMA engine's 1-D mode, no tensor maps): 16 KB of activations (hi|lo, 128 rows x 32 k) and this
+// CTA's half of the weight stage (NC*64 B).  Activations between layers go through a CTA-private
+// scratch that lives in L2 (a 128x512 tile in split precision is 256 KB: more than shared memory, and
+// TMEM holds the accumulators); the epilogue writes it with full-line 16-byte stores and the loader
+// streams it back.  Two row tiles are interleaved per CTA so the epilogue of one overlaps the MMAs of
+// the other; the order of jobs is a host-built table (layer 0 of the next pair is merged into the
+// current pair's output phase).
 //
-// Warp roles (384 threads): warp 0 loader (bulk copies), warp 1 MMA issuer (one thread),
-// warp 2 TMEM allocator + parameter standardiser, warp 3 idle, warps 4..11 epilogue
-// (2 warps per TMEM lane quarter, each owning half of the chunk's columns).
-// The epilogue reads accumulators with tcgen05.ld.16x256b, whose fragment gives a thread 2
-// adjacent columns of 2 rows: 4 neighbouring lanes then hold one 16-byte core-matrix row, so the
-// next layer's operand is written with full 128-byte lines and no shared-memory transpose (the
-// shared-memory data pipe is the scarce resource: the tensor core's operand reads and the bulk
-// copies already use most of it).
+// Warp roles (384 threads): warp 0 loader (bulk copies), warp 1 MMA issuer (one thread of the leader
+// CTA; relay thread in the peer), warp 2 TMEM allocator + parameter standardiser, warp 3 idle (or,
+// with warp 2, the optional CUDA-core first layer), warps 4..11 epilogue (2 warps per TMEM lane
+// quarter, 32-column pieces dealt alternately, TMEM reads software-pipelined half a piece ahead).
+// The epilogue reads accumulators with tcgen05.ld.16x256b, whose fragment gives a thread 2 adjacent
+// columns of 2 rows; the weight columns are packed in that order, so 4 neighbouring lanes hold one
+// 64-byte tile row and the next layer's operand is written with full 128-byte lines - no
+// shared-memory transpose (the shared-memory data pipe is the scarce resource: the tensor core's
+// operand reads and the bulk copies already use most of it).
 //
 // Reference math: cosmopower/cosmopower_NN.py:371-384,425 and
 // cosmopower/cosmopower_PCAplusNN.py:368-381,421.
@@ -47,9 +51,9 @@ constexpr int UM_A_STAGE_BYTES = 2 * UM_A_HALF_BYTES;        // 16384
 constexpr int UM_B_STAGE_BYTES_MAX = 2 * (UM_MAX_NC / 2) * UM_KS * 2;   // 16384: each CTA of the pair holds half of the chunk's columns
 constexpr int UM_STAGE_BYTES = UM_A_STAGE_BYTES + UM_B_STAGE_BYTES_MAX;   // 32768
 constexpr int UM_MAX_GEMMS = 8;
-constexpr int UM_THREADS = 640;
+constexpr int UM_THREADS = 384;
 constexpr int UM_EPI_WARP0 = 4;
-constexpr int UM_EPI_WARPS = 16;
+constexpr int UM_EPI_WARPS = 8;
 constexpr int UM_EPI_THREADS = UM_EPI_WARPS * 32;
 constexpr bool UM_DISCARD_DEAD_TILES = true;                      // discard.global.L2 on consumed activation tiles
 constexpr bool UM_EPI_PREFETCH = false;                          // software-pipeline the TMEM reads (needs > 96 registers)
@@ -411,6 +415,43 @@ struct EpiCtx {
 
 // hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
 // contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
+// One half piece = 16 TMEM lanes (rows tq, tq+8 of this warp's lower or upper 16 rows) x 32 accumulator columns:
+// v[4i + 2rr + cc] = (row 8rr + tq, lane value j = 2i + cc).
+template <int KIND>
+__device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const float4 (&pp)[8], float acc_scale,
+                                                 uint8_t* dst, uint64_t pol_keep) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        // written stage by stage (all 8 values through each step) so that the MUFU latencies of the
+        // 8 independent chains overlap instead of being serialised value after value
+        float hv[8];
+        if (KIND == EPI_ACT) {
+            float z[8], e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), acc_scale, pp[j].x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = ex2_approx(z[j] * pp[j].y);         // exp(-alpha*z)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = rcp_approx(1.f + e[j]);            // sigmoid; inf -> 0, as numpy
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hv[j] = fmaf(pp[j].w, e[j], pp[j].z) * z[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hv[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), pp[j].x, pp[j].y);
+        }
+        uint4 hi, lo;
+        split2(hv[0], hv[1], hi.x, lo.x);
+        split2(hv[2], hv[3], hi.y, lo.y);
+        split2(hv[4], hv[5], hi.z, lo.z);
+        split2(hv[6], hv[7], hi.w, lo.w);
+        // rows +8rr: 64 B per row; a warp store covers 8 rows x 64 B = 4 full lines
+        st_global_v4_hint(dst + rr * 512, hi, pol_keep);
+        st_global_v4_hint(dst + rr * 512 + UM_A_HALF_BYTES, lo, pol_keep);
+    }
+}
+
+// hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
+// contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
 template <int KIND>
 __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_scale, uint8_t* a_dst) {
     const uint64_t pol_keep = policy_evict_last();
@@ -419,61 +460,64 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
     // so this lane owns 8 consecutive logical columns = one 16-byte row chunk of the next A tile
     const int lcol0 = 8 * E.tr;
     constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
+    int pc = E.cw * UM_PIECE;
     uint32_t va[16], vb[16];
-    if (UM_EPI_PREFETCH && E.cw * UM_PIECE < E.nc) {                   // software-pipelined TMEM reads
-        tmem_ld_16x256b_x4(E.t_addr0 + E.cw * UM_PIECE, va);
-        tmem_ld_16x256b_x4(t_addr1 + E.cw * UM_PIECE, vb);
-    }
-    for (int pc = E.cw * UM_PIECE; pc < E.nc; pc += kStep) {
+    if (pc < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);            // TMEM reads run one half piece ahead of the math
+    for (; pc < E.nc; pc += kStep) {
         float4 pp[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) pp[j] = E.par[lcol0 + pc + j];
-        if (!UM_EPI_PREFETCH) {
-            tmem_ld_16x256b_x4(E.t_addr0 + pc, va);
-            tmem_ld_16x256b_x4(t_addr1 + pc, vb);
-        }
-        float x[32];
-        tmem_ld_wait32(va, vb);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { x[j] = __uint_as_float(va[j]); x[16 + j] = __uint_as_float(vb[j]); }
-        if (UM_EPI_PREFETCH && pc + kStep < E.nc) {
-            tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
-            tmem_ld_16x256b_x4(t_addr1 + pc + kStep, vb);
-        }
         const int kk = E.chunk_col0 + lcol0 + pc;                      // next layer's k index of this lane's 8 values
         // (kk % 32) >> 3 == tr; rows 32q + 16h + 8rr + tq share (row >> 1) & 3 == (tq >> 1) & 3
         uint8_t* dst = a_dst + static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(E.q * 32 + E.tq, E.tr);
-        // x[16h + 4i + 2rr + cc] = (row 16h + 8rr + tq, lane value j = 2i + cc)
+        tmem_ld_wait16(va);
+        tmem_ld_16x256b_x4(t_addr1 + pc, vb);
+        epi_operand_half<KIND>(va, pp, acc_scale, dst, pol_keep);
+        tmem_ld_wait16(vb);
+        if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
+        epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep);          // rows +16
+    }
+}
+
+template <bool TEN_TO, bool ACC>
+__device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const float2 (&pp)[8], float* drow, long long pitch,
+                                                bool fast, int row_in_q, long long rows_left, int gc, int n_modes) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+    for (int rr = 0; rr < 2; ++rr) {
+        float y[8];
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                // written stage by stage (all 8 values through each step) so that the MUFU latencies of the
-                // 8 independent chains overlap instead of being serialised value after value
-                float hv[8];
-                if (KIND == EPI_ACT) {
-                    float z[8], e[8];
+        for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), pp[j].x, pp[j].y);
+        float* dst = drow + static_cast<long long>(8 * rr) * pitch;
+        const bool row_ok = row_in_q + 8 * rr < rows_left;
+        if (ACC) {
+            // fused sum of log-spectra (e.g. log P_lin + log boost): add what the previous emulator left in `out`
+            const float ks = TEN_TO ? 3.3219280948873623f : 1.f;
+            if (fast) {
+                const float4 p0 = *reinterpret_cast<const float4*>(dst), p1 = *reinterpret_cast<const float4*>(dst + 16);
+                y[0] = fmaf(p0.x, ks, y[0]); y[1] = fmaf(p0.y, ks, y[1]); y[2] = fmaf(p0.z, ks, y[2]); y[3] = fmaf(p0.w, ks, y[3]);
+                y[4] = fmaf(p1.x, ks, y[4]); y[5] = fmaf(p1.y, ks, y[5]); y[6] = fmaf(p1.z, ks, y[6]); y[7] = fmaf(p1.w, ks, y[7]);
+            } else if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], acc_scale, pp[j].x);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) e[j] = ex2_approx(z[j] * pp[j].y);         // exp(-alpha*z)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) e[j] = rcp_approx(1.f + e[j]);            // sigmoid; inf -> 0, as numpy
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) hv[j] = fmaf(pp[j].w, e[j], pp[j].z) * z[j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) hv[j] = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], pp[j].x, pp[j].y);
+                for (int j = 0; j < 4; ++j) {
+                    if (gc + j < n_modes) y[j] = fmaf(dst[j], ks, y[j]);
+                    if (gc + 16 + j < n_modes) y[4 + j] = fmaf(dst[16 + j], ks, y[4 + j]);
                 }
-                uint4 hi, lo;
-                split2(hv[0], hv[1], hi.x, lo.x);
-                split2(hv[2], hv[3], hi.y, lo.y);
-                split2(hv[4], hv[5], hi.z, lo.z);
-                split2(hv[6], hv[7], hi.w, lo.w);
-                // rows +16h +8rr: 64 B per row; a warp store covers 8 rows x 64 B = 4 full lines
-                st_global_v4_hint(dst + (2 * h + rr) * 512, hi, pol_keep);
-                st_global_v4_hint(dst + (2 * h + rr) * 512 + UM_A_HALF_BYTES, lo, pol_keep);
             }
+        }
+        if (TEN_TO) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = ex2_approx(y[j]);
+        }
+        if (fast) {
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(y[0], y[1], y[2], y[3]));
+            __stcs(reinterpret_cast<float4*>(dst + 16), make_float4(y[4], y[5], y[6], y[7]));
+        } else if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (gc + j < n_modes) __stcs(dst + j, y[j]);
+                if (gc + 16 + j < n_modes) __stcs(dst + 16 + j, y[4 + j]);
+            }
+        }
     }
 }
 
@@ -483,12 +527,10 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
                                                  long long rows_left, int n_modes) {
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
     constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
+    int pc = E.cw * UM_PIECE;
     uint32_t va[16], vb[16];
-    if (UM_EPI_PREFETCH && E.cw * UM_PIECE < E.nc) {                   // software-pipelined TMEM reads
-        tmem_ld_16x256b_x4(E.t_addr0 + E.cw * UM_PIECE, va);
-        tmem_ld_16x256b_x4(t_addr1 + E.cw * UM_PIECE, vb);
-    }
-    for (int pc = E.cw * UM_PIECE; pc < E.nc; pc += kStep) {
+    if (pc < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);            // TMEM reads run one half piece ahead of the math
+    for (; pc < E.nc; pc += kStep) {
         // output layers are packed so that lane value j is logical column 4tr + j (j < 4) or 16 + 4tr + (j - 4):
         // each 16-byte store instruction then covers 64 contiguous bytes per row
         const int ocol = pc + 4 * E.tr;
@@ -500,60 +542,15 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
             pp[j] = TEN_TO ? make_float2(p0.z, p0.w) : make_float2(p0.x, p0.y);
             pp[4 + j] = TEN_TO ? make_float2(p1.z, p1.w) : make_float2(p1.x, p1.y);
         }
-        if (!UM_EPI_PREFETCH) {
-            tmem_ld_16x256b_x4(E.t_addr0 + pc, va);
-            tmem_ld_16x256b_x4(t_addr1 + pc, vb);
-        }
-        float x[32];
-        tmem_ld_wait32(va, vb);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { x[j] = __uint_as_float(va[j]); x[16 + j] = __uint_as_float(vb[j]); }
-        if (UM_EPI_PREFETCH && pc + kStep < E.nc) {
-            tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
-            tmem_ld_16x256b_x4(t_addr1 + pc + kStep, vb);
-        }
         const int gc = E.chunk_col0 + ocol;
         const bool fast = fast_rows && gc + 20 <= n_modes;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                float y[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = fmaf(x[16 * h + 4 * (j >> 1) + 2 * rr + (j & 1)], pp[j].x, pp[j].y);
-                const int rl = 16 * h + 8 * rr;
-                float* dst = orow0 + static_cast<long long>(rl) * pitch + gc;
-                const bool row_ok = E.q * 32 + E.tq + rl < rows_left;
-                if (ACC) {
-                    // fused sum of log-spectra (e.g. log P_lin + log boost): add what the previous emulator left in `out`
-                    const float ks = TEN_TO ? 3.3219280948873623f : 1.f;
-                    if (fast) {
-                        const float4 p0 = *reinterpret_cast<const float4*>(dst), p1 = *reinterpret_cast<const float4*>(dst + 16);
-                        y[0] = fmaf(p0.x, ks, y[0]); y[1] = fmaf(p0.y, ks, y[1]); y[2] = fmaf(p0.z, ks, y[2]); y[3] = fmaf(p0.w, ks, y[3]);
-                        y[4] = fmaf(p1.x, ks, y[4]); y[5] = fmaf(p1.y, ks, y[5]); y[6] = fmaf(p1.z, ks, y[6]); y[7] = fmaf(p1.w, ks, y[7]);
-                    } else if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (gc + j < n_modes) y[j] = fmaf(dst[j], ks, y[j]);
-                            if (gc + 16 + j < n_modes) y[4 + j] = fmaf(dst[16 + j], ks, y[4 + j]);
-                        }
-                    }
-                }
-                if (TEN_TO) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) y[j] = ex2_approx(y[j]);
-                }
-                if (fast) {
-                    __stcs(reinterpret_cast<float4*>(dst), make_float4(y[0], y[1], y[2], y[3]));
-                    __stcs(reinterpret_cast<float4*>(dst + 16), make_float4(y[4], y[5], y[6], y[7]));
-                } else if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (gc + j < n_modes) __stcs(dst + j, y[j]);
-                        if (gc + 16 + j < n_modes) __stcs(dst + 16 + j, y[4 + j]);
-                    }
-                }
-            }
+        float* drow = orow0 + gc;                                       // row 32q + tq of the tile
+        tmem_ld_wait16(va);
+        tmem_ld_16x256b_x4(t_addr1 + pc, vb);
+        epi_output_half<TEN_TO, ACC>(va, pp, drow, pitch, fast, E.q * 32 + E.tq, rows_left, gc, n_modes);
+        tmem_ld_wait16(vb);
+        if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
+        epi_output_half<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, pitch, fast, E.q * 32 + E.tq + 16, rows_left, gc, n_modes);
     }
 }
 
