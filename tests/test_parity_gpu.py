@@ -209,3 +209,26 @@ def test_cuda_core_first_layer_variant(monkeypatch):
         x = priors.sample_prior(m.parameters, 3000, seed=77)
         assert parity.model_error(name, m.forward_pass_np(x), oracle_np.forward_pass(attrs, x)) <= parity.model_tol(name)
         m.close()
+
+
+def test_streaming_sweep_matches_oracle_checksum():
+    """configs[4] at test size: all six emulators, chunked stream through one reused buffer, parameters drawn on
+    the device; the float64 checksum of one regenerated chunk is compared with the oracle."""
+    import torch
+    from cosmopower_b200 import sweep as sw
+    models = {name: get_model(name)[0] for name in parity.MODELS}
+    n_total, chunk = 70000, 32768                      # 3 chunks, the last one ragged
+    res = sw.sweep(models, n_total, chunk_rows=chunk, seed=5)
+    assert all(r["rows"] == n_total for r in res.values())
+    two = [sw.sweep(models, n_total, chunk_rows=chunk, seed=5, world_size=2, rank=r) for r in range(2)]
+    for name in parity.MODELS:                          # shards are disjoint and complete
+        assert two[0][name]["rows"] + two[1][name]["rows"] == n_total
+        np.testing.assert_allclose(two[0][name]["checksum"] + two[1][name]["checksum"], res[name]["checksum"], rtol=1e-12)
+    for name in ("PKLIN_NN", "cmb_PP_PCAplusNN"):
+        m, attrs = get_model(name)
+        ref = 0.0
+        for ci in range(3):
+            rows = min(chunk, n_total - ci * chunk)
+            x = sw.chunk_parameters(m.parameters, ci, rows, 5, torch.device("cuda", 0)).cpu().numpy().astype(np.float64)
+            ref += float(oracle_np.forward_chunked(attrs, x).sum())
+        assert abs(res[name]["checksum"] - ref) <= 1e-6 * abs(ref) + 1e-3
