@@ -12,7 +12,7 @@ from cosmopower_b200 import standins, sweep  # noqa: E402
 
 
 def main():
-    n_total = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
+    n_total = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 100_000_000
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -21,7 +21,7 @@ def main():
     for name in standins.ALL_MODELS:
         kind, path = standins.model_path(name)
         models[name] = getattr(cp, kind)(restore=True, restore_filename=path, device=local)
-    res = sweep.sweep(models, n_total, chunk_rows=1 << 20, seed=1, device=local, ten_to=True, checksum=True,
+    res = sweep.sweep(models, n_total, chunk_rows=1 << 20, seed=1, device=local, ten_to=False, checksum=("--no-checksum" not in sys.argv),
                       world_size=world, rank=rank)
     for name, r in res.items():
         r["spectra_per_s"] = r["rows"] / r["seconds"]
