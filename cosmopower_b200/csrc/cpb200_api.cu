@@ -80,9 +80,7 @@ struct cpb200_engine {
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
     int* d_error_flag = nullptr;
     unsigned* d_jobs = nullptr;         // job table of the fused kernel (build_jobs)
-    float* d_l0_w = nullptr;            // fp32 layer-0 weights for the CUDA-core first layer
-    int l0_simt = 0, l0_free_gemm = 0, l0_n = 0;
-    int n_jobs = 0, n_bufs = 2, l0_out_buf = 1;
+    int n_jobs = 0;
     long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
     // host pipeline
     cudaStream_t hstream[2] = {nullptr, nullptr};
@@ -234,15 +232,8 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
 // Job sequence of one iteration of the fused kernel: all chunks of contractions 1..G-1 for the
 // current pair of tiles, with the NEXT pair's layer-0 chunks merged into the last contraction's
 // (output) phase, so that their epilogues overlap MMAs that do not depend on them.
-std::vector<unsigned> build_jobs(const std::vector<Gemm>& gemms, bool l0_on_cuda_cores) {
+std::vector<unsigned> build_jobs(const std::vector<Gemm>& gemms) {
     const int G = static_cast<int>(gemms.size());
-    if (l0_on_cuda_cores) {         // layer 0 is produced off the tensor pipeline: the table is just contractions 1..G-1
-        std::vector<unsigned> jobs;
-        for (int g = 1; g < G; ++g)
-            for (int t = 0; t < 2; ++t)
-                for (int c = 0; c < gemms[g].n_chunks; ++c) jobs.push_back(static_cast<unsigned>(g | (t << 8) | (c << 16)));
-        return jobs;
-    }
     std::vector<unsigned> cur_head, cur_out, next0, jobs;
     auto enc = [](int g, int t, int c, int next) { return static_cast<unsigned>(g | (t << 8) | (c << 16) | (next << 24)); };
     for (int t = 0; t < 2; ++t)
@@ -324,12 +315,6 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.scratch_cta_bytes = e->um_scratch_cta;
     p.a0_bytes = e->um_a0_bytes;
     p.abuf_bytes = e->um_abuf_bytes;
-    p.n_bufs = e->n_bufs;
-    p.l0_out_buf = e->l0_out_buf;
-    p.l0_simt = e->l0_simt;
-    p.l0_free_gemm = e->l0_free_gemm;
-    p.l0_n = e->l0_n;
-    p.l0_w = e->d_l0_w;
     p.jobs = e->d_jobs;
     p.n_jobs = e->n_jobs;
     p.error_flag = e->d_error_flag;
@@ -442,27 +427,9 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
         }
         e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
         e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
-        // layer 0 of the next pair is written while the current pair's last contraction still streams its
-        // operand: with an even number of contractions that is the buffer contraction 1 would read, so a
-        // third buffer takes the layer-0 output
-        const int G = static_cast<int>(e->gemms.size());
-        e->n_bufs = (G % 2 == 0 && G > 1) ? 3 : 2;
-        e->l0_out_buf = e->n_bufs == 3 ? 2 : 1;
-        // Optional: first layer on CUDA cores (warps 2-3 produce the next pair's h1 off the tensor pipeline).
-        // Measured on B200 it is not a win - two warps need 60-100 k cycles per tile for the 128x512 activations,
-        // which starves the short P(k) pairs (PKLIN 4.33 ms vs 3.83 ms) and only breaks even on TT - so the
-        // default keeps layer 0 on the tensor pipe (zero-padded K = 32) with its chunks overlapped into the
-        // previous pair's output phase.  CPB200_L0_CUDA_CORES=1 selects it (covered by the GPU tests).
-        // The buffer it writes is free once its last reader of the current pair has finished: contraction 1
-        // (3 buffers) or the last odd contraction G-2 (2 buffers, G odd).
-        const char* l0env = getenv("CPB200_L0_CUDA_CORES");
-        e->l0_simt = (G >= 2 && e->P <= cpb::UM_L0_MAX_PARAMS && l0env && atoi(l0env) != 0) ? 1 : 0;
-        e->l0_free_gemm = e->n_bufs == 3 ? 1 : G - 2;
-        e->l0_n = e->gemms[0].N;
-        if (e->l0_simt && (rc = upload(&e->d_l0_w, e->gemms[0].W.data(), e->gemms[0].W.size()))) return bail(rc);
-        e->um_scratch_cta = 2ull * e->um_a0_bytes + 2ull * e->n_bufs * e->um_abuf_bytes;
+        e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes;
         {
-            std::vector<unsigned> jobs = build_jobs(e->gemms, e->l0_simt != 0);
+            std::vector<unsigned> jobs = build_jobs(e->gemms);
             if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
                 return bail(fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
             e->n_jobs = static_cast<int>(jobs.size());
@@ -501,7 +468,7 @@ int cpb200_destroy(cpb200_engine* e) {
     }
     cudaFree(e->d_pmean); cudaFree(e->d_pstd);
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
-    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters); cudaFree(e->d_jobs); cudaFree(e->d_l0_w);
+    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters); cudaFree(e->d_jobs);
     for (int i = 0; i < 2; ++i) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);

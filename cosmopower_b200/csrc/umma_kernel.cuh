@@ -45,6 +45,7 @@ constexpr int UM_TILE_M = 128;
 constexpr int UM_KS = 32;                                    // k elements per pipeline stage
 constexpr int UM_MAX_NC = 256;                               // widest N chunk (one accumulator)
 constexpr int UM_STAGES = 6;
+constexpr int UM_ACT_BUFS = 3;                               // activation buffers per CTA (rotated between its two tiles)
 constexpr int UM_CLUSTER = 2;                                // CTA pair: one tcgen05.mma.cta_group::2 (M = 256) drives both SMs
 constexpr int UM_A_HALF_BYTES = UM_TILE_M * UM_KS * 2;       // 8192: one of (hi, lo)
 constexpr int UM_A_STAGE_BYTES = 2 * UM_A_HALF_BYTES;        // 16384
@@ -70,9 +71,7 @@ constexpr int UM_NUM_BARS = 3 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_MAX_JOBS = 96;
 constexpr int UM_SMEM_JOBS = UM_SMEM_TMEMPTR + 16;
-constexpr int UM_L0_MAX_PARAMS = 8;                          // widest input the CUDA-core first layer handles
-constexpr int UM_SMEM_L0X = (UM_SMEM_JOBS + UM_MAX_JOBS * 4 + 15) / 16 * 16;   // standardised inputs of one tile: 128 x 8 floats
-constexpr int UM_SMEM_BYTES = UM_SMEM_L0X + UM_TILE_M * UM_L0_MAX_PARAMS * 4 + 1024;   // + alignment slack
+constexpr int UM_SMEM_BYTES = UM_SMEM_JOBS + UM_MAX_JOBS * 4 + 1024;         // + alignment slack
 
 struct UmmaGemm {
     const __half* wpack;   // [n_chunks][k_stages][hi|lo][nc x 32] core-matrix tiles
@@ -102,13 +101,7 @@ struct UmmaParams {
     uint8_t* scratch;          // gridDim.x * scratch_cta_bytes
     unsigned long long scratch_cta_bytes;
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
-    unsigned abuf_bytes;       // per tile per buffer: max k_stages(gemm >= 1) * 16384
-    int n_bufs;                // activation buffers per tile: 2, or 3 when the number of contractions is even
-    int l0_out_buf;            // buffer layer 0 writes (read by contraction 1): 1, or 2 when n_bufs == 3
-    int l0_simt;               // 1: layer 0 (K = n_parameters) runs on CUDA cores in warps 2-3, ahead of the tensor pipeline
-    int l0_free_gemm;          // contraction whose completion frees the buffer layer 0 writes for the next pair
-    int l0_n;                  // logical width of layer 0
-    const float* l0_w;         // layer-0 weights, (n_parameters, l0_n) row-major fp32
+    unsigned abuf_bytes;       // per activation buffer: max k_stages(gemm >= 1) * 16384; a CTA owns UM_ACT_BUFS of them
     const unsigned* jobs;      // job table: g | t << 8 | c << 16 | next << 24 (see cpb200_api.cu build_jobs)
     int n_jobs;
     int debug_flags;           // timing ablations only (results are wrong when set): 1 no MUFU, 2 no scratch stores, 4 no output stores, 8 no fence
@@ -601,7 +594,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar_aready(t), UM_EPI_WARPS);
-            mbar_init(bar_a0ready(t), P.l0_simt ? 2 : 1);      // two producer warps, or the one standardiser warp
+            mbar_init(bar_a0ready(t), 1);
             mbar_init(bar_a0free(t), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -629,12 +622,20 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 
     uint8_t* cta_scratch = P.scratch + static_cast<unsigned long long>(blockIdx.x) * P.scratch_cta_bytes;
     auto a0_buf = [&](int t) { return cta_scratch + static_cast<size_t>(t) * P.a0_bytes; };
-    auto a_buf = [&](int t, int b) {
-        return cta_scratch + 2ull * P.a0_bytes + (static_cast<size_t>(t) * P.n_bufs + b) * P.abuf_bytes;
-    };
-    // activation buffer read by contraction g (g >= 1) = written by contraction g-1
-    auto in_buf = [&](int g, int t) { return a_buf(t, g == 1 ? P.l0_out_buf : (g & 1)); };
     const int G = P.n_gemms;
+    // Activation buffers: THREE per CTA, rotated between its two tiles.  With the job order X.g, Y.g, X.g+1, ...
+    // at most three 128 x K tiles are live at any time (X.in, X.out, Y.in - or Y.in, Y.out, X.out), so step
+    // n = 2(g-1) + t of pair number `pidx` reads slot (2n + pidx(G-1)) mod 3 and writes slot (2n + 1 + ...) mod 3
+    // (= the slot step n+2, the same tile's next contraction, reads).  The per-pair offset makes the next
+    // pair's layer 0, which runs inside this pair's output phase, land in the slot that is free then.
+    // 3 x 256 KB per CTA instead of 4-6 keeps the whole scratch (111 MB) under the L2 capacity.
+    auto act_slot = [&](int slot) { return cta_scratch + 2ull * P.a0_bytes + static_cast<size_t>(slot) * P.abuf_bytes; };
+    auto in_buf = [&](int g, int t, long long pidx) {      // operand of contraction g >= 1
+        return act_slot(static_cast<int>((2 * (2 * (g - 1) + t) + pidx * (G - 1)) % 3));
+    };
+    auto out_buf = [&](int g, int t, long long pidx) {     // written by contraction g (any g that is not the last)
+        return act_slot(static_cast<int>((2 * (2 * (g - 1) + t) + 3 + 1 + pidx * (G - 1)) % 3));
+    };
 
 // every role walks the same job sequence
 #define UM_FOR_EACH_JOB(...)                                                                           \
@@ -646,8 +647,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const bool is_next = (jw >> 24) != 0;                                                      \
             if (is_next ? !has_next : !has_cur) continue;                                              \
             /* rows beyond n_rows are padding (computed, never stored) */                              \
-            const long long pair = (pg_first + (is_next ? it : it - 1) * pg_step) * UM_CLUSTER + cta_rank; \
-            (void)pair; (void)c;                                                                       \
+            const long long pidx = is_next ? it : it - 1;      /* this cluster's running pair number */  \
+            const long long pair = (pg_first + pidx * pg_step) * UM_CLUSTER + cta_rank;                \
+            (void)pair; (void)c; (void)pidx;                                                           \
             __VA_ARGS__                                                                                \
         }                                                                                              \
     }
@@ -664,10 +666,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const UmmaGemm& L = P.g[g];
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
                 if (c == 0) {                                     // the whole K extent of this tile's operand must be written
-                    if (g == 0 || (g == 1 && P.l0_simt)) { w_aready += mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1; }
+                    if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1; }
                     else { w_aready += mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1; }
                 }
-                const uint8_t* a_src = g == 0 ? a0_buf(t) : in_buf(g, t);
+                const uint8_t* a_src = g == 0 ? a0_buf(t) : in_buf(g, t, pidx);
                 {   // this chunk's per-column epilogue constants -> shared memory (ring of 2 by job parity)
                     const int pb = job & 1;
                     w_empty += mbar_wait(bar_parempty(pb), ph_parempty[pb], P.error_flag, 104); ph_parempty[pb] ^= 1;
@@ -745,89 +747,13 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                 }
                 umma_commit_2cta(bar_accfull(buf));               // both CTAs' epilogues may drain their 128 rows
-                // the layer-0 operand (tensor-core first layer) / the buffer the CUDA-core first layer writes is free
-                if (g == (P.l0_simt ? P.l0_free_gemm : 0) && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));
+                if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
                 ++job;
             })
             if (PROF && P.counters) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
                 cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty; cnt[UM_CNT_MMA_WAIT_PEERFULL] = w_peer;
                 cnt[UM_CNT_MMA_TOTAL] = now() - t_begin;
-            }
-        }
-    } else if ((warp == 2 || warp == 3) && P.l0_simt) {
-        // ===================== first layer on CUDA cores (K = n_parameters is far too small for the tensor pipe) ====
-        // Two warps produce h1 = act(x_std . W0 + b0) for the NEXT pair of tiles, already split and laid out as
-        // contraction 1's A operand, while the tensor pipeline works on the current pair.  lane = output column.
-        const int pw = warp - 2;
-        const UmmaGemm& L0 = P.g[0];
-        const int np = P.n_parameters;
-        const int n0_blocks = (L0.n_chunks * L0.nc) / UM_KS;        // 32-column blocks of the padded layer width
-        float* xs = reinterpret_cast<float*>(sbase + UM_SMEM_L0X);
-        uint32_t ph_free[2] = {1, 1};
-        for (long long pgi = 0; pgi < n_my_pg; ++pgi) {
-            const long long pair = (pg_first + pgi * pg_step) * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding
-            for (int t = 0; t < 2; ++t) {
-                mbar_wait(bar_a0free(t), ph_free[t], P.error_flag, 302); ph_free[t] ^= 1;
-                const long long row0 = (pair * 2 + t) * UM_TILE_M;
-                for (int r = pw * 32 + lane; r < UM_TILE_M; r += 64) {   // standardise (reference cosmopower_NN.py:371)
-                    const long long grow = row0 + r;
-#pragma unroll
-                    for (int k = 0; k < UM_L0_MAX_PARAMS; ++k) {
-                        float v = 0.f;
-                        if (k < np && grow < P.n_rows) v = (P.params[grow * np + k] - P.pmean[k]) / P.pstd[k];
-                        xs[r * UM_L0_MAX_PARAMS + k] = v;
-                    }
-                }
-                asm volatile("bar.sync 2, 64;" ::: "memory");
-                uint8_t* dst = in_buf(1, t);
-                for (int cb = pw; cb < n0_blocks; cb += 2) {
-                    const int col = cb * UM_KS + lane;
-                    float w[UM_L0_MAX_PARAMS];
-#pragma unroll
-                    for (int k = 0; k < UM_L0_MAX_PARAMS; ++k) w[k] = (k < np && col < P.l0_n) ? P.l0_w[k * P.l0_n + col] : 0.f;
-                    const float4 pp = L0.epi[col];                  // {b, -alpha*log2e, beta*s, (1-beta)*s}; zeros on padding
-                    uint8_t* d = dst + static_cast<size_t>(cb) * UM_A_STAGE_BYTES + (lane & 7) * 2;
-                    const int chunk = lane >> 3;
-                    // rows in batches of 4, each step done for the whole batch: the loads, the two MUFU ops and the
-                    // stores of different rows overlap (the compiler cannot reorder them across the scratch stores itself)
-                    for (int r0 = 0; r0 < UM_TILE_M; r0 += 4) {
-                        float4 xa[4], xb[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4* xr = reinterpret_cast<const float4*>(xs + (r0 + i) * UM_L0_MAX_PARAMS);
-                            xa[i] = xr[0]; xb[i] = xr[1];
-                        }
-                        float z[4], e[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float za = fmaf(xa[i].w, w[3], fmaf(xa[i].z, w[2], fmaf(xa[i].y, w[1], fmaf(xa[i].x, w[0], pp.x))));
-                            const float zb = fmaf(xb[i].w, w[7], fmaf(xb[i].z, w[6], fmaf(xb[i].y, w[5], xb[i].x * w[4])));
-                            z[i] = za + zb;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) e[i] = ex2_approx(z[i] * pp.y);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) e[i] = rcp_approx(1.f + e[i]);
-                        __half hi[4], lo[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float h = fmaf(pp.w, e[i], pp.z) * z[i];
-                            hi[i] = __float2half_rn(h);
-                            lo[i] = __float2half_rn(h - __half2float(hi[i]));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t off = a_tile_off(r0 + i, chunk);
-                            *reinterpret_cast<__half*>(d + off) = hi[i];              // 32 lanes = one 64-byte tile row
-                            *reinterpret_cast<__half*>(d + off + UM_A_HALF_BYTES) = lo[i];
-                        }
-                    }
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a0ready(t));
-                asm volatile("bar.sync 2, 64;" ::: "memory");       // xs may be overwritten
             }
         }
     } else if (warp == 2) {
@@ -905,12 +831,12 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 // this was the last chunk to stream the tile's operand: every copy of it has landed and been
                 // consumed (its MMAs are complete), so its L2 lines are dead - drop them instead of letting
                 // them be written back to HBM on eviction
-                const uint8_t* dead = in_buf(g, t);
+                const uint8_t* dead = in_buf(g, t, pidx);
                 const int n_lines = L.k_stages * (UM_A_STAGE_BYTES / 128);
                 for (int ln = threadIdx.x - UM_EPI_WARP0 * 32; ln < n_lines; ln += UM_EPI_THREADS) l2_discard_line(dead + ln * 128);
             }
-            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, in_buf(g + 1, t));
-            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, in_buf(g + 1, t));
+            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, out_buf(g, t, pidx));
+            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, out_buf(g, t, pidx));
             else {
                 const bool rows_ok = row0 + UM_TILE_M <= P.n_rows;
                 // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq

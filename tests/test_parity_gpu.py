@@ -199,18 +199,6 @@ def test_unusual_architectures_against_oracle(n_hidden, n_params, n_modes):
         m.close()
 
 
-def test_cuda_core_first_layer_variant(monkeypatch):
-    """CPB200_L0_CUDA_CORES=1: layer 0 produced by CUDA-core warps ahead of the tensor pipeline (optional path)."""
-    monkeypatch.setenv("CPB200_L0_CUDA_CORES", "1")
-    for name in ("PKNLBOOST_NN", "cmb_PP_PCAplusNN", "cmb_TT_NN"):
-        kind, path = standins.model_path(name)
-        m = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
-        attrs = standins.load_attrs(kind, path)
-        x = priors.sample_prior(m.parameters, 3000, seed=77)
-        assert parity.model_error(name, m.forward_pass_np(x), oracle_np.forward_pass(attrs, x)) <= parity.model_tol(name)
-        m.close()
-
-
 def test_streaming_sweep_matches_oracle_checksum():
     """configs[4] at test size: all six emulators, chunked stream through one reused buffer, parameters drawn on
     the device; the float64 checksum of one regenerated chunk is compared with the oracle."""
