@@ -208,20 +208,28 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
             pack[base + tile + off] = lo;
         }
     }
+    // Epilogue constants, stored in the order the epilogue lanes read them: inside each 32-column block lane
+    // group t (= lane & 3) owns 8 logical columns - 8t..8t+7 for operand-producing layers, 4t..4t+3 and
+    // 16+4t..16+4t+3 for output layers - and its j-th value sits at position 4j + t.
     std::vector<float4> epi(static_cast<size_t>(g.n_chunks) * g.nc, make_float4(0.f, 0.f, 0.f, 0.f));
     for (int n = 0; n < g.N; ++n) {
+        const int nb = n & 31;
+        int t, j;
+        if (g.epi == cpb::EPI_OUT) { t = (nb & 15) >> 2; j = (nb & 3) | ((nb >> 4) << 2); }
+        else { t = nb >> 3; j = nb & 7; }
+        float4& dst = epi[(n & ~31) + 4 * j + t];
         if (g.epi == cpb::EPI_ACT) {
             const float alpha = g.p1[n], beta = g.p2[n];
             // a = acc*acc_scale + b;  h*s_out = ((1-beta)*s_out * sigmoid + beta*s_out) * a
-            epi[n] = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
-                                 beta * s_out, (1.f - beta) * s_out);
+            dst = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
+                              beta * s_out, (1.f - beta) * s_out);
         } else if (g.epi == cpb::EPI_AFFINE) {
-            epi[n] = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
+            dst = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
         } else {
             // {scale, shift} for predictions; {scale, shift} * log2(10) for 10**y = 2**(y*log2 10)
             const double l2_10 = 3.321928094887362;
-            epi[n] = make_float4(g.p0[n] * inv, g.p1[n], static_cast<float>(static_cast<double>(g.p0[n]) * inv * l2_10),
-                                 static_cast<float>(static_cast<double>(g.p1[n]) * l2_10));
+            dst = make_float4(g.p0[n] * inv, g.p1[n], static_cast<float>(static_cast<double>(g.p0[n]) * inv * l2_10),
+                              static_cast<float>(static_cast<double>(g.p1[n]) * l2_10));
         }
     }
     if (int rc = upload(&g.dwpack, pack.data(), pack.size())) return rc;
@@ -318,7 +326,6 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.jobs = e->d_jobs;
     p.n_jobs = e->n_jobs;
     p.error_flag = e->d_error_flag;
-    if (const char* dbg = getenv("CPB200_DEBUG_FLAGS")) p.debug_flags = atoi(dbg);   // timing ablations only
     p.counters = e->d_counters;
     const int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * cpb::UM_CLUSTER;

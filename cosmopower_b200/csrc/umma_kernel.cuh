@@ -104,7 +104,6 @@ struct UmmaParams {
     unsigned abuf_bytes;       // per activation buffer: max k_stages(gemm >= 1) * 16384; a CTA owns UM_ACT_BUFS of them
     const unsigned* jobs;      // job table: g | t << 8 | c << 16 | next << 24 (see cpb200_api.cu build_jobs)
     int n_jobs;
-    int debug_flags;           // timing ablations only (results are wrong when set): 1 no MUFU, 2 no scratch stores, 4 no output stores, 8 no fence
     int* error_flag;           // set to a code by the watchdog before trapping
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
 };
@@ -400,7 +399,6 @@ struct EpiCtx {
     uint32_t t_addr0;        // TMEM address of this warp's first column, lanes +0
     int nc;                  // chunk width (multiple of 32)
     int cw;                  // this warp takes the 32-column pieces cw, cw + UM_EPI_WARPS/4, ...
-    int dbg;
     int chunk_col0;          // c * nc
     int q, tq, tr;
     const float4* par;       // the chunk's per-column constants in shared memory (logical column order)
@@ -457,9 +455,11 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
     uint32_t va[16], vb[16];
     if (pc < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);            // TMEM reads run one half piece ahead of the math
     for (; pc < E.nc; pc += kStep) {
+        // the constants of a 32-column block are stored lane-interleaved (value j of lane group tr at 4j + tr):
+        // the four lane groups read 64 contiguous bytes - no shared-memory bank conflicts
         float4 pp[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pp[j] = E.par[lcol0 + pc + j];
+        for (int j = 0; j < 8; ++j) pp[j] = E.par[pc + 4 * j + E.tr];
         const int kk = E.chunk_col0 + lcol0 + pc;                      // next layer's k index of this lane's 8 values
         // (kk % 32) >> 3 == tr; rows 32q + 16h + 8rr + tq share (row >> 1) & 3 == (tq >> 1) & 3
         uint8_t* dst = a_dst + static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(E.q * 32 + E.tq, E.tr);
@@ -530,7 +530,7 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
         float2 pp[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4 p0 = E.par[ocol + j], p1 = E.par[ocol + 16 + j];
+            const float4 p0 = E.par[pc + 4 * j + E.tr], p1 = E.par[pc + 4 * (4 + j) + E.tr];     // lane-interleaved, see epi_chunk_operand
             // ten_to: 10**y = 2**(y*log2(10)); the factor is folded into .z/.w on the host
             pp[j] = TEN_TO ? make_float2(p0.z, p0.w) : make_float2(p0.x, p0.y);
             pp[4 + j] = TEN_TO ? make_float2(p1.z, p1.w) : make_float2(p1.x, p1.y);
@@ -813,7 +813,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = now();
         int job = 0;
         EpiCtx E;
-        E.q = q; E.tq = tq; E.tr = tr; E.cw = cw; E.dbg = P.debug_flags;
+        E.q = q; E.tq = tq; E.tr = tr; E.cw = cw;
         const uint32_t accempty_leader0 = map_to_cta(bar_accempty(0), 0);
         UM_FOR_EACH_JOB({
             const UmmaGemm& L = P.g[g];
@@ -853,7 +853,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             tc_fence_before();
             // the next layer's loader may only read the scratch once every chunk of this layer is
             // written: one fence per thread before the last chunk's arrive covers all its stores
-            if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1 && !(P.debug_flags & 8)) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
+            if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
             __syncwarp();
             if (lane == 0) {
                 if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
