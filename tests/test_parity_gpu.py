@@ -220,3 +220,21 @@ def test_streaming_sweep_matches_oracle_checksum():
             x = sw.chunk_parameters(m.parameters, ci, rows, 5, torch.device("cuda", 0)).cpu().numpy().astype(np.float64)
             ref += float(oracle_np.forward_chunked(attrs, x).sum())
         assert abs(res[name]["checksum"] - ref) <= 1e-6 * abs(ref) + 1e-3
+
+
+@pytest.mark.parametrize("name,n", [("cmb_TT_NN", 1000), ("PKLIN_NN", 257), ("cmb_PP_PCAplusNN", 129)])
+def test_no_write_outside_the_output_rows(name, n):
+    """Guard rows/columns around the caller's output window must stay untouched (compute-sanitizer is closed on
+    this pool, so out-of-bounds stores are hunted with sentinels): ragged row counts, padded and tight pitches."""
+    import torch
+    m, _ = get_model(name)
+    x = torch.from_numpy(priors.sample_prior(m.parameters, n, seed=3, dtype=np.float32)).cuda()
+    for pitch in (m.n_modes, (m.n_modes + 7) // 8 * 8 + 8):
+        big = torch.full((n + 256, pitch), -123.0, device="cuda")
+        window = big[128:128 + n, :m.n_modes]
+        m.engine().forward_torch(x, out=window, ten_to=True)
+        torch.cuda.synchronize()
+        assert torch.all(big[:128] == -123.0) and torch.all(big[128 + n:] == -123.0)
+        if pitch > m.n_modes:
+            assert torch.all(big[128:128 + n, m.n_modes:] == -123.0)
+        assert torch.all(torch.isfinite(window)) and torch.all(window > 0)
