@@ -57,7 +57,6 @@ constexpr int UM_EPI_WARP0 = 4;
 constexpr int UM_EPI_WARPS = 8;
 constexpr int UM_EPI_THREADS = UM_EPI_WARPS * 32;
 constexpr bool UM_DISCARD_DEAD_TILES = true;                      // discard.global.L2 on consumed activation tiles
-constexpr bool UM_EPI_PREFETCH = false;                          // software-pipeline the TMEM reads (needs > 96 registers)
 constexpr int UM_PIECE = 32;                                 // accumulator columns per epilogue piece
 constexpr float UM_INPUT_SCALE = 1024.f;                     // power-of-two pre-scale of the standardised parameters
 constexpr float UM_TRUNC_BIAS_ULPS_PER_STEP = 0.16f;               // mean accumulator loss per MMA step, in ulps (calibrated on B200)
@@ -67,15 +66,16 @@ constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre
 constexpr int UM_SMEM_STAGES = 0;
 constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // 2 x 256 float4
 constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + 2 * UM_MAX_NC * 16;
-constexpr int UM_NUM_BARS = 3 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
+constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_MAX_JOBS = 96;
 constexpr int UM_SMEM_JOBS = UM_SMEM_TMEMPTR + 16;
 constexpr int UM_SMEM_BYTES = UM_SMEM_JOBS + UM_MAX_JOBS * 4 + 1024;         // + alignment slack
 
 struct UmmaGemm {
-    const __half* wpack;   // [n_chunks][k_stages][hi|lo][nc x 32] core-matrix tiles
-    const float4* epi;     // per padded output column: ACT {b, -alpha*log2e, beta*s, (1-beta)*s}; else {scale, shift,0,0}
+    const __half* wpack;   // [n_chunks][k_stages][CTA0: hi|lo half tiles][CTA1: hi|lo half tiles], core-matrix order
+    const float4* epi;     // per padded output column (lane-interleaved inside 32-column blocks):
+                           // ACT {b, -alpha*log2e, beta*s, (1-beta)*s}; AFFINE {scale, shift}; OUT {scale, shift, *log2 10}
     int k_stages;          // K_pad / 32
     int nc;                // chunk width: multiple of 32, <= 256
     int n_chunks;
@@ -112,7 +112,7 @@ struct UmmaParams {
 enum { UM_CNT_LOAD_WAIT_EMPTY = 0, UM_CNT_LOAD_WAIT_AREADY = 1, UM_CNT_LOAD_TOTAL = 2,
        UM_CNT_MMA_WAIT_FULL = 3, UM_CNT_MMA_WAIT_ACCEMPTY = 4, UM_CNT_MMA_TOTAL = 5,
        UM_CNT_EPI_WAIT_ACCFULL = 6, UM_CNT_EPI_ACT = 7, UM_CNT_EPI_OUT = 8, UM_CNT_EPI_TOTAL = 9,
-       UM_CNT_IN_WAIT = 10, UM_CNT_IN_TOTAL = 11, UM_CNT_MMA_WAIT_PEERFULL = 12, UM_CNT_SLOTS = 16 };
+       UM_CNT_IN_WAIT = 10, UM_CNT_IN_TOTAL = 11, UM_CNT_SLOTS = 16 };
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -165,13 +165,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// the same bytes land at the same CTA-relative shared-memory offset of every CTA in `mask`, and each
-// destination's mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
-                                                   uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
-}
 // L2 eviction-priority policies: the CTA-private activation scratch and the weights must stay in L2
 // (evict_last); an activation tile's final read and the spectrum output are streaming (evict_first)
 __device__ __forceinline__ uint64_t policy_evict_last() {
@@ -187,11 +180,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_multicast_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
-                                                        uint16_t mask, uint64_t pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void st_global_v4_hint(void* ptr, const uint4& v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
@@ -213,14 +201,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // 2-CTA MMA: D[256 x N] (128 rows in each CTA's TMEM) += A[256 x 16] (128 rows from each CTA's smem)
 // x B[N x 16] (N/2 rows from each CTA's smem).  Issued by one thread of the leader CTA only.
 __device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -242,57 +222,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t target_c
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(target_cta));
     return raddr;
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t target_cta) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(bar, target_cta)) : "memory");
-}
 // pure event signal (no data of this thread is published through it): no release fence on the issue path
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t raddr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok;
-}
-// wait on a barrier that CTAs of the cluster arrive on remotely
-__device__ __noinline__ long long mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag, int code) {
-    if (mbar_try_wait_cluster(bar, parity)) return 0;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > CPB_WATCHDOG_CYCLES) {
-            if (error_flag) atomicExch(error_flag, code);
-            __threadfence_system();
-            __trap();
-        }
-    }
-    return clock64() - t0;
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// arrive (once the MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-// 16 lanes x (2 x 256 bit): thread t gets, for column group i in {0,1}: v[4i+0..1] = (lane t/4, cols 8i+2(t%4)+{0,1}),
-// v[4i+2..3] = (lane t/4+8, same cols)
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-        : "r"(taddr) : "memory");
 }
 // 16 lanes x (4 x 256 bit): thread t gets, for column group i in 0..3: v[4i+0..1] = (lane t/4, cols 8i+2(t%4)+{0,1}),
 // v[4i+2..3] = (lane t/4+8, same cols)
@@ -303,26 +235,6 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&a)[16], uint32_t (&b)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
-                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
-                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
-                   "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
-                 :: "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait16x(uint32_t (&a)[8], uint32_t (&b)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
-                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
-                 :: "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&v)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
-                 :: "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait for outstanding tcgen05.ld; the registers are listed as in/out so that no use of them can be
 // scheduled above the wait
 __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
@@ -368,10 +280,6 @@ __device__ __forceinline__ uint32_t umma_idesc(int nc) {
     return (1u << 4) | (static_cast<uint32_t>(nc >> 3) << 17) | (static_cast<uint32_t>((UM_CLUSTER * UM_TILE_M) >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
 // split two floats into fp16 hi and lo parts (hi = rn(x), lo = rn(x - hi)), packed as half2
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     __half2 h = __floats2half2_rn(a, b);
@@ -573,21 +481,20 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const uint32_t bars = base + UM_SMEM_BARS;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (UM_STAGES + s); };
-    auto bar_peerfull = [&](int s) { return bars + 8u * (2 * UM_STAGES + s); };   // leader only: the peer's stage has landed
-    auto bar_accfull = [&](int b) { return bars + 8u * (3 * UM_STAGES + b); };
-    auto bar_accempty = [&](int b) { return bars + 8u * (3 * UM_STAGES + 2 + b); }; // leader only: both CTAs' epilogues arrive
-    auto bar_aready = [&](int t) { return bars + 8u * (3 * UM_STAGES + 4 + t); };
-    auto bar_a0ready = [&](int t) { return bars + 8u * (3 * UM_STAGES + 6 + t); };
-    auto bar_a0free = [&](int t) { return bars + 8u * (3 * UM_STAGES + 8 + t); };
-    auto bar_parfull = [&](int b) { return bars + 8u * (3 * UM_STAGES + 10 + b); };
-    auto bar_parempty = [&](int b) { return bars + 8u * (3 * UM_STAGES + 12 + b); };
+    auto bar_accfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + b); };
+    auto bar_accempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 2 + b); }; // leader only: both CTAs' epilogues arrive
+    auto bar_aready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 4 + t); };
+    auto bar_a0ready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 6 + t); };
+    auto bar_a0free = [&](int t) { return bars + 8u * (2 * UM_STAGES + 8 + t); };
+    auto bar_parfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + 10 + b); };
+    auto bar_parempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 12 + b); };
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbase + UM_SMEM_TMEMPTR);
 
     if (threadIdx.x == 0) {
         // the leader's "full" barrier of a stage completes when its own copies have landed (arrive.expect_tx by
         // its loader) AND the peer's relay has reported the peer's copies (one remote arrive): one wait per stage
         const uint32_t full_count = (UM_CLUSTER > 1 && cluster_ctarank() == 0) ? 2 : 1;
-        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), full_count); mbar_init(bar_empty(s), 1); mbar_init(bar_peerfull(s), 1); }
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), full_count); mbar_init(bar_empty(s), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS);
             mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS);
@@ -702,18 +609,18 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         if (lane == 0 && cta_rank != 0) {
             // the peer's operands live in its own shared memory: tell the leader when each stage has landed
             int stage = 0; uint32_t ph_full = 0;
-            const uint32_t peerfull0 = map_to_cta(bar_full(0), 0);        // the leader's full barriers
+            const uint32_t leader_full0 = map_to_cta(bar_full(0), 0);     // the leader's full barriers
             UM_FOR_EACH_JOB({
                 (void)t;
                 const int ks = P.g[g].k_stages;
                 for (int i = 0; i < ks; ++i) {
                     mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
-                    mbar_arrive_remote_relaxed(peerfull0 + 8u * stage);
+                    mbar_arrive_remote_relaxed(leader_full0 + 8u * stage);
                     if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                 }
             })
         } else if (lane == 0) {
-            long long w_full = 0, w_accempty = 0, w_peer = 0; const long long t_begin = now();
+            long long w_full = 0, w_accempty = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_full = 0;
             uint32_t ph_accempty[2] = {1, 1};
             int job = 0;
@@ -752,7 +659,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             })
             if (PROF && P.counters) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
-                cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty; cnt[UM_CNT_MMA_WAIT_PEERFULL] = w_peer;
+                cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty;
                 cnt[UM_CNT_MMA_TOTAL] = now() - t_begin;
             }
         }

@@ -12,7 +12,7 @@ import cosmopower_b200 as cp  # noqa: E402
 from cosmopower_b200 import priors, standins  # noqa: E402
 
 NAMES = ["load_wait_empty", "load_wait_aready", "load_total", "mma_wait_full", "mma_wait_accempty", "mma_total",
-         "epi_wait_accfull", "epi_act", "epi_out", "epi_total", "in_wait", "in_total", "mma_wait_peerfull"]
+         "epi_wait_accfull", "epi_act", "epi_out", "epi_total", "in_wait", "in_total"]
 
 
 def main():
