@@ -61,7 +61,7 @@ struct Gemm {
     float4* depi = nullptr;
 };
 
-constexpr int64_t HOST_CHUNK_BYTES = 64ll << 20;   // output bytes per pipelined host chunk
+constexpr int64_t HOST_CHUNK_BYTES = 128ll << 20;  // output bytes per pipelined host chunk
 
 }  // namespace
 

@@ -1,0 +1,56 @@
+"""Extract the judged subset of an `ncu --set full` report into profiles/<tag>_ncu_full_summary.csv
+and refresh profiles/traffic.json.
+
+usage: python tools/ncu_summary.py gpurun_out/prof_full.ncu-rep r1e
+"""
+import csv
+import io
+import json
+import re
+import subprocess
+import sys
+
+KEEP = re.compile(
+    r"pipe_tensor|dram__bytes_(read|write)\.sum$|dram__throughput|lts__t_(bytes|sectors)\.sum$|"
+    r"lts__t_sector_hit_rate|lts__throughput|l1tex__throughput|gpu__time_duration\.sum|"
+    r"sm__throughput|sm__cycles_elapsed\.(avg|max)$|sm__cycles_active\.avg$|sm__warps_active|"
+    r"launch__(registers_per_thread|grid_size|block_size|cluster|shared_mem_per_block_dynamic|occupancy_limit)|"
+    r"smsp__inst_executed\.sum$|sm__inst_executed_pipe_(xu|fma|alu|lsu|uniform)|smsp__issue_active|"
+    r"l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum$|l1tex__data_bank_conflicts_pipe_lsu_mem_shared\.sum$|"
+    r"smsp__average_warp.*issue_stalled.*_per_warp_active|sm__clock|gpc__cycles_elapsed\.max")
+
+
+def main():
+    rep, tag = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], check=True,
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    names, units = rows[0], rows[1]
+    launch = rows[2]
+    kname = launch[names.index("Kernel Name")] if "Kernel Name" in names else "?"
+    out = [("metric", "unit", "value")]
+    vals = {}
+    for n, u, v in zip(names, units, launch):
+        if KEEP.search(n):
+            out.append((n, u, v))
+        vals[n] = (u, v)
+    path = f"profiles/{tag}_ncu_full_summary.csv"
+    with open(path, "w", newline="") as f:
+        csv.writer(f).writerows(out)
+
+    def to_bytes(n):
+        u, v = vals[n]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+        return float(v.replace(",", "")) * scale
+
+    traffic = {"kernel": kname, "launch": "cmb_TT_NN stand-in, 1048576 rows, ten_to",
+               "dram_bytes_read": to_bytes("dram__bytes_read.sum"),
+               "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
+               "source": f"{path} (ncu --set full, one launch)"}
+    with open("profiles/traffic.json", "w") as f:
+        json.dump(traffic, f)
+    print(path, len(out) - 1, "metrics;", traffic)
+
+
+if __name__ == "__main__":
+    main()
