@@ -327,7 +327,8 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.n_jobs = e->n_jobs;
     p.error_flag = e->d_error_flag;
     p.counters = e->d_counters;
-    const int max_clusters = e->num_sms / cpb::UM_CLUSTER;
+    int max_clusters = e->num_sms / cpb::UM_CLUSTER;
+    if (const char* cap = getenv("CPB200_DEBUG_MAX_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(cap)));  // tuning aid
     const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * cpb::UM_CLUSTER;
     if (p.counters) cpb::fused_mlp_umma_kernel<true><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
     else cpb::fused_mlp_umma_kernel<false><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
@@ -603,7 +604,7 @@ int cpb200_engine_info(const cpb200_engine* e, int32_t* n_parameters, int32_t* n
 int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int32_t capacity) {
     if (!e) return fail(CPB200_E_INVALID, "null engine");
     DeviceGuard guard(e->device);
-    const size_t n = static_cast<size_t>(e->num_sms) * cpb::UM_CNT_SLOTS;
+    const size_t n = static_cast<size_t>(e->num_sms + cpb::UM_MAX_JOBS) * cpb::UM_CNT_SLOTS;   // per-CTA rows, then per-job rows
     if (out && e->d_counters) {
         CU(cudaDeviceSynchronize());
         std::vector<long long> h(n);

@@ -64,9 +64,10 @@ constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre
 
 // shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int UM_SMEM_STAGES = 0;
-constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // 2 x 256 float4
-constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + 2 * UM_MAX_NC * 16;
-constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 4;
+constexpr int UM_PAR_SLOTS = 4;          // ring of per-chunk epilogue constants: deep enough that the loader never waits for an epilogue
+constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // UM_PAR_SLOTS x 256 float4
+constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + UM_PAR_SLOTS * UM_MAX_NC * 16;
+constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 2 * UM_PAR_SLOTS;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_MAX_JOBS = 96;
 constexpr int UM_SMEM_JOBS = UM_SMEM_TMEMPTR + 16;
@@ -113,6 +114,12 @@ enum { UM_CNT_LOAD_WAIT_EMPTY = 0, UM_CNT_LOAD_WAIT_AREADY = 1, UM_CNT_LOAD_TOTA
        UM_CNT_MMA_WAIT_FULL = 3, UM_CNT_MMA_WAIT_ACCEMPTY = 4, UM_CNT_MMA_TOTAL = 5,
        UM_CNT_EPI_WAIT_ACCFULL = 6, UM_CNT_EPI_ACT = 7, UM_CNT_EPI_OUT = 8, UM_CNT_EPI_TOTAL = 9,
        UM_CNT_IN_WAIT = 10, UM_CNT_IN_TOTAL = 11, UM_CNT_SLOTS = 16 };
+// After the per-CTA slots the counter buffer holds UM_MAX_JOBS rows of UM_CNT_SLOTS values written by CTA 0
+// only: per job-table entry, waits summed over all iterations plus one iteration's time stamps.
+enum { UM_JOB_MMA_WAIT_FULL = 0, UM_JOB_MMA_WAIT_ACCEMPTY = 1, UM_JOB_MMA_BUSY = 2, UM_JOB_EPI_WAIT = 3,
+       UM_JOB_EPI_BUSY = 4, UM_JOB_LOAD_WAIT_AREADY = 5, UM_JOB_LOAD_WAIT_EMPTY = 6,
+       UM_JOB_T_MMA0 = 8, UM_JOB_T_MMA1 = 9, UM_JOB_T_EPI0 = 10, UM_JOB_T_EPI1 = 11, UM_JOB_T_LOAD0 = 12,
+       UM_JOB_T_LOAD1 = 13, UM_JOB_TRACE_ITERATION = 3 };
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -487,7 +494,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     auto bar_a0ready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 6 + t); };
     auto bar_a0free = [&](int t) { return bars + 8u * (2 * UM_STAGES + 8 + t); };
     auto bar_parfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + 10 + b); };
-    auto bar_parempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 12 + b); };
+    auto bar_parempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 10 + UM_PAR_SLOTS + b); };
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbase + UM_SMEM_TMEMPTR);
 
     if (threadIdx.x == 0) {
@@ -495,10 +502,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         // its loader) AND the peer's relay has reported the peer's copies (one remote arrive): one wait per stage
         const uint32_t full_count = (UM_CLUSTER > 1 && cluster_ctarank() == 0) ? 2 : 1;
         for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), full_count); mbar_init(bar_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS);
-            mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS);
-        }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS); }
+        for (int b = 0; b < UM_PAR_SLOTS; ++b) { mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS); }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar_aready(t), UM_EPI_WARPS);
             mbar_init(bar_a0ready(t), 1);
@@ -566,20 +571,22 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         if (lane == 0) {
             long long w_empty = 0, w_aready = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_empty = 1;                 // fresh "empty" barriers pass at parity 1
-            uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0}, ph_parempty[2] = {1, 1};
+            uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0};
+            uint32_t ph_parempty = (1u << UM_PAR_SLOTS) - 1;      // one phase bit per slot
             const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
             int job = 0;
             UM_FOR_EACH_JOB({
                 const UmmaGemm& L = P.g[g];
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
+                const long long j_t0 = now(), j_we0 = w_empty, j_wa0 = w_aready;
                 if (c == 0) {                                     // the whole K extent of this tile's operand must be written
                     if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1; }
                     else { w_aready += mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1; }
                 }
                 const uint8_t* a_src = g == 0 ? a0_buf(t) : in_buf(g, t, pidx);
-                {   // this chunk's per-column epilogue constants -> shared memory (ring of 2 by job parity)
-                    const int pb = job & 1;
-                    w_empty += mbar_wait(bar_parempty(pb), ph_parempty[pb], P.error_flag, 104); ph_parempty[pb] ^= 1;
+                {   // this chunk's per-column epilogue constants -> shared memory (ring indexed by the job count)
+                    const int pb = job & (UM_PAR_SLOTS - 1);
+                    w_empty += mbar_wait(bar_parempty(pb), (ph_parempty >> pb) & 1, P.error_flag, 104); ph_parempty ^= 1u << pb;
                     mbar_arrive_expect_tx(bar_parfull(pb), L.nc * 16u);
                     bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), L.epi + c * L.nc, L.nc * 16u, bar_parfull(pb));
                 }
@@ -595,6 +602,11 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes + cta_rank * (b_bytes / 2),
                                   b_bytes / 2, bar_full(stage), pol_keep);
                     if (++stage == UM_STAGES) { stage = 0; ph_empty ^= 1; }
+                }
+                if (PROF && P.counters && blockIdx.x == 0) {
+                    long long* jc = P.counters + (gridDim.x + ji) * UM_CNT_SLOTS;
+                    jc[UM_JOB_LOAD_WAIT_AREADY] += w_aready - j_wa0; jc[UM_JOB_LOAD_WAIT_EMPTY] += w_empty - j_we0;
+                    if (it == UM_JOB_TRACE_ITERATION) { jc[UM_JOB_T_LOAD0] = j_t0; jc[UM_JOB_T_LOAD1] = now(); }
                 }
                 ++job;
             })
@@ -629,6 +641,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const uint32_t idesc = umma_idesc(L.nc);
                 const uint32_t b_half = static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u;     // bytes of one (hi or lo) half tile
                 const int buf = job & 1;
+                const long long j_t0 = now(), j_wf0 = w_full, j_wa0 = w_accempty;
                 // (a cluster-scope acquire would cost an L1 invalidate per wait on the issue path; the peer
                 // only hands back TMEM it has finished reading - tcgen05.wait::ld precedes its arrive)
                 w_accempty += mbar_wait(bar_accempty(buf), ph_accempty[buf], P.error_flag, 201); ph_accempty[buf] ^= 1;
@@ -655,6 +668,13 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 }
                 umma_commit_2cta(bar_accfull(buf));               // both CTAs' epilogues may drain their 128 rows
                 if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
+                if (PROF && P.counters && blockIdx.x == 0) {
+                    long long* jc = P.counters + (gridDim.x + ji) * UM_CNT_SLOTS;
+                    const long long j_t1 = now();
+                    jc[UM_JOB_MMA_WAIT_FULL] += w_full - j_wf0; jc[UM_JOB_MMA_WAIT_ACCEMPTY] += w_accempty - j_wa0;
+                    jc[UM_JOB_MMA_BUSY] += j_t1 - j_t0; jc[UM_CNT_SLOTS - 1] = jw;
+                    if (it == UM_JOB_TRACE_ITERATION) { jc[UM_JOB_T_MMA0] = j_t0; jc[UM_JOB_T_MMA1] = j_t1; }
+                }
                 ++job;
             })
             if (PROF && P.counters) {
@@ -716,7 +736,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         const int tq = lane >> 2, tr = lane & 3;     // fragment coordinates: rows tq, tq+8 (+16 for the 2nd load); cols 2*tr, 2*tr+1
         // 16-byte output stores need a 16-byte aligned base and a row pitch that is a multiple of 4 floats
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(P.out) & 15) | (static_cast<uintptr_t>(P.out_pitch) & 3)) == 0;
-        uint32_t ph_accfull[2] = {0, 0};
+        uint32_t ph_accfull[2] = {0, 0}, ph_parfull = 0;
         long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = now();
         int job = 0;
         EpiCtx E;
@@ -727,8 +747,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             E.nc = L.nc;
             const long long row0 = (pair * 2 + t) * UM_TILE_M;
             const int buf = job & 1;
-            E.par = epipar + buf * UM_MAX_NC;                 // filled by the loader's bulk copy
-            w_accfull += mbar_wait(bar_parfull(buf), ph_accfull[buf], P.error_flag, 402);
+            const int pb = job & (UM_PAR_SLOTS - 1);
+            E.par = epipar + pb * UM_MAX_NC;                  // filled by the loader's bulk copy
+            const long long j_w0 = w_accfull;
+            w_accfull += mbar_wait(bar_parfull(pb), (ph_parfull >> pb) & 1, P.error_flag, 402); ph_parfull ^= 1u << pb;
             w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
             tc_fence_after();
             const long long t_job = now();
@@ -765,10 +787,16 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             if (lane == 0) {
                 if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
                 else mbar_arrive_remote_relaxed(accempty_leader0 + 8u * buf);   // TMEM reads are complete (wait::ld)
-                mbar_arrive(bar_parempty(buf));
+                mbar_arrive(bar_parempty(pb));
                 if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
             }
             if (L.epi_kind == EPI_OUT) c_out += now() - t_job; else c_act += now() - t_job;
+            if (PROF && P.counters && blockIdx.x == 0 && ew == 0 && lane == 0) {
+                long long* jc = P.counters + (gridDim.x + ji) * UM_CNT_SLOTS;
+                const long long j_t1 = now();
+                jc[UM_JOB_EPI_WAIT] += w_accfull - j_w0; jc[UM_JOB_EPI_BUSY] += j_t1 - t_job;
+                if (it == UM_JOB_TRACE_ITERATION) { jc[UM_JOB_T_EPI0] = t_job; jc[UM_JOB_T_EPI1] = j_t1; }
+            }
             ++job;
         })
         if (PROF && P.counters && ew == 0 && lane == 0) {

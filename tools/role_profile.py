@@ -37,9 +37,26 @@ def main():
     ms = e0.elapsed_time(e1)
     print("%s rows=%d: %.3f ms, %.3g spectra/s" % (name, rows, ms, rows / ms * 1e3))
     tot = c[:, 5].max()
+    lead = c[: c.shape[0] - 96, 5]
+    lead = lead[lead > 0]
+    print("median over leader CTAs of the MMA role total = %.0f cycles (clock-independent figure of merit)" % np.median(lead))
     print("max over CTAs of the MMA role total = %.3g cycles -> %.0f MHz effective (leader CTAs only record MMA counters)" % (tot, tot / ms / 1e3))
+    ncta = c.shape[0] - 96                     # per-CTA rows, then 96 per-job rows written by CTA 0
+    jobs = c[ncta:]
+    c = c[:ncta]
     for i, n in enumerate(NAMES):
         print("  %-18s mean %12.0f  (%5.1f%% of mma_total)  min %12.0f max %12.0f" % (n, c[:, i].mean(), 100 * c[:, i].mean() / tot, c[:, i].min(), c[:, i].max()))
+    print("per job-table entry of CTA 0 (cycles summed over its iterations; time stamps of iteration 3 relative to the first):")
+    print("  ji  g t  c nxt | mma: wait_full wait_accempty     busy | epi:     wait     busy | load: wait_aready wait_empty | t_mma0  t_mma1  t_epi0  t_epi1 t_load0 t_load1")
+    t0 = min(x for x in jobs[:, 8] if x > 0) if (jobs[:, 8] > 0).any() else 0
+    for ji in range(96):
+        r = jobs[ji]
+        if r[2] == 0:
+            continue
+        jw = int(r[15])
+        ts = ["%7d" % (x - t0) if x > 0 else "      -" for x in r[8:14]]
+        print("  %2d %2d %d %2d  %d  | %14.0f %13.0f %8.0f | %13.0f %8.0f | %17.0f %10.0f | %s" % (
+            ji, jw & 255, (jw >> 8) & 255, (jw >> 16) & 255, jw >> 24, r[0], r[1], r[2], r[3], r[4], r[5], r[6], " ".join(ts)))
 
 
 if __name__ == "__main__":
