@@ -79,7 +79,7 @@ struct cpb200_engine {
     unsigned long long um_scratch_cta = 0;
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
     int* d_error_flag = nullptr;
-    unsigned* d_jobs = nullptr;         // job table of the fused kernel (build_jobs)
+    std::vector<unsigned> jobs;         // job table of the fused kernel (build_jobs), passed in the kernel parameters
     int n_jobs = 0;
     long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
     // host pipeline
@@ -193,14 +193,7 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
             // (tcgen05.ld.16x256b fragment); the map is its own inverse
             const int c = n / g.nc, nl = n % g.nc, s = k / cpb::UM_KS, kk = k % cpb::UM_KS;
             const int nb = nl & 31;
-            int nn;
-            if (g.epi == cpb::EPI_OUT) {
-                // output layers: a lane owns logical columns 4t..4t+3 and 16+4t..16+4t+3 (two 16-byte stores)
-                const int t4 = (nb & 15) >> 2, j = (nb & 3) | ((nb >> 4) << 2);
-                nn = (nl & ~31) | ((j >> 1) << 3) | (t4 << 1) | (j & 1);
-            } else {
-                nn = (nl & ~31) | (((nb >> 1) & 3) << 3) | ((nb >> 3) << 1) | (nb & 1);
-            }
+            const int nn = (nl & ~31) | (((nb >> 1) & 3) << 3) | ((nb >> 3) << 1) | (nb & 1);
             const int half = g.nc / 2, r = nn / half, nh = nn % half;          // which CTA of the pair holds this column
             const size_t base = (static_cast<size_t>(c) * g.k_stages + s) * 4 * tile + static_cast<size_t>(r) * 2 * tile;
             const size_t off = static_cast<size_t>(nh / 8) * 256 + (kk / 8) * 64 + (nh % 8) * 8 + (kk % 8);
@@ -209,27 +202,39 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
         }
     }
     // Epilogue constants, stored in the order the epilogue lanes read them: inside each 32-column block lane
-    // group t (= lane & 3) owns 8 logical columns - 8t..8t+7 for operand-producing layers, 4t..4t+3 and
-    // 16+4t..16+4t+3 for output layers - and its j-th value sits at position 4j + t.
-    std::vector<float4> epi(static_cast<size_t>(g.n_chunks) * g.nc, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int n = 0; n < g.N; ++n) {
-        const int nb = n & 31;
-        int t, j;
-        if (g.epi == cpb::EPI_OUT) { t = (nb & 15) >> 2; j = (nb & 3) | ((nb >> 4) << 2); }
-        else { t = nb >> 3; j = nb & 7; }
-        float4& dst = epi[(n & ~31) + 4 * j + t];
-        if (g.epi == cpb::EPI_ACT) {
-            const float alpha = g.p1[n], beta = g.p2[n];
-            // a = acc*acc_scale + b;  h*s_out = ((1-beta)*s_out * sigmoid + beta*s_out) * a
-            dst = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
-                              beta * s_out, (1.f - beta) * s_out);
-        } else if (g.epi == cpb::EPI_AFFINE) {
-            dst = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
-        } else {
-            // {scale, shift} for predictions; {scale, shift} * log2(10) for 10**y = 2**(y*log2 10)
-            const double l2_10 = 3.321928094887362;
-            dst = make_float4(g.p0[n] * inv, g.p1[n], static_cast<float>(static_cast<double>(g.p0[n]) * inv * l2_10),
-                              static_cast<float>(static_cast<double>(g.p1[n]) * l2_10));
+    // group t (= lane & 3) owns the 8 logical columns 8t..8t+7.  Operand-producing layers: one float4 per column,
+    // the group's j-th column at position 4j + t.  Output layers: {scale, shift} pairs, two columns per float4,
+    // the group's m-th pair (columns 8t+2m, 8t+2m+1) at position 4m + t of the block's 16 float4; the whole
+    // array once for predictions and once more multiplied by log2(10) for 10**y = 2**(y*log2 10).
+    std::vector<float4> epi;
+    if (g.epi == cpb::EPI_OUT) {
+        const size_t per_variant = static_cast<size_t>(g.n_chunks) * (g.nc / 2);
+        epi.assign(2 * per_variant, make_float4(0.f, 0.f, 0.f, 0.f));
+        const double l2_10 = 3.321928094887362;
+        for (int n = 0; n < g.N; ++n) {
+            const int nb = n & 31, t = nb >> 3, m = (nb & 7) >> 1;
+            const size_t idx = static_cast<size_t>(n >> 5) * 16 + 4 * m + t;
+            const float sc = g.p0[n] * inv, sh = g.p1[n];
+            const float sc10 = static_cast<float>(static_cast<double>(g.p0[n]) * inv * l2_10);
+            const float sh10 = static_cast<float>(static_cast<double>(g.p1[n]) * l2_10);
+            float4& a = epi[idx];
+            float4& b10 = epi[per_variant + idx];
+            if (n & 1) { a.z = sc; a.w = sh; b10.z = sc10; b10.w = sh10; }
+            else { a.x = sc; a.y = sh; b10.x = sc10; b10.y = sh10; }
+        }
+    } else {
+        epi.assign(static_cast<size_t>(g.n_chunks) * g.nc, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int n = 0; n < g.N; ++n) {
+            const int nb = n & 31, t = nb >> 3, j = nb & 7;
+            float4& dst = epi[(n & ~31) + 4 * j + t];
+            if (g.epi == cpb::EPI_ACT) {
+                const float alpha = g.p1[n], beta = g.p2[n];
+                // a = acc*acc_scale + b;  h*s_out = ((1-beta)*s_out * sigmoid + beta*s_out) * a
+                dst = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
+                                  beta * s_out, (1.f - beta) * s_out);
+            } else {
+                dst = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
+            }
         }
     }
     if (int rc = upload(&g.dwpack, pack.data(), pack.size())) return rc;
@@ -310,6 +315,8 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.n_modes = e->n_modes;
     p.ten_to = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
     p.accumulate = (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0;
+    p.debug_flags = 0;
+    if (e->d_counters) if (const char* dbg = getenv("CPB200_DEBUG_EPILOGUE")) p.debug_flags = atoi(dbg);   // profiling ablations
     p.params = params;
     p.pmean = e->d_pmean;
     p.pstd = e->d_pstd;
@@ -323,7 +330,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.scratch_cta_bytes = e->um_scratch_cta;
     p.a0_bytes = e->um_a0_bytes;
     p.abuf_bytes = e->um_abuf_bytes;
-    p.jobs = e->d_jobs;
+    for (int i = 0; i < e->n_jobs; ++i) p.jobs[i] = e->jobs[i];
     p.n_jobs = e->n_jobs;
     p.error_flag = e->d_error_flag;
     p.counters = e->d_counters;
@@ -441,7 +448,7 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
             if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
                 return bail(fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
             e->n_jobs = static_cast<int>(jobs.size());
-            if ((rc = upload(&e->d_jobs, jobs.data(), jobs.size()))) return bail(rc);
+            e->jobs = jobs;
         }
         const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
         if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
@@ -476,7 +483,7 @@ int cpb200_destroy(cpb200_engine* e) {
     }
     cudaFree(e->d_pmean); cudaFree(e->d_pstd);
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
-    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters); cudaFree(e->d_jobs);
+    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters);
     for (int i = 0; i < 2; ++i) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);
@@ -604,7 +611,8 @@ int cpb200_engine_info(const cpb200_engine* e, int32_t* n_parameters, int32_t* n
 int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int32_t capacity) {
     if (!e) return fail(CPB200_E_INVALID, "null engine");
     DeviceGuard guard(e->device);
-    const size_t n = static_cast<size_t>(e->num_sms + cpb::UM_MAX_JOBS) * cpb::UM_CNT_SLOTS;   // per-CTA rows, then per-job rows
+    const size_t n = static_cast<size_t>(e->num_sms + cpb::UM_MAX_JOBS) * cpb::UM_CNT_SLOTS      // per-CTA rows, then per-job rows,
+                     + static_cast<size_t>(cpb::UM_MAX_JOBS) * cpb::UM_TRACE_STAGES * 2;                // then the stage trace
     if (out && e->d_counters) {
         CU(cudaDeviceSynchronize());
         std::vector<long long> h(n);

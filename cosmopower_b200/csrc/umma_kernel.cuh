@@ -70,8 +70,7 @@ constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + UM_PAR_SLOTS * UM_MAX_NC * 16;
 constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 2 * UM_PAR_SLOTS;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_MAX_JOBS = 96;
-constexpr int UM_SMEM_JOBS = UM_SMEM_TMEMPTR + 16;
-constexpr int UM_SMEM_BYTES = UM_SMEM_JOBS + UM_MAX_JOBS * 4 + 1024;         // + alignment slack
+constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // + alignment slack
 
 struct UmmaGemm {
     const __half* wpack;   // [n_chunks][k_stages][CTA0: hi|lo half tiles][CTA1: hi|lo half tiles], core-matrix order
@@ -90,6 +89,7 @@ struct UmmaParams {
     int n_parameters;
     int n_modes;
     int ten_to;
+    int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM (results are garbage)
     int accumulate;            // output layers add the log10 values already in `out` before the optional 10**
     const float* params;       // (n_rows, n_parameters)
     const float* pmean;
@@ -103,7 +103,8 @@ struct UmmaParams {
     unsigned long long scratch_cta_bytes;
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
     unsigned abuf_bytes;       // per activation buffer: max k_stages(gemm >= 1) * 16384; a CTA owns UM_ACT_BUFS of them
-    const unsigned* jobs;      // job table: g | t << 8 | c << 16 | next << 24 (see cpb200_api.cu build_jobs)
+    unsigned jobs[UM_MAX_JOBS];   // job table: g | t << 8 | c << 16 | next << 24 (cpb200_api.cu build_jobs); lives in the
+                                  // constant bank with the other parameters, so every role decodes it with uniform loads
     int n_jobs;
     int* error_flag;           // set to a code by the watchdog before trapping
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
@@ -119,7 +120,9 @@ enum { UM_CNT_LOAD_WAIT_EMPTY = 0, UM_CNT_LOAD_WAIT_AREADY = 1, UM_CNT_LOAD_TOTA
 enum { UM_JOB_MMA_WAIT_FULL = 0, UM_JOB_MMA_WAIT_ACCEMPTY = 1, UM_JOB_MMA_BUSY = 2, UM_JOB_EPI_WAIT = 3,
        UM_JOB_EPI_BUSY = 4, UM_JOB_LOAD_WAIT_AREADY = 5, UM_JOB_LOAD_WAIT_EMPTY = 6,
        UM_JOB_T_MMA0 = 8, UM_JOB_T_MMA1 = 9, UM_JOB_T_EPI0 = 10, UM_JOB_T_EPI1 = 11, UM_JOB_T_LOAD0 = 12,
-       UM_JOB_T_LOAD1 = 13, UM_JOB_TRACE_ITERATION = 3 };
+       UM_JOB_T_LOAD1 = 13, UM_JOB_TRACE_ITERATION = 3, UM_TRACE_STAGES = 16 };
+// ... followed by UM_MAX_JOBS x UM_TRACE_STAGES x 2 time stamps of the traced iteration: per K stage, when the
+// loader issued its copies and when the MMA issuer saw them landed.
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -167,6 +170,12 @@ __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, in
     if (mbar_try_wait(bar, parity)) return clock64() - t0;
     mbar_wait_slow(bar, parity, error_flag, code);
     return clock64() - t0;
+}
+// true in exactly one lane of a converged warp; code under it can use the warp's uniform values directly
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -317,6 +326,7 @@ struct EpiCtx {
     int chunk_col0;          // c * nc
     int q, tq, tr;
     const float4* par;       // the chunk's per-column constants in shared memory (logical column order)
+    int dbg;                 // profiling ablations (always 0 in the production instantiation): 4 = no global stores, 8 = no constant loads
 };
 
 // hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
@@ -325,7 +335,7 @@ struct EpiCtx {
 // v[4i + 2rr + cc] = (row 8rr + tq, lane value j = 2i + cc).
 template <int KIND>
 __device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const float4 (&pp)[8], float acc_scale,
-                                                 uint8_t* dst, uint64_t pol_keep) {
+                                                 uint8_t* dst, uint64_t pol_keep, int dbg) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
         // written stage by stage (all 8 values through each step) so that the MUFU latencies of the
@@ -351,6 +361,7 @@ __device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const 
         split2(hv[4], hv[5], hi.z, lo.z);
         split2(hv[6], hv[7], hi.w, lo.w);
         // rows +8rr: 64 B per row; a warp store covers 8 rows x 64 B = 4 full lines
+        if (dbg & 4) { if (hi.x == 0x7fff7fffu && lo.y == 0x12345u) st_global_v4_hint(dst, hi, pol_keep); continue; }
         st_global_v4_hint(dst + rr * 512, hi, pol_keep);
         st_global_v4_hint(dst + rr * 512 + UM_A_HALF_BYTES, lo, pol_keep);
     }
@@ -374,22 +385,35 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
         // the four lane groups read 64 contiguous bytes - no shared-memory bank conflicts
         float4 pp[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pp[j] = E.par[pc + 4 * j + E.tr];
+        for (int j = 0; j < 8; ++j) pp[j] = (E.dbg & 8) ? make_float4(0.1f, -1.f, 0.5f, 0.5f) : E.par[pc + 4 * j + E.tr];
         const int kk = E.chunk_col0 + lcol0 + pc;                      // next layer's k index of this lane's 8 values
         // (kk % 32) >> 3 == tr; rows 32q + 16h + 8rr + tq share (row >> 1) & 3 == (tq >> 1) & 3
         uint8_t* dst = a_dst + static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(E.q * 32 + E.tq, E.tr);
         tmem_ld_wait16(va);
         tmem_ld_16x256b_x4(t_addr1 + pc, vb);
-        epi_operand_half<KIND>(va, pp, acc_scale, dst, pol_keep);
+        epi_operand_half<KIND>(va, pp, acc_scale, dst, pol_keep, E.dbg);
         tmem_ld_wait16(vb);
         if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
-        epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep);          // rows +16
+        epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep, E.dbg);          // rows +16
     }
 }
 
+// 32-byte global accesses (sm_100): one lane covers 8 consecutive floats, 4 lanes a full 128-byte line
+__device__ __forceinline__ void stg_cs_v8(float* p, const float (&y)[8]) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]), "f"(y[4]), "f"(y[5]), "f"(y[6]), "f"(y[7]) : "memory");
+}
+__device__ __forceinline__ void ldg_v8(const float* p, float (&y)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(y[0]), "=f"(y[1]), "=f"(y[2]), "=f"(y[3]), "=f"(y[4]), "=f"(y[5]), "=f"(y[6]), "=f"(y[7]) : "l"(p) : "memory");
+}
+
+// store mode of one lane's 8 consecutive output columns
+enum { OUT_SCALAR = 0, OUT_VEC16 = 1, OUT_VEC32 = 2 };
+
 template <bool TEN_TO, bool ACC>
 __device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const float2 (&pp)[8], float* drow, long long pitch,
-                                                bool fast, int row_in_q, long long rows_left, int gc, int n_modes) {
+                                                int mode, int row_in_q, long long rows_left, int gc, int n_modes, int dbg) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
         float y[8];
@@ -400,38 +424,45 @@ __device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const f
         if (ACC) {
             // fused sum of log-spectra (e.g. log P_lin + log boost): add what the previous emulator left in `out`
             const float ks = TEN_TO ? 3.3219280948873623f : 1.f;
-            if (fast) {
-                const float4 p0 = *reinterpret_cast<const float4*>(dst), p1 = *reinterpret_cast<const float4*>(dst + 16);
+            if (mode == OUT_VEC32) {
+                float p[8];
+                ldg_v8(dst, p);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = fmaf(p[j], ks, y[j]);
+            } else if (mode == OUT_VEC16) {
+                const float4 p0 = *reinterpret_cast<const float4*>(dst), p1 = *reinterpret_cast<const float4*>(dst + 4);
                 y[0] = fmaf(p0.x, ks, y[0]); y[1] = fmaf(p0.y, ks, y[1]); y[2] = fmaf(p0.z, ks, y[2]); y[3] = fmaf(p0.w, ks, y[3]);
                 y[4] = fmaf(p1.x, ks, y[4]); y[5] = fmaf(p1.y, ks, y[5]); y[6] = fmaf(p1.z, ks, y[6]); y[7] = fmaf(p1.w, ks, y[7]);
             } else if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j)
                     if (gc + j < n_modes) y[j] = fmaf(dst[j], ks, y[j]);
-                    if (gc + 16 + j < n_modes) y[4 + j] = fmaf(dst[16 + j], ks, y[4 + j]);
-                }
             }
         }
         if (TEN_TO) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = ex2_approx(y[j]);
         }
-        if (fast) {
+        if (dbg & 4) {
+            if (y[0] == 1.2345e-30f && y[5] == 3.4e29f) stg_cs_v8(dst, y);
+        } else if (mode == OUT_VEC32) {
+            stg_cs_v8(dst, y);                 // 8 rows x 128 B per warp instruction: full lines
+        } else if (mode == OUT_VEC16) {
             __stcs(reinterpret_cast<float4*>(dst), make_float4(y[0], y[1], y[2], y[3]));
-            __stcs(reinterpret_cast<float4*>(dst + 16), make_float4(y[4], y[5], y[6], y[7]));
+            __stcs(reinterpret_cast<float4*>(dst + 4), make_float4(y[4], y[5], y[6], y[7]));
         } else if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j)
                 if (gc + j < n_modes) __stcs(dst + j, y[j]);
-                if (gc + 16 + j < n_modes) __stcs(dst + 16 + j, y[4 + j]);
-            }
         }
     }
 }
 
-// output layers: de-standardise (+ 10**y) and store rows of the spectrum.
+// output layers: de-standardise (+ 10**y) and store rows of the spectrum.  Columns are packed like the operand
+// layers' (a lane owns 8 consecutive logical columns), constants are {scale, shift} pairs, two columns per float4,
+// lane-interleaved (float4 4m + tr of a 32-column block = columns 8tr + 2m, 8tr + 2m + 1).
 template <bool TEN_TO, bool ACC>
-__device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, long long pitch, bool fast_rows,
+__device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, long long pitch, int vec_mode,
                                                  long long rows_left, int n_modes) {
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
     constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
@@ -439,26 +470,22 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     uint32_t va[16], vb[16];
     if (pc < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);            // TMEM reads run one half piece ahead of the math
     for (; pc < E.nc; pc += kStep) {
-        // output layers are packed so that lane value j is logical column 4tr + j (j < 4) or 16 + 4tr + (j - 4):
-        // each 16-byte store instruction then covers 64 contiguous bytes per row
-        const int ocol = pc + 4 * E.tr;
         float2 pp[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 p0 = E.par[pc + 4 * j + E.tr], p1 = E.par[pc + 4 * (4 + j) + E.tr];     // lane-interleaved, see epi_chunk_operand
-            // ten_to: 10**y = 2**(y*log2(10)); the factor is folded into .z/.w on the host
-            pp[j] = TEN_TO ? make_float2(p0.z, p0.w) : make_float2(p0.x, p0.y);
-            pp[4 + j] = TEN_TO ? make_float2(p1.z, p1.w) : make_float2(p1.x, p1.y);
+        for (int m = 0; m < 4; ++m) {
+            const float4 q4 = (E.dbg & 8) ? make_float4(1.f, 0.f, 1.f, 0.f) : E.par[(pc >> 1) + 4 * m + E.tr];
+            pp[2 * m] = make_float2(q4.x, q4.y);
+            pp[2 * m + 1] = make_float2(q4.z, q4.w);
         }
-        const int gc = E.chunk_col0 + ocol;
-        const bool fast = fast_rows && gc + 20 <= n_modes;
+        const int gc = E.chunk_col0 + pc + 8 * E.tr;
+        const int mode = gc + 8 <= n_modes ? vec_mode : OUT_SCALAR;
         float* drow = orow0 + gc;                                       // row 32q + tq of the tile
         tmem_ld_wait16(va);
         tmem_ld_16x256b_x4(t_addr1 + pc, vb);
-        epi_output_half<TEN_TO, ACC>(va, pp, drow, pitch, fast, E.q * 32 + E.tq, rows_left, gc, n_modes);
+        epi_output_half<TEN_TO, ACC>(va, pp, drow, pitch, mode, E.q * 32 + E.tq, rows_left, gc, n_modes, E.dbg);
         tmem_ld_wait16(vb);
         if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
-        epi_output_half<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, pitch, fast, E.q * 32 + E.tq + 16, rows_left, gc, n_modes);
+        epi_output_half<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, pitch, mode, E.q * 32 + E.tq + 16, rows_left, gc, n_modes, E.dbg);
     }
 }
 
@@ -482,7 +509,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sbase = smem_raw + (base - raw);
 
-    const int warp = threadIdx.x >> 5;
+    // broadcast values are warp-uniform for the compiler: the issuing roles below then keep their addresses
+    // and descriptors in uniform registers instead of re-broadcasting them before every copy / MMA
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     const uint32_t bars = base + UM_SMEM_BARS;
@@ -511,7 +540,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < P.n_jobs) reinterpret_cast<uint32_t*>(sbase + UM_SMEM_JOBS)[threadIdx.x] = P.jobs[threadIdx.x];
     if (warp == 2) {
         // pair-wide allocation: the same warp of both CTAs issues it; each CTA gets the same 512 columns
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -522,14 +550,13 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     __syncthreads();
     if (UM_CLUSTER > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive / multicast
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t cta_rank = UM_CLUSTER > 1 ? cluster_ctarank() : 0;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+    const uint32_t cta_rank = UM_CLUSTER > 1 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0;
     const long long pg_first = blockIdx.x / UM_CLUSTER, pg_step = gridDim.x / UM_CLUSTER;
     // pair-groups this cluster walks; iteration `it` runs the table's "cur" jobs (contractions >= 1) for
     // pair-group it-1 and its "next" jobs (layer 0) for pair-group it, so a pair's layer-0 epilogues hide
     // behind the previous pair's output phase instead of stalling the tensor pipe at every pair start
     const long long n_my_pg = P.n_pairgroups > pg_first ? (P.n_pairgroups - pg_first + pg_step - 1) / pg_step : 0;
-    const uint32_t* jobtab = reinterpret_cast<const uint32_t*>(sbase + UM_SMEM_JOBS);
     const int n_jobs = P.n_jobs;
 
     uint8_t* cta_scratch = P.scratch + static_cast<unsigned long long>(blockIdx.x) * P.scratch_cta_bytes;
@@ -554,7 +581,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     for (long long it = 0; it <= n_my_pg; ++it) {                                                      \
         const bool has_cur = it >= 1, has_next = it < n_my_pg;                                         \
         for (int ji = 0; ji < n_jobs; ++ji) {                                                          \
-            const uint32_t jw = jobtab[ji];                                                            \
+            const uint32_t jw = P.jobs[ji];                                                              \
             const int g = jw & 0xff, t = (jw >> 8) & 0xff, c = (jw >> 16) & 0xff;                      \
             const bool is_next = (jw >> 24) != 0;                                                      \
             if (is_next ? !has_next : !has_cur) continue;                                              \
@@ -568,49 +595,65 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 
     if (warp == 0) {
         // ===================== loader: bulk copies into the stage ring =====================
-        if (lane == 0) {
+        // The whole warp walks the loop (warp-uniform control flow and values); one elected lane issues.
+        {
             long long w_empty = 0, w_aready = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_empty = 1;                 // fresh "empty" barriers pass at parity 1
-            uint32_t ph_aready[2] = {0, 0}, ph_a0ready[2] = {0, 0};
+            uint32_t ph_aready = 0, ph_a0ready = 0;               // one phase bit per tile
             uint32_t ph_parempty = (1u << UM_PAR_SLOTS) - 1;      // one phase bit per slot
             const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
             int job = 0;
             UM_FOR_EACH_JOB({
                 const UmmaGemm& L = P.g[g];
+                const int k_stages = L.k_stages;
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
                 const long long j_t0 = now(), j_we0 = w_empty, j_wa0 = w_aready;
                 if (c == 0) {                                     // the whole K extent of this tile's operand must be written
-                    if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), ph_a0ready[t], P.error_flag, 101); ph_a0ready[t] ^= 1; }
-                    else { w_aready += mbar_wait(bar_aready(t), ph_aready[t], P.error_flag, 102); ph_aready[t] ^= 1; }
+                    if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), (ph_a0ready >> t) & 1, P.error_flag, 101); ph_a0ready ^= 1u << t; }
+                    else { w_aready += mbar_wait(bar_aready(t), (ph_aready >> t) & 1, P.error_flag, 102); ph_aready ^= 1u << t; }
                 }
                 const uint8_t* a_src = g == 0 ? a0_buf(t) : in_buf(g, t, pidx);
                 {   // this chunk's per-column epilogue constants -> shared memory (ring indexed by the job count)
                     const int pb = job & (UM_PAR_SLOTS - 1);
                     w_empty += mbar_wait(bar_parempty(pb), (ph_parempty >> pb) & 1, P.error_flag, 104); ph_parempty ^= 1u << pb;
-                    mbar_arrive_expect_tx(bar_parfull(pb), L.nc * 16u);
-                    bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), L.epi + c * L.nc, L.nc * 16u, bar_parfull(pb));
+                    // operand layers: one float4 per column; output layers: {scale, shift} pairs, two columns per
+                    // float4, in two variants (plain, then pre-multiplied by log2(10) for ten_to)
+                    const bool is_out = L.epi_kind == EPI_OUT;
+                    const uint32_t par_bytes = is_out ? L.nc * 8u : L.nc * 16u;
+                    const float4* par_src = is_out ? L.epi + (P.ten_to ? L.n_chunks * (L.nc / 2) : 0) + c * (L.nc / 2) : L.epi + c * L.nc;
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar_parfull(pb), par_bytes);
+                        bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), par_src, par_bytes, bar_parfull(pb));
+                    }
                 }
-                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack) + static_cast<size_t>(c) * L.k_stages * b_bytes;
-                for (int s = 0; s < L.k_stages; ++s) {
+                // this CTA's half of each weight stage ([hi | lo] of its nc/2 columns)
+                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack) + static_cast<size_t>(c) * k_stages * b_bytes
+                                     + cta_rank * (b_bytes / 2);
+                // an activation tile is dead after its last chunk has streamed it
+                const uint64_t pol_a = c == L.n_chunks - 1 ? pol_stream : pol_keep;
+                const uint32_t tx_bytes = UM_A_STAGE_BYTES + b_bytes / 2;
+                for (int s = 0; s < k_stages; ++s) {
                     w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
-                    const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
-                    mbar_arrive_expect_tx(bar_full(stage), UM_A_STAGE_BYTES + b_bytes / 2);
-                    // an activation tile is dead after its last chunk has streamed it
-                    bulk_g2s_hint(dst, a_src + static_cast<size_t>(s) * UM_A_STAGE_BYTES, UM_A_STAGE_BYTES, bar_full(stage),
-                                  c == L.n_chunks - 1 ? pol_stream : pol_keep);
-                    // this CTA's half of the weight stage ([hi | lo] of its nc/2 columns)
-                    bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src + static_cast<size_t>(s) * b_bytes + cta_rank * (b_bytes / 2),
-                                  b_bytes / 2, bar_full(stage), pol_keep);
+                    if (PROF && P.counters && blockIdx.x == 0 && it == UM_JOB_TRACE_ITERATION && s < UM_TRACE_STAGES && lane == 0)
+                        P.counters[(gridDim.x + UM_MAX_JOBS) * UM_CNT_SLOTS + (ji * UM_TRACE_STAGES + s) * 2] = now();
+                    if (elect_one()) {
+                        const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
+                        mbar_arrive_expect_tx(bar_full(stage), tx_bytes);
+                        bulk_g2s_hint(dst, a_src, UM_A_STAGE_BYTES, bar_full(stage), pol_a);
+                        bulk_g2s_hint(dst + UM_A_STAGE_BYTES, b_src, b_bytes / 2, bar_full(stage), pol_keep);
+                    }
+                    a_src += UM_A_STAGE_BYTES;
+                    b_src += b_bytes;
                     if (++stage == UM_STAGES) { stage = 0; ph_empty ^= 1; }
                 }
-                if (PROF && P.counters && blockIdx.x == 0) {
+                if (PROF && P.counters && blockIdx.x == 0 && lane == 0) {
                     long long* jc = P.counters + (gridDim.x + ji) * UM_CNT_SLOTS;
                     jc[UM_JOB_LOAD_WAIT_AREADY] += w_aready - j_wa0; jc[UM_JOB_LOAD_WAIT_EMPTY] += w_empty - j_we0;
                     if (it == UM_JOB_TRACE_ITERATION) { jc[UM_JOB_T_LOAD0] = j_t0; jc[UM_JOB_T_LOAD1] = now(); }
                 }
                 ++job;
             })
-            if (PROF && P.counters) {
+            if (PROF && P.counters && lane == 0) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
                 cnt[UM_CNT_LOAD_WAIT_EMPTY] = w_empty; cnt[UM_CNT_LOAD_WAIT_AREADY] = w_aready;
                 cnt[UM_CNT_LOAD_TOTAL] = now() - t_begin;
@@ -618,7 +661,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) / stage relay (peer CTA) =====================
-        if (lane == 0 && cta_rank != 0) {
+        // whole-warp, warp-uniform loops as in the loader; one elected lane issues
+        if (cta_rank != 0) {
             // the peer's operands live in its own shared memory: tell the leader when each stage has landed
             int stage = 0; uint32_t ph_full = 0;
             const uint32_t leader_full0 = map_to_cta(bar_full(0), 0);     // the leader's full barriers
@@ -627,48 +671,56 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const int ks = P.g[g].k_stages;
                 for (int i = 0; i < ks; ++i) {
                     mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
-                    mbar_arrive_remote_relaxed(leader_full0 + 8u * stage);
+                    if (elect_one()) mbar_arrive_remote_relaxed(leader_full0 + 8u * stage);
                     if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                 }
             })
-        } else if (lane == 0) {
+        } else {
             long long w_full = 0, w_accempty = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_full = 0;
-            uint32_t ph_accempty[2] = {1, 1};
+            uint32_t ph_accempty = 3;                             // one phase bit per accumulator buffer
             int job = 0;
+            // shared-memory descriptors of ring stage 0; a stage advances the 14-bit address field by its size >> 4
+            const uint64_t a_hi0 = umma_desc_a(base + UM_SMEM_STAGES);
+            const uint64_t a_lo0 = umma_desc_a(base + UM_SMEM_STAGES + UM_A_HALF_BYTES);
+            const uint64_t b_hi0 = umma_desc(base + UM_SMEM_STAGES + UM_A_STAGE_BYTES);
             UM_FOR_EACH_JOB({
                 const UmmaGemm& L = P.g[g];
+                const int k_stages = L.k_stages;
                 const uint32_t idesc = umma_idesc(L.nc);
-                const uint32_t b_half = static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u;     // bytes of one (hi or lo) half tile
+                const uint64_t b_lo_off = static_cast<uint64_t>((static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u) >> 4);   // (hi -> lo half tile) >> 4
                 const int buf = job & 1;
                 const long long j_t0 = now(), j_wf0 = w_full, j_wa0 = w_accempty;
                 // (a cluster-scope acquire would cost an L1 invalidate per wait on the issue path; the peer
                 // only hands back TMEM it has finished reading - tcgen05.wait::ld precedes its arrive)
-                w_accempty += mbar_wait(bar_accempty(buf), ph_accempty[buf], P.error_flag, 201); ph_accempty[buf] ^= 1;
+                w_accempty += mbar_wait(bar_accempty(buf), (ph_accempty >> buf) & 1, P.error_flag, 201); ph_accempty ^= 1u << buf;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
-                for (int s = 0; s < L.k_stages; ++s) {
+                for (int s = 0; s < k_stages; ++s) {
                     w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
+                    if (PROF && P.counters && blockIdx.x == 0 && it == UM_JOB_TRACE_ITERATION && s < UM_TRACE_STAGES && lane == 0)
+                        P.counters[(gridDim.x + UM_MAX_JOBS) * UM_CNT_SLOTS + (ji * UM_TRACE_STAGES + s) * 2 + 1] = now();
                     tc_fence_after();
-                    const uint32_t sa = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
-                    const uint64_t a_hi = umma_desc_a(sa);
-                    const uint64_t a_lo = umma_desc_a(sa + UM_A_HALF_BYTES);
-                    const uint64_t b_hi = umma_desc(sa + UM_A_STAGE_BYTES);
-                    const uint64_t b_lo = umma_desc(sa + UM_A_STAGE_BYTES + b_half);
+                    if (elect_one()) {
+                        const uint64_t adv = static_cast<uint64_t>(stage) * (UM_STAGE_BYTES >> 4);
+                        const uint64_t a_hi = a_hi0 + adv, a_lo = a_lo0 + adv, b_hi = b_hi0 + adv, b_lo = b_hi + b_lo_off;
 #pragma unroll
-                    for (int kk = 0; kk < UM_KS / 16; ++kk) {
-                        const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
-                        const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
-                        umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
-                        umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
-                        umma_f16_2cta(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                        for (int kk = 0; kk < UM_KS / 16; ++kk) {
+                            const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
+                            const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
+                            umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
+                            umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                            umma_f16_2cta(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                        }
+                        umma_commit_2cta(bar_empty(stage));       // frees the stage in both CTAs
                     }
-                    umma_commit_2cta(bar_empty(stage));           // frees the stage in both CTAs
                     if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                 }
-                umma_commit_2cta(bar_accfull(buf));               // both CTAs' epilogues may drain their 128 rows
-                if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
-                if (PROF && P.counters && blockIdx.x == 0) {
+                if (elect_one()) {
+                    umma_commit_2cta(bar_accfull(buf));           // both CTAs' epilogues may drain their 128 rows
+                    if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
+                }
+                if (PROF && P.counters && blockIdx.x == 0 && lane == 0) {
                     long long* jc = P.counters + (gridDim.x + ji) * UM_CNT_SLOTS;
                     const long long j_t1 = now();
                     jc[UM_JOB_MMA_WAIT_FULL] += w_full - j_wf0; jc[UM_JOB_MMA_WAIT_ACCEMPTY] += w_accempty - j_wa0;
@@ -677,7 +729,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 }
                 ++job;
             })
-            if (PROF && P.counters) {
+            if (PROF && P.counters && lane == 0) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
                 cnt[UM_CNT_MMA_WAIT_FULL] = w_full; cnt[UM_CNT_MMA_WAIT_ACCEMPTY] = w_accempty;
                 cnt[UM_CNT_MMA_TOTAL] = now() - t_begin;
@@ -734,13 +786,15 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         const int cw = ew >> 2;                      // which of the lane quarter's warps: takes every (UM_EPI_WARPS/4)-th 32-column piece
         const float4* epipar = reinterpret_cast<const float4*>(sbase + UM_SMEM_EPIPAR);
         const int tq = lane >> 2, tr = lane & 3;     // fragment coordinates: rows tq, tq+8 (+16 for the 2nd load); cols 2*tr, 2*tr+1
-        // 16-byte output stores need a 16-byte aligned base and a row pitch that is a multiple of 4 floats
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(P.out) & 15) | (static_cast<uintptr_t>(P.out_pitch) & 3)) == 0;
+        // 32-byte (16-byte) output stores need a 32-byte (16-byte) aligned base and a row pitch that is a multiple of 8 (4) floats
+        const int vec_mode = ((reinterpret_cast<uintptr_t>(P.out) & 31) | (static_cast<uintptr_t>(P.out_pitch) & 7)) == 0 ? OUT_VEC32
+                           : ((reinterpret_cast<uintptr_t>(P.out) & 15) | (static_cast<uintptr_t>(P.out_pitch) & 3)) == 0 ? OUT_VEC16 : OUT_SCALAR;
         uint32_t ph_accfull[2] = {0, 0}, ph_parfull = 0;
         long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = now();
         int job = 0;
         EpiCtx E;
         E.q = q; E.tq = tq; E.tr = tr; E.cw = cw;
+        E.dbg = PROF ? P.debug_flags : 0;
         const uint32_t accempty_leader0 = map_to_cta(bar_accempty(0), 0);
         UM_FOR_EACH_JOB({
             const UmmaGemm& L = P.g[g];
@@ -764,6 +818,15 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const int n_lines = L.k_stages * (UM_A_STAGE_BYTES / 128);
                 for (int ln = threadIdx.x - UM_EPI_WARP0 * 32; ln < n_lines; ln += UM_EPI_THREADS) l2_discard_line(dead + ln * 128);
             }
+            if (PROF && (P.debug_flags & 3)) {
+                if (P.debug_flags & 2) {           // TMEM reads only
+                    uint32_t va[16];
+                    for (int pc = cw * UM_PIECE; pc < L.nc; pc += (UM_EPI_WARPS / 4) * UM_PIECE) {
+                        tmem_ld_16x256b_x4(E.t_addr0 + pc, va); tmem_ld_wait16(va);
+                        tmem_ld_16x256b_x4(E.t_addr0 + (16u << 16) + pc, va); tmem_ld_wait16(va);
+                    }
+                }
+            } else
             if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, out_buf(g, t, pidx));
             else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, out_buf(g, t, pidx));
             else {
@@ -771,11 +834,11 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
                 float* orow0 = P.out + (row0 + q * 32 + tq) * P.out_pitch;
                 if (P.accumulate) {
-                    if (P.ten_to) epi_chunk_output<true, true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
-                    else epi_chunk_output<false, true>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                    if (P.ten_to) epi_chunk_output<true, true>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
+                    else epi_chunk_output<false, true>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
                 } else {
-                    if (P.ten_to) epi_chunk_output<true, false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
-                    else epi_chunk_output<false, false>(E, orow0, P.out_pitch, vec_ok && rows_ok, P.n_rows - row0, P.n_modes);
+                    if (P.ten_to) epi_chunk_output<true, false>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
+                    else epi_chunk_output<false, false>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
                 }
             }
             // accumulator drained: hand the TMEM buffer back to the MMA issuer

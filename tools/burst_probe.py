@@ -36,7 +36,7 @@ def main():
         torch.cuda.synchronize()
         c = eng.debug_counters(enable=False, read=True).astype(np.float64)
         ms = e0.elapsed_time(e1)
-        jobs = c[2 * cap: 2 * cap + 96]
+        jobs = c.reshape(-1)[: c.size - 96 * 32].reshape(-1, 16)[2 * cap: 2 * cap + 96]
         tot = c[:2 * cap, 5].max()
         kinds = {}
         for r in jobs:

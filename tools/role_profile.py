@@ -36,14 +36,18 @@ def main():
     c = eng.debug_counters(enable=False, read=True).astype(np.float64)
     ms = e0.elapsed_time(e1)
     print("%s rows=%d: %.3f ms, %.3g spectra/s" % (name, rows, ms, rows / ms * 1e3))
-    tot = c[:, 5].max()
-    lead = c[: c.shape[0] - 96, 5]
-    lead = lead[lead > 0]
-    print("median over leader CTAs of the MMA role total = %.0f cycles (clock-independent figure of merit)" % np.median(lead))
-    print("max over CTAs of the MMA role total = %.3g cycles -> %.0f MHz effective (leader CTAs only record MMA counters)" % (tot, tot / ms / 1e3))
+    flat = c.reshape(-1)
+    ntrace = 96 * 16 * 2
+    trace = flat[flat.size - ntrace:].reshape(96, 16, 2)     # [job][stage][loader issue, MMA saw it landed]
+    c = flat[:flat.size - ntrace].reshape(-1, 16)
     ncta = c.shape[0] - 96                     # per-CTA rows, then 96 per-job rows written by CTA 0
     jobs = c[ncta:]
     c = c[:ncta]
+    tot = c[:, 5].max()
+    lead = c[:, 5]
+    lead = lead[lead > 0]
+    print("median over leader CTAs of the MMA role total = %.0f cycles (clock-independent figure of merit)" % np.median(lead))
+    print("max over CTAs of the MMA role total = %.3g cycles -> %.0f MHz effective (leader CTAs only record MMA counters)" % (tot, tot / ms / 1e3))
     for i, n in enumerate(NAMES):
         print("  %-18s mean %12.0f  (%5.1f%% of mma_total)  min %12.0f max %12.0f" % (n, c[:, i].mean(), 100 * c[:, i].mean() / tot, c[:, i].min(), c[:, i].max()))
     print("per job-table entry of CTA 0 (cycles summed over its iterations; time stamps of iteration 3 relative to the first):")
@@ -57,6 +61,20 @@ def main():
         ts = ["%7d" % (x - t0) if x > 0 else "      -" for x in r[8:14]]
         print("  %2d %2d %d %2d  %d  | %14.0f %13.0f %8.0f | %13.0f %8.0f | %17.0f %10.0f | %s" % (
             ji, jw & 255, (jw >> 8) & 255, (jw >> 16) & 255, jw >> 24, r[0], r[1], r[2], r[3], r[4], r[5], r[6], " ".join(ts)))
+    print_trace(trace, jobs, t0)
+
+
+
+
+def print_trace(trace, jobs, t0):
+    print("stage trace of the traced iteration (cycles relative to its first MMA job): per job, loader issue times then MMA landed times")
+    for ji in range(96):
+        if jobs[ji][2] == 0 or trace[ji, 0, 1] == 0:
+            continue
+        ld = " ".join("%6d" % (x - t0) if x > 0 else "     -" for x in trace[ji, :, 0])
+        mm = " ".join("%6d" % (x - t0) if x > 0 else "     -" for x in trace[ji, :, 1])
+        print("  job %2d load %s" % (ji, ld))
+        print("         mma  %s" % mm)
 
 
 if __name__ == "__main__":
