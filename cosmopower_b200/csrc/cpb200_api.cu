@@ -316,6 +316,8 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.ten_to = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
     p.accumulate = (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0;
     p.debug_flags = 0;
+    p.discard_ok = 1;
+    for (size_t i = 0; i + 1 < e->gemms.size(); ++i) if (e->gemms[i].nc % 64) p.discard_ok = 0;
     if (e->d_counters) if (const char* dbg = getenv("CPB200_DEBUG_EPILOGUE")) p.debug_flags = atoi(dbg);   // profiling ablations
     p.params = params;
     p.pmean = e->d_pmean;

@@ -89,6 +89,7 @@ struct UmmaParams {
     int n_parameters;
     int n_modes;
     int ten_to;
+    int discard_ok;            // every operand-producing contraction has a chunk width that is a multiple of 64 (see the epilogue's discard)
     int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM (results are garbage)
     int accumulate;            // output layers add the log10 values already in `out` before the optional 10**
     const float* params;       // (n_rows, n_parameters)
@@ -810,14 +811,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const long long t_job = now();
             E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * UM_MAX_NC);
             E.chunk_col0 = c * L.nc;
-            if (UM_DISCARD_DEAD_TILES && g >= 1 && c == L.n_chunks - 1) {
-                // this was the last chunk to stream the tile's operand: every copy of it has landed and been
-                // consumed (its MMAs are complete), so its L2 lines are dead - drop them instead of letting
-                // them be written back to HBM on eviction
-                const uint8_t* dead = in_buf(g, t, pidx);
-                const int n_lines = L.k_stages * (UM_A_STAGE_BYTES / 128);
-                for (int ln = threadIdx.x - UM_EPI_WARP0 * 32; ln < n_lines; ln += UM_EPI_THREADS) l2_discard_line(dead + ln * 128);
-            }
             if (PROF && (P.debug_flags & 3)) {
                 if (P.debug_flags & 2) {           // TMEM reads only
                     uint32_t va[16];
@@ -841,17 +834,31 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     else epi_chunk_output<false, false>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
                 }
             }
-            // accumulator drained: hand the TMEM buffer back to the MMA issuer
+            // accumulator drained (every lane has passed tcgen05.wait::ld): hand the TMEM buffer back to the MMA
+            // issuer first - the rest of this job's tail does not touch TMEM
             tc_fence_before();
-            // the next layer's loader may only read the scratch once every chunk of this layer is
-            // written: one fence per thread before the last chunk's arrive covers all its stores
-            if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) { UM_SCRATCH_FENCE(); fence_proxy_async(); }
             __syncwarp();
             if (lane == 0) {
                 if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
                 else mbar_arrive_remote_relaxed(accempty_leader0 + 8u * buf);   // TMEM reads are complete (wait::ld)
                 mbar_arrive(bar_parempty(pb));
-                if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) mbar_arrive(bar_aready(t));
+            }
+            if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) {
+                // the next layer's loader may only read the scratch once every chunk of this layer is
+                // written: one fence per thread before the last chunk's arrive covers all its stores
+                UM_SCRATCH_FENCE(); fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_aready(t));
+            }
+            if (UM_DISCARD_DEAD_TILES && P.discard_ok && g >= 1 && c == L.n_chunks - 1) {
+                // This was the last chunk to stream the tile's operand: every copy of it has landed and been consumed
+                // (its MMAs are complete), so its L2 lines are dead - drop them instead of letting them be written
+                // back to HBM on eviction.  The slot is rewritten by the very next step, possibly while slower warps
+                // are still in this job, so a warp only drops the lines it will itself rewrite (program order then
+                // keeps discard before store): with chunk widths that are multiples of 64 (discard_ok) warp (q, cw)
+                // writes exactly the rows of lane quarter q in the K stages of parity cw - 32 lines per stage.
+                const uint8_t* dead = in_buf(g, t, pidx) + (lane >> 4) * UM_A_HALF_BYTES + q * 2048 + (lane & 15) * 128;
+                for (int sd = cw; sd < L.k_stages; sd += UM_EPI_WARPS / 4) l2_discard_line(dead + static_cast<size_t>(sd) * UM_A_STAGE_BYTES);
             }
             if (L.epi_kind == EPI_OUT) c_out += now() - t_job; else c_act += now() - t_job;
             if (PROF && P.counters && blockIdx.x == 0 && ew == 0 && lane == 0) {
