@@ -32,6 +32,12 @@ class ModelDesc(ctypes.Structure):
                 ("pca_mean", _fp), ("pca_std", _fp), ("pca_transform_matrix", _fp)]
 
 
+class PlikDesc(ctypes.Structure):
+    _fields_ = [("n_ell", ctypes.c_int32), ("n_bins", ctypes.c_int32), ("n_gather", ctypes.c_int32),
+                ("bin_start", ctypes.POINTER(ctypes.c_int32)), ("gather_first", ctypes.POINTER(ctypes.c_int32)),
+                ("window", _fp), ("x_data", _fp), ("fisher", _fp), ("units_factor", ctypes.c_float)]
+
+
 # every symbol include/cpb200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("cpb200_abi_version", ctypes.c_int, []),
@@ -51,6 +57,12 @@ SYMBOLS = [
     ("cpb200_engine_set_timing", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     ("cpb200_engine_debug_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
+    ("cpb200_plik_create", ctypes.c_int, [ctypes.POINTER(PlikDesc), ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    ("cpb200_plik_destroy", ctypes.c_int, [ctypes.c_void_p]),
+    ("cpb200_plik_loglike_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    ("cpb200_plik_launch_count", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_last_error", ctypes.c_char_p, []),
 ]
 
@@ -250,3 +262,61 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self._lib.cpb200_engine_last_kernel_ms(self._h))
+
+
+class PlikEngine:
+    """Device-side Planck-lite likelihood tail (cpb200_plik_*): band-power binning + Fisher quadratic form."""
+
+    def __init__(self, n_ell, bin_start, gather_first, window, x_data, fisher, units_factor, device=0):
+        lib = load_library()
+        self._lib = lib
+        self._keep = [np.ascontiguousarray(bin_start, dtype=np.int32), np.ascontiguousarray(gather_first, dtype=np.int32),
+                      _f32(window), _f32(x_data), _f32(fisher)]
+        bs, gf, w, xd, f = self._keep
+        self.n_ell, self.n_bins, self.device = int(n_ell), int(xd.size), int(device)
+        if f.shape != (self.n_bins, self.n_bins) or bs.size != self.n_bins + 1 or gf.size != self.n_bins:
+            raise ValueError("inconsistent likelihood tables")
+        ip = ctypes.POINTER(ctypes.c_int32)
+        desc = PlikDesc(self.n_ell, self.n_bins, int(w.size), bs.ctypes.data_as(ip), gf.ctypes.data_as(ip),
+                        _ptr(w), _ptr(xd), _ptr(f), float(units_factor))
+        h = ctypes.c_void_p()
+        _check(lib.cpb200_plik_create(ctypes.byref(desc), self.device, ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cpb200_plik_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self._lib.cpb200_plik_launch_count(self._h))
+
+    def loglike_torch(self, cl_tt, cl_te, cl_ee, cal, return_binned=False):
+        """cl_* : CUDA float32 (N, n_ell) tensors with a common row stride; cal: CUDA float32 (N,).
+        Returns loglike (N,) [and the (N, n_bins) model band powers]."""
+        import torch
+        n = int(cl_tt.shape[0])
+        for t in (cl_tt, cl_te, cl_ee):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape == cl_tt.shape and
+                    t.shape[1] == self.n_ell and t.stride(1) == 1 and t.stride(0) == cl_tt.stride(0) and
+                    t.device.index == self.device):
+                raise ValueError("spectra must be CUDA float32 (N, %d) tensors on device %d with a common row stride"
+                                 % (self.n_ell, self.device))
+        cal = cal.to(device=cl_tt.device, dtype=torch.float32).contiguous().reshape(-1)
+        if cal.numel() != n:
+            raise ValueError("cal must hold one A_planck per row")
+        out = torch.empty((n,), dtype=torch.float32, device=cl_tt.device)
+        binned = torch.empty((n, self.n_bins), dtype=torch.float32, device=cl_tt.device) if return_binned else None
+        stream = torch.cuda.current_stream(cl_tt.device).cuda_stream
+        _check(self._lib.cpb200_plik_loglike_device(
+            self._h, cl_tt.data_ptr(), cl_te.data_ptr(), cl_ee.data_ptr(), int(cl_tt.stride(0)) if n else self.n_ell,
+            cal.data_ptr(), n, out.data_ptr(), binned.data_ptr() if return_binned else None,
+            self.n_bins, ctypes.c_void_p(stream)))
+        return (out, binned) if return_binned else out

@@ -17,6 +17,7 @@
 #include "../../include/cpb200.h"
 #include "simt_kernels.cuh"
 #include "umma_kernel.cuh"
+#include "plik_kernels.cuh"
 
 namespace {
 
@@ -651,5 +652,133 @@ float cpb200_engine_last_kernel_ms(cpb200_engine* e) {
     }
     return ms;
 }
+
+}  // extern "C"
+
+
+// ---------------------------------------------------------------------------------------------
+// Planck-lite likelihood tail
+// ---------------------------------------------------------------------------------------------
+struct cpb200_plik {
+    int device = 0;
+    int n_ell = 0, n_bins = 0, n_gather = 0, pad = 0, n_jt = 0, num_sms = 0;
+    float units_factor = 0.f;
+    int* d_bin_start = nullptr;
+    int* d_gather_first = nullptr;
+    float* d_window = nullptr;
+    float* d_x_data = nullptr;
+    float* d_fprime = nullptr;          // pad x pad: strict upper triangle of F + half its diagonal, zero elsewhere
+    float* d_diff = nullptr;            // chunk_rows x pad
+    float* d_partial = nullptr;         // chunk_rows x n_jt
+    int64_t chunk_rows = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+void plik_free(cpb200_plik* p) {
+    if (!p) return;
+    cudaFree(p->d_bin_start); cudaFree(p->d_gather_first); cudaFree(p->d_window); cudaFree(p->d_x_data);
+    cudaFree(p->d_fprime); cudaFree(p->d_diff); cudaFree(p->d_partial);
+    delete p;
+}
+}  // namespace
+
+extern "C" {
+
+int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** out) {
+    if (!d || !out) return fail(CPB200_E_INVALID, "null argument");
+    *out = nullptr;
+    if (d->n_ell < 1 || d->n_bins < 1 || d->n_gather < 1 || !d->bin_start || !d->gather_first || !d->window ||
+        !d->x_data || !d->fisher)
+        return fail(CPB200_E_INVALID, "incomplete likelihood description");
+    if (d->bin_start[0] != 0 || d->bin_start[d->n_bins] != d->n_gather) return fail(CPB200_E_INVALID, "bin_start does not span n_gather");
+    for (int b = 0; b < d->n_bins; ++b) {
+        const int len = d->bin_start[b + 1] - d->bin_start[b];
+        if (len < 0 || d->gather_first[b] < 0 || d->gather_first[b] + len > 3 * d->n_ell)
+            return fail(CPB200_E_INVALID, "bin %d gathers outside the three spectra", b);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CPB200_E_NO_DEVICE, "no CUDA device visible; this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(CPB200_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (static_cast<size_t>(3 * d->n_ell) * sizeof(float) > prop.sharedMemPerBlockOptin)
+        return fail(CPB200_E_UNSUPPORTED, "3 x %d multipoles do not fit one block's shared memory", d->n_ell);
+    cpb200_plik* p = new cpb200_plik();
+    auto bail = [&](int rc) { plik_free(p); return rc; };
+    p->device = device;
+    p->num_sms = prop.multiProcessorCount;
+    p->n_ell = d->n_ell; p->n_bins = d->n_bins; p->n_gather = d->n_gather;
+    p->units_factor = d->units_factor;
+    p->pad = round_up(d->n_bins, cpb::PLIK_QF_BN);
+    p->n_jt = p->pad / cpb::PLIK_QF_BN;
+    int rc;
+    if ((rc = upload(&p->d_bin_start, d->bin_start, static_cast<size_t>(d->n_bins) + 1))) return bail(rc);
+    if ((rc = upload(&p->d_gather_first, d->gather_first, static_cast<size_t>(d->n_bins)))) return bail(rc);
+    if ((rc = upload(&p->d_window, d->window, static_cast<size_t>(d->n_gather)))) return bail(rc);
+    if ((rc = upload(&p->d_x_data, d->x_data, static_cast<size_t>(d->n_bins)))) return bail(rc);
+    {   // F' = strict upper triangle of the symmetrised F + half its diagonal: chi^2 = 2 d^T F' d
+        std::vector<float> fp(static_cast<size_t>(p->pad) * p->pad, 0.f);
+        for (int i = 0; i < d->n_bins; ++i)
+            for (int j = i; j < d->n_bins; ++j) {
+                const double fij = 0.5 * (static_cast<double>(d->fisher[static_cast<size_t>(i) * d->n_bins + j]) +
+                                          static_cast<double>(d->fisher[static_cast<size_t>(j) * d->n_bins + i]));
+                if (!std::isfinite(fij)) return bail(fail(CPB200_E_RANGE, "non-finite Fisher element"));
+                fp[static_cast<size_t>(i) * p->pad + j] = static_cast<float>(i == j ? 0.5 * fij : fij);
+            }
+        if ((rc = upload(&p->d_fprime, fp.data(), fp.size()))) return bail(rc);
+    }
+    p->chunk_rows = 131072;
+    if (cudaMalloc(reinterpret_cast<void**>(&p->d_diff), static_cast<size_t>(p->chunk_rows) * p->pad * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&p->d_partial), static_cast<size_t>(p->chunk_rows) * p->n_jt * sizeof(float)) != cudaSuccess)
+        return bail(fail(CPB200_E_CUDA, "likelihood scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaFuncSetAttribute(cpb::plik_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(3 * d->n_ell * sizeof(float))) != cudaSuccess)
+        return bail(fail(CPB200_E_CUDA, "cannot size the binning kernel's shared memory"));
+    *out = p;
+    return 0;
+}
+
+int cpb200_plik_destroy(cpb200_plik* p) {
+    if (!p) return 0;
+    DeviceGuard guard(p->device);
+    cudaDeviceSynchronize();
+    plik_free(p);
+    return 0;
+}
+
+int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* cl_te, const float* cl_ee,
+                               int64_t pitch, const float* cal, int64_t n_rows, float* loglike, float* binned,
+                               int64_t binned_pitch, void* stream) {
+    if (!p) return fail(CPB200_E_INVALID, "null likelihood");
+    if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
+    if (n_rows == 0) return 0;
+    if (!cl_tt || !cl_te || !cl_ee || !cal || !loglike) return fail(CPB200_E_INVALID, "null device pointer");
+    if (pitch < p->n_ell) return fail(CPB200_E_INVALID, "pitch %lld < n_ell %d", static_cast<long long>(pitch), p->n_ell);
+    if (binned && binned_pitch < p->n_bins) return fail(CPB200_E_INVALID, "binned_pitch < n_bins");
+    DeviceGuard guard(p->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = static_cast<size_t>(3) * p->n_ell * sizeof(float);
+    for (int64_t r0 = 0; r0 < n_rows; r0 += p->chunk_rows) {
+        const int64_t m = std::min<int64_t>(p->chunk_rows, n_rows - r0);
+        const int grid_bin = static_cast<int>(std::min<int64_t>(m, static_cast<int64_t>(p->num_sms) * 7 * 4));
+        cpb::plik_bin_kernel<<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
+            cl_tt + r0 * pitch, cl_te + r0 * pitch, cl_ee + r0 * pitch, pitch, cal + r0, m, p->n_ell, p->d_bin_start,
+            p->d_gather_first, p->d_window, p->d_x_data, p->n_bins, p->units_factor, p->d_diff, p->pad,
+            binned ? binned + r0 * binned_pitch : nullptr, binned_pitch);
+        dim3 grid_qf(static_cast<unsigned>(p->n_jt), static_cast<unsigned>((m + cpb::PLIK_QF_BM - 1) / cpb::PLIK_QF_BM));
+        cpb::plik_quadform_kernel<<<grid_qf, 256, 0, st>>>(p->d_diff, p->pad, p->d_fprime, p->pad, m, p->d_partial, p->n_jt);
+        cpb::plik_finish_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(p->d_partial, p->n_jt, m, loglike + r0);
+        p->launches += 3;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int64_t cpb200_plik_launch_count(const cpb200_plik* p) { return p ? p->launches : 0; }
 
 }  // extern "C"

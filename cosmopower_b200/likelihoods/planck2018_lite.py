@@ -1,0 +1,198 @@
+"""Planck 2018 plik-lite likelihood evaluated on the GPU behind the B200 emulators.
+
+Host-side mirror of the reference class `tf_planck2018_lite`
+(cosmopower/likelihoods/tf_planck2018_lite/tf_planck2018_lite.py): same constructor keywords (:38-47), same
+public attributes (`parameters`, `parameter_keys`, `indices`, `indices_rep`, `window_ttteee`, `X_data`,
+`fisher`, `nbin_tot`, ...), same methods `get_loglkl` (:257-304), `loglkl` (:309-326) and `posterior`
+(:349-365), on torch CUDA tensors instead of TensorFlow ones.  The three emulators run through the fused
+kernel (TT and EE with 10**, TE linear, :276-278) and the binning + Fisher quadratic form run in
+cpb200_plik_loglike_device; there is no CPU path.
+
+The Planck data vector, window functions and covariance come from the flat file written by
+tools/convert_planck_lite.py (`tf_planck2018_lite_path` may instead point at a directory holding the
+reference's own `data/planck2018_plik_lite/*.dat`, read as the reference reads them, :104-124, :206-216).
+"""
+import os
+
+import numpy as np
+
+from .. import _engine
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DATA_NPZ = os.path.join(_HERE, "data", "planck2018_plik_lite.npz")
+
+
+def _read_reference_dir(data_dir, nbin_hi):
+    from scipy.io import FortranFile
+    bval, x_data, x_sig = np.genfromtxt(os.path.join(data_dir, "cl_cmb_plik_v22.dat"), unpack=True)
+    blmin = np.loadtxt(os.path.join(data_dir, "blmin.dat")).astype(int)
+    blmax = np.loadtxt(os.path.join(data_dir, "blmax.dat")).astype(int)
+    bin_w = np.loadtxt(os.path.join(data_dir, "bweight.dat"))
+    f = FortranFile(os.path.join(data_dir, "c_matrix_plik_v22.dat"), "r")
+    cov = f.read_reals(dtype=float).reshape((nbin_hi, nbin_hi))
+    f.close()
+    cov = np.tril(cov) + np.tril(cov, -1).T
+    return dict(bval=bval, X_data=x_data, X_sig=x_sig, blmin=blmin, blmax=blmax, bin_w=bin_w, cov=cov)
+
+
+def binning_tables(blmin, blmax, bin_w, n_ell=2507, plmin_tt=30, plmin=30, nbins=(215, 199, 199)):
+    """Gather ranges of the three spectra in the concatenated [TT | TE | EE] vector, as the reference builds them
+    (:126-202).  Returns (gather_first, bin_start, window, indices, indices_rep): a bin gathers the
+    bin_start[b+1]-bin_start[b] consecutive multipoles that start at gather_first[b]; `indices`, `indices_rep`
+    and `window` are the reference's flat tables (self.indices, self.indices_rep, self.window_ttteee)."""
+    first, start, window, indices, indices_rep = [], [0], [], [], []
+    b = 0
+    for nb, pl, off in zip(nbins, (plmin_tt, plmin, plmin), (0, n_ell, 2 * n_ell)):
+        for i in range(nb):
+            lo, hi = int(blmin[i]) + pl - 2, int(blmax[i]) + pl + 1 - 2
+            first.append(off + lo)
+            start.append(start[-1] + hi - lo)
+            window.append(bin_w[blmin[i]:blmax[i] + 1])
+            indices.append(off + np.arange(lo, hi))
+            indices_rep.append(np.full(hi - lo, b))
+            b += 1
+    return (np.array(first, dtype=np.int32), np.array(start, dtype=np.int32), np.concatenate(window).astype(np.float32),
+            np.concatenate(indices), np.concatenate(indices_rep))
+
+
+def fisher_from_covariance(cov):
+    """Fisher matrix of the band powers (:206-230).  The reference inverts the float32 covariance by Cholesky in
+    float32; here the float32-cast covariance is inverted in float64 and rounded once."""
+    c = np.asarray(cov, dtype=np.float32).astype(np.float64)
+    L = np.linalg.cholesky(c)
+    y = np.linalg.solve(L, np.eye(c.shape[0]))
+    return np.linalg.solve(L.T, y).T.astype(np.float32)
+
+
+class _Prior:
+    """Product of independent uniform / gaussian densities (reference set_priors, :331-346, without tfp)."""
+
+    def __init__(self, parameters):
+        self.kinds, self.a, self.b = [], [], []
+        for name in parameters:
+            low, high, kind = parameters[name]
+            if kind not in ("uniform", "gaussian"):
+                raise ValueError("prior of %r must be 'uniform' or 'gaussian'" % name)
+            self.kinds.append(kind); self.a.append(float(low)); self.b.append(float(high))
+
+    def prob(self, x):
+        import torch
+        p = torch.ones(x.shape[0], dtype=torch.float32, device=x.device)
+        for i, (kind, a, b) in enumerate(zip(self.kinds, self.a, self.b)):
+            xi = x[:, i]
+            if kind == "uniform":
+                p = p * torch.where((xi >= a) & (xi <= b), torch.full_like(xi, 1.0 / (b - a)), torch.zeros_like(xi))
+            else:
+                p = p * torch.exp(-0.5 * ((xi - a) / b) ** 2) / (b * float(np.sqrt(2 * np.pi)))
+        return p
+
+
+class tf_planck2018_lite:
+    def __init__(self, parameters=None, tf_planck2018_lite_path=None, spectra="TTTEEE", use_low_ell_bins=False,
+                 units_factor=(2.7255e6) ** 2, tt_emu_model=None, te_emu_model=None, ee_emu_model=None, device=None,
+                 chunk_rows=262144):
+        self.parameters = parameters
+        self.priors = _Prior(parameters) if parameters is not None else None
+        self.spectra = spectra
+        self.use_low_ell_bins = use_low_ell_bins
+        self.units_factor = units_factor
+        if tt_emu_model is None:
+            raise ValueError("Unrecognised emulator for TT spectrum")
+        if te_emu_model is None:
+            raise ValueError("Unrecognised emulator for TE spectrum")
+        if ee_emu_model is None:
+            raise ValueError("Unrecognised emulator for EE spectrum")
+        self.tt_emu_model, self.te_emu_model, self.ee_emu_model = tt_emu_model, te_emu_model, ee_emu_model
+        if not (list(tt_emu_model.parameters) == list(te_emu_model.parameters) == list(ee_emu_model.parameters)):
+            raise ValueError("different ordering in emulators")          # the reference prints and stops (:73-75)
+        if spectra != "TTTEEE":
+            raise ValueError("Spectra must be TTTEEE")                   # :93-95
+        if use_low_ell_bins:
+            # the reference sets nbintt_low_ell = 2 but never loads the low-ell data (:77-82): its Fisher matrix stays
+            # 613 x 613 against 615 bins, so that branch cannot run there either
+            raise NotImplementedError("use_low_ell_bins=True is not runnable in the reference; not provided")
+        self.parameter_keys = list(parameters.keys()) if parameters is not None else list(tt_emu_model.parameters) + ["A_planck"]
+        self.nbintt_low_ell, self.plmin_TT = 0, 30
+        self.plmin, self.plmax = 30, 2508
+        self.nbintt_hi, self.nbinte, self.nbinee = 215, 199, 199
+        self.nbin_hi = self.nbintt_hi + self.nbinte + self.nbinee
+        self.nbintt = self.nbintt_hi + self.nbintt_low_ell
+        self.nbin_tot = self.nbintt + self.nbinte + self.nbinee
+
+        if tf_planck2018_lite_path is not None and os.path.isdir(os.path.join(tf_planck2018_lite_path, "data", "planck2018_plik_lite")):
+            self.data_directory = os.path.join(tf_planck2018_lite_path, "data")
+            d = _read_reference_dir(os.path.join(self.data_directory, "planck2018_plik_lite"), self.nbin_hi)
+        else:
+            self.data_directory = os.path.dirname(DATA_NPZ)
+            with np.load(DATA_NPZ) as z:
+                d = {k: z[k] for k in z.files}
+        self.bval, self.X_sig = d["bval"], d["X_sig"]
+        self.blmin, self.blmax = d["blmin"].astype(int), d["blmax"].astype(int)
+        self.bin_w = d["bin_w"].astype("float32")
+        self.blmin_TT, self.blmax_TT, self.bin_w_TT = self.blmin, self.blmax, self.bin_w
+        x_data = d["X_data"].astype("float32")
+
+        n_ell = self.plmax - 1
+        for m in (tt_emu_model, te_emu_model, ee_emu_model):
+            if int(m.n_modes) != n_ell:
+                raise ValueError("emulators must predict %d multipoles (ell = 2 .. %d)" % (n_ell, self.plmax))
+        first, start, window, self.indices, self.indices_rep = binning_tables(
+            self.blmin, self.blmax, self.bin_w, n_ell, self.plmin_TT, self.plmin, (self.nbintt, self.nbinte, self.nbinee))
+        self.window_ttteee = window.reshape(1, -1)
+        self.X_data = x_data.reshape(1, -1)
+        self.fisher = self.get_inverse_covmat(d["cov"])
+        self.device = device if device is not None else (getattr(tt_emu_model, "_device", None) or 0)
+        self.chunk_rows = int(chunk_rows)
+        self._engine = _engine.PlikEngine(n_ell, start, first, self.window_ttteee.reshape(-1), x_data, self.fisher,
+                                          units_factor, device=self.device)
+
+    # ===== INVERSE COVARIANCE ======  (:206-230)
+    def get_inverse_covmat(self, cov):
+        return fisher_from_covariance(cov)
+
+    def _split(self, parameters):
+        import torch
+        if not isinstance(parameters, torch.Tensor):
+            parameters = torch.as_tensor(np.asarray(parameters, dtype=np.float32))
+        parameters = parameters.to(device="cuda:%d" % self.device, dtype=torch.float32)
+        keys = self.parameter_keys
+        cal = parameters[:, keys.index("A_planck")]
+        cols = [keys.index(k) for k in self.tt_emu_model.parameters]
+        return parameters, parameters[:, cols].contiguous(), cal
+
+    def get_loglkl(self, parameters):
+        """(N, len(parameter_keys)) -> (N, 1) log-likelihood, as the reference's get_loglkl (:257-304)."""
+        import torch
+        parameters, cosmo, cal = self._split(parameters)
+        n = cosmo.shape[0]
+        out = torch.empty((n, 1), dtype=torch.float32, device=cosmo.device)
+        for r0 in range(0, n, self.chunk_rows):
+            x = cosmo[r0:r0 + self.chunk_rows]
+            cl_tt = self.tt_emu_model.ten_to_predictions_tf(x)
+            cl_te = self.te_emu_model.predictions_tf(x)
+            cl_ee = self.ee_emu_model.ten_to_predictions_tf(x)
+            out[r0:r0 + x.shape[0], 0] = self._engine.loglike_torch(cl_tt, cl_te, cl_ee, cal[r0:r0 + x.shape[0]])
+        return out
+
+    def loglkl(self, parameters, prodpri):
+        """:309-326 - rows whose prior probability is zero get -1e12."""
+        import torch
+        loglike = self.get_loglkl(parameters)
+        prodpri = torch.as_tensor(prodpri).to(loglike.device).reshape(-1, 1)
+        return torch.where(prodpri == 0.0, torch.full_like(loglike, -0.5 * 2e12), loglike)
+
+    def posterior(self, params):
+        """:349-365 - log-likelihood + log-prior."""
+        import torch
+        parameters, _, _ = self._split(params)
+        pr = self.priors.prob(parameters).reshape(-1, 1)
+        logpr = torch.log(pr)
+        loglike = self.loglkl(parameters, pr)
+        logpr = torch.where(torch.isinf(logpr), torch.full_like(logpr, -1e32), logpr)
+        return loglike + logpr
+
+    def close(self):
+        self._engine.close()
+
+
+

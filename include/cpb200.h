@@ -135,6 +135,46 @@ int cpb200_engine_set_timing(cpb200_engine* e, int enabled);
  * Returns the number of int64 values available, or a negative error. */
 int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int32_t capacity);
 
+/* -------------------------------------------------------------------------------------------------
+ * Planck 2018 plik-lite likelihood tail behind the TT / TE / EE emulators.
+ *
+ * Replaces: tf_planck2018_lite.get_loglkl from the point where the three spectra exist
+ * (cosmopower/likelihoods/tf_planck2018_lite/tf_planck2018_lite.py:281-304): units factor,
+ * gather * window and segment sum into the band powers (:284-291; tables built at :126-202),
+ * division by A_planck^2 (:294), difference to the data vector and Fisher quadratic form (:297-302),
+ * -chi^2 / 2 (:302).  The Fisher matrix (:206-230) is computed by the caller and passed in.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct cpb200_plik cpb200_plik;
+
+typedef struct {
+    int32_t n_ell;              /* multipoles per spectrum row (2507: ell = 2 .. 2508) */
+    int32_t n_bins;             /* 613 = 215 TT + 199 TE + 199 EE */
+    int32_t n_gather;           /* total gathered multipoles (tf_planck2018_lite.py:196-197), = bin_start[n_bins] */
+    const int32_t* bin_start;   /* n_bins + 1 offsets into `window` (CSR over the reference's indices_rep) */
+    const int32_t* gather_first;/* n_bins: position of a bin's first multipole in the concatenated [TT|TE|EE] row;
+                                   a bin gathers bin_start[b+1]-bin_start[b] consecutive multipoles (:131-176) */
+    const float* window;        /* n_gather window weights, the reference's window_ttteee (:282) */
+    const float* x_data;        /* n_bins data vector (:107-109) */
+    const float* fisher;        /* n_bins x n_bins, row-major, symmetric (:206-230) */
+    float units_factor;         /* (T_CMB in muK)^2 (:45, :281) */
+} cpb200_plik_desc;
+
+int cpb200_plik_create(const cpb200_plik_desc* desc, int32_t device, cpb200_plik** out);
+int cpb200_plik_destroy(cpb200_plik* p);
+
+/*
+ * loglike_dev[r] = -0.5 * chi^2 of row r, for r < n_rows.  cl_tt / cl_te / cl_ee are device float32
+ * (n_rows, n_ell) arrays with a common row pitch in elements (the emulators' outputs: TT and EE from
+ * ten_to_predictions, TE from predictions, :276-278); cal_dev holds A_planck per row (:270).
+ * binned_dev, when non-NULL, receives the (n_rows, n_bins) model band powers X_model (:294) with row pitch
+ * binned_pitch.  Asynchronous on `stream`; rows are processed in engine-owned chunks.
+ */
+int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt_dev, const float* cl_te_dev,
+                               const float* cl_ee_dev, int64_t pitch, const float* cal_dev, int64_t n_rows,
+                               float* loglike_dev, float* binned_dev, int64_t binned_pitch, void* stream);
+/* Kernels launched by this object since creation. */
+int64_t cpb200_plik_launch_count(const cpb200_plik* p);
+
 /* Message for the most recent failure on this thread ("" if none). */
 const char* cpb200_last_error(void);
 

@@ -76,3 +76,131 @@ def restore_reference(name, filename_without_suffix):
     obj = object.__new__(cls)
     cls.restore(obj, filename_without_suffix)
     return obj
+
+
+# ---------------------------------------------------------------------------------------------------
+# Planck-lite likelihood: execute the unmodified reference source with a NumPy-backed TensorFlow stub
+# ---------------------------------------------------------------------------------------------------
+def _numpy_tf():
+    """A tensorflow / tensorflow_probability look-alike covering exactly the calls made by
+    cosmopower/likelihoods/tf_planck2018_lite/tf_planck2018_lite.py, on float32 NumPy arrays."""
+    import numpy as np
+
+    tf = types.ModuleType("tensorflow")
+    tf._cpb200_stub = True
+    tf.float32 = np.float32
+    tf.string = str
+
+    def function(*a, **k):
+        if len(a) == 1 and callable(a[0]) and not k:
+            return a[0]
+        return lambda f: f
+    tf.function = function
+    tf.convert_to_tensor = lambda x: np.asarray(x)
+    tf.reshape = lambda x, shape: np.reshape(x, [int(s) for s in shape])
+    tf.shape = lambda x: np.array(np.shape(x))
+    tf.constant = lambda x, shape=None: np.asarray(x) if shape is None else np.asarray(x).reshape(shape)
+    tf.concat = lambda xs, axis=0: np.concatenate(xs, axis=axis)
+    tf.eye = lambda n: np.eye(int(n), dtype=np.float32)
+    tf.transpose = lambda x: np.transpose(x)
+    tf.zeros = lambda shape: np.zeros(shape, dtype=np.float32)
+    tf.scalar_mul = lambda s, x: (np.float32(s) * x).astype(np.float32)
+    tf.tile = lambda x, reps: np.tile(x, reps)
+    tf.gather = lambda x, idx, axis=0: np.take(x, idx, axis=axis)
+    tf.divide = lambda a, b: a / b
+    tf.square = np.square
+    tf.subtract = lambda a, b: a - b
+    tf.add = lambda a, b: a + b
+    tf.matmul = lambda a, b: np.matmul(a, b)
+    tf.where = np.where
+    tf.equal = lambda a, b: a == b
+
+    linalg = types.ModuleType("tensorflow.linalg")
+    linalg.cholesky = np.linalg.cholesky
+    linalg.cholesky_solve = lambda chol, rhs: np.linalg.solve(chol.T, np.linalg.solve(chol, rhs)).astype(chol.dtype)
+    linalg.diag_part = np.diagonal
+    tf.linalg = linalg
+
+    math = types.ModuleType("tensorflow.math")
+    math.multiply = lambda a, b: a * b
+    math.log = np.log
+    math.is_inf = np.isinf
+
+    def segment_sum(data, segment_ids):
+        out = np.zeros((int(np.max(segment_ids)) + 1,) + data.shape[1:], dtype=data.dtype)
+        np.add.at(out, np.asarray(segment_ids), data)
+        return out
+    math.segment_sum = segment_sum
+    tf.math = math
+
+    class DenseHashTable:
+        def __init__(self, key_dtype=None, value_dtype=None, empty_key=None, deleted_key=None, default_value=None):
+            self._d, self._default = {}, default_value
+
+        def insert(self, keys, values):
+            for k, v in zip(list(keys), values):
+                self._d[str(k)] = v
+
+        def lookup(self, keys):
+            return np.stack([self._d.get(str(k), self._default) for k in np.asarray(keys).reshape(-1)])
+    lookup = types.ModuleType("tensorflow.lookup")
+    lookup.experimental = types.ModuleType("tensorflow.lookup.experimental")
+    lookup.experimental.DenseHashTable = DenseHashTable
+    tf.lookup = lookup
+
+    tfp = types.ModuleType("tensorflow_probability")
+    dist = types.ModuleType("tensorflow_probability.distributions")
+
+    class Uniform:
+        def __init__(self, low, high):
+            self.low, self.high = low, high
+
+        def prob(self, x):
+            return np.where((x >= self.low) & (x <= self.high), 1.0 / (self.high - self.low), 0.0)
+
+    class Normal:
+        def __init__(self, loc, scale):
+            self.loc, self.scale = loc, scale
+
+        def prob(self, x):
+            return np.exp(-0.5 * ((x - self.loc) / self.scale) ** 2) / (self.scale * np.sqrt(2 * np.pi))
+
+    class Blockwise:
+        def __init__(self, parts):
+            self.parts = parts
+
+        def prob(self, x):
+            p = np.ones(x.shape[0])
+            for i, d in enumerate(self.parts):
+                p = p * d.prob(x[:, i])
+            return p.astype(np.float32)
+    dist.Uniform, dist.Normal, dist.Blockwise = Uniform, Normal, Blockwise
+    tfp.distributions = dist
+    return tf, tfp
+
+
+def reference_planck_lite_class():
+    """The reference class tf_planck2018_lite, imported from its own source file."""
+    if "tf_planck2018_lite" not in _classes:
+        tf, tfp = _numpy_tf()
+        saved = {k: sys.modules.get(k) for k in ("tensorflow", "tensorflow_probability", "cosmopower")}
+        sys.modules["tensorflow"] = tf
+        sys.modules["tensorflow_probability"] = tfp
+        sys.modules["cosmopower"] = types.ModuleType("cosmopower")       # imported by the file, not used by the class
+        try:
+            path = os.path.join(REF_ROOT, "cosmopower", "likelihoods", "tf_planck2018_lite", "tf_planck2018_lite.py")
+            spec = importlib.util.spec_from_file_location("_ref_tf_planck2018_lite", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _classes["tf_planck2018_lite"] = mod.tf_planck2018_lite
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+    return _classes["tf_planck2018_lite"]
+
+
+def reference_planck_lite_path():
+    return os.path.join(REF_ROOT, "cosmopower", "likelihoods", "tf_planck2018_lite")

@@ -1,0 +1,151 @@
+"""GPU parity of the Planck-lite likelihood tail (cpb200_plik_*) against the float64 NumPy oracle
+(oracle/planck_lite_np.py, pinned to the executed reference by tests/golden/planck_lite.npz).
+
+Tolerance: the reference computes this part in float32 (tf_planck2018_lite.py:108, :224, :281-304) and so does
+the CUDA path; against the float64 oracle the log-likelihood must agree to
+    |ll - ll_ref| <= 2e-4 * |ll_ref| + 2e-3
+(the absolute term covers near-fit rows, where chi^2 ~ 1 is a small difference of large products).  The model
+band powers must agree to 2e-6 of the row's largest |band power|.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np, planck_lite_np
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_REL, TOL_ABS, TOL_BIN = 2e-4, 2e-3, 2e-6
+
+
+def _close(ll, ref):
+    ll = np.asarray(ll, np.float64).reshape(-1)
+    ref = np.asarray(ref, np.float64).reshape(-1)
+    err = np.abs(ll - ref)
+    bound = TOL_REL * np.abs(ref) + TOL_ABS
+    assert (err <= bound).all(), "worst %.3g of bound at row %d (ll %.6g ref %.6g)" % (
+        float((err / bound).max()), int((err / bound).argmax()), ll[(err / bound).argmax()], ref[(err / bound).argmax()])
+    return float((err / np.maximum(np.abs(ref), 1.0)).max())
+
+
+@pytest.fixture(scope="module")
+def plik():
+    from cosmopower_b200 import _engine
+    from cosmopower_b200.likelihoods import planck2018_lite as pl
+    d = planck_lite_np.load_data()
+    first, start, window, _, _ = pl.binning_tables(d["blmin"], d["blmax"], d["bin_w"].astype(np.float32))
+    eng = _engine.PlikEngine(planck_lite_np.N_ELL, start, first, window, d["X_data"].astype(np.float32),
+                             pl.fisher_from_covariance(d["cov"]), (2.7255e6) ** 2, device=0)
+    yield eng
+    eng.close()
+
+
+def _padded(a, pitch=2512):
+    import torch
+    buf = torch.zeros((a.shape[0], pitch), dtype=torch.float32, device="cuda")
+    buf[:, :a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    return buf[:, :a.shape[1]]
+
+
+def test_golden_spectra(plik):
+    import torch
+    with np.load(os.path.join(REPO, "tests", "golden", "planck_lite.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    ll, binned = plik.loglike_torch(_padded(g["cl_tt"]), _padded(g["cl_te"]), _padded(g["cl_ee"]),
+                                    torch.from_numpy(g["cal"]).cuda(), return_binned=True)
+    torch.cuda.synchronize()
+    o = planck_lite_np.PlanckLiteOracle()
+    ref_binned = o.bin_spectra(g["cl_tt"], g["cl_te"], g["cl_ee"]) / np.square(g["cal"].astype(np.float64))[:, None]
+    berr = np.abs(binned.cpu().numpy() - ref_binned).max(axis=1) / np.abs(ref_binned).max(axis=1)
+    assert berr.max() <= TOL_BIN, berr.max()
+    worst = _close(ll.cpu().numpy(), g["loglkl_np64"])
+    print("planck-lite golden: worst relative log-likelihood error %.3g, band powers %.3g" % (worst, berr.max()))
+    assert plik.launch_count == 3
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 1000])
+def test_ragged_sizes_and_tight_pitch(plik, n):
+    import torch
+    rng = np.random.default_rng(n)
+    o = planck_lite_np.PlanckLiteOracle()
+    nl = planck_lite_np.N_ELL
+    cl = np.abs(rng.standard_normal((n, 3 * nl))) * 1e-12
+    cl[:, o.indices] = o.X_data[o.indices_rep] * (1 + 0.01 * rng.standard_normal((n, o.indices.size))) / o.units_factor
+    cl = cl.astype(np.float32)
+    cal = (1 + 0.0025 * rng.standard_normal(n)).astype(np.float32)
+    ref = o.loglike_from_spectra(cl[:, :nl], cl[:, nl:2 * nl], cl[:, 2 * nl:], cal)
+    parts = [torch.from_numpy(np.ascontiguousarray(cl[:, i * nl:(i + 1) * nl])).cuda() for i in range(3)]   # pitch 2507: scalar loads
+    ll = plik.loglike_torch(*parts, torch.from_numpy(cal).cuda())
+    _close(ll.cpu().numpy(), ref)
+    ll2 = plik.loglike_torch(_padded(cl[:, :nl]), _padded(cl[:, nl:2 * nl]), _padded(cl[:, 2 * nl:]), torch.from_numpy(cal).cuda())
+    assert torch.equal(ll, ll2)                       # the vector and scalar load paths agree bit for bit
+
+
+def test_empty_batch(plik):
+    import torch
+    e = torch.empty((0, planck_lite_np.N_ELL), dtype=torch.float32, device="cuda")
+    assert plik.loglike_torch(e, e, e, torch.empty((0,), device="cuda")).shape == (0,)
+
+
+def test_chunk_boundaries_and_determinism(plik):
+    """More rows than one engine chunk (131072): every row must equal the same row evaluated in a small batch."""
+    import torch
+    n = 131072 + 300
+    rng = np.random.default_rng(7)
+    base = np.abs(rng.standard_normal((64, 3 * planck_lite_np.N_ELL))).astype(np.float32) * 1e-10
+    rows = rng.integers(0, 64, size=n)
+    nl = planck_lite_np.N_ELL
+    small = [_padded(base[:, i * nl:(i + 1) * nl]) for i in range(3)]
+    cal = torch.ones(64, device="cuda")
+    ll_small = plik.loglike_torch(*small, cal)
+    idx = torch.from_numpy(rows).cuda()
+    big = [torch.empty((n, 2512), dtype=torch.float32, device="cuda")[:, :nl] for _ in range(3)]
+    for b, s in zip(big, small):
+        b.copy_(s[idx])
+    ll_big = plik.loglike_torch(*big, torch.ones(n, device="cuda"))
+    assert torch.equal(ll_big, ll_small[idx])
+    assert torch.equal(ll_big, plik.loglike_torch(*big, torch.ones(n, device="cuda")))
+
+
+def test_end_to_end_class_against_the_oracle_pipeline():
+    """tf_planck2018_lite mirror: emulators + likelihood on the device vs oracle emulators + oracle likelihood."""
+    import torch
+    import cosmopower_b200 as cp
+    from cosmopower_b200 import priors, standins
+    from cosmopower_b200.likelihoods import tf_planck2018_lite
+    models, attrs = {}, {}
+    for key, name in (("tt", "cmb_TT_NN"), ("te", "cmb_TE_PCAplusNN"), ("ee", "cmb_EE_NN")):
+        kind, path = standins.model_path(name)
+        models[key] = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
+        attrs[key] = standins.load_attrs(kind, path)
+    params = list(models["tt"].parameters)
+    spec = {k: (lo, hi, "uniform") for k, (lo, hi) in priors.prior_for(params).items()}
+    spec["A_planck"] = (1.0, 0.0025, "gaussian")
+    like = tf_planck2018_lite(parameters=spec, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"])
+    n = 2048
+    x = priors.sample_prior(params, n, seed=11)
+    x[:8, 0] = 1.0                                     # omega_b outside its prior: zero prior probability
+    cal = 1 + 0.0025 * np.random.default_rng(3).standard_normal(n)
+    full = np.concatenate([x, cal[:, None]], axis=1).astype(np.float32)
+    x32 = full[:, :len(params)].astype(np.float64)
+    with np.errstate(over="ignore"):
+        cl_tt = 10.0 ** oracle_np.forward_pass(attrs["tt"], x32)
+        cl_te = oracle_np.forward_pass(attrs["te"], x32)
+        cl_ee = 10.0 ** oracle_np.forward_pass(attrs["ee"], x32)
+    o = planck_lite_np.PlanckLiteOracle()
+    ref = o.loglike_from_spectra(cl_tt, cl_te, cl_ee, full[:, -1].astype(np.float64))
+    ll = like.get_loglkl(torch.from_numpy(full).cuda()).cpu().numpy()
+    assert ll.shape == (n, 1)
+    # emulator tolerance (1e-5 in log10 C_ell) enters chi^2 twice: allow 1e-3 relative end to end
+    rel = np.abs(ll[8:] - ref[8:]) / np.abs(ref[8:])          # the first 8 rows are far outside the prior (overflow)
+    assert rel.max() <= 1e-3, rel.max()
+    post = like.posterior(torch.from_numpy(full).cuda()).cpu().numpy()
+    assert (post[:8] <= -1e12).all() and np.isfinite(post[8:]).all()
+    pr = like.priors.prob(torch.from_numpy(full).cuda()).cpu().numpy()
+    assert (pr[:8] == 0).all() and (pr[8:] > 0).all()
+    masked = like.loglkl(torch.from_numpy(full).cuda(), pr).cpu().numpy()
+    assert (masked[:8] == -1e12).all() and np.array_equal(masked[8:], ll[8:])
+    like.close()
+    for m in models.values():
+        m.close()

@@ -1,0 +1,59 @@
+"""CPU tests of the Planck-lite likelihood tail: the NumPy oracle against the executed reference's golden
+vectors (tests/golden/planck_lite.npz, written by oracle/make_planck_goldens.py) and the host-side tables of
+cosmopower_b200.likelihoods against the oracle's."""
+import os
+
+import numpy as np
+
+from cosmopower_b200.likelihoods import planck2018_lite as pl
+from oracle import planck_lite_np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden", "planck_lite.npz")
+
+
+def _golden():
+    with np.load(GOLDEN) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_float32_oracle_reproduces_the_executed_reference():
+    g = _golden()
+    o32 = planck_lite_np.PlanckLiteOracle(dtype=np.float32)
+    ll = o32.loglike_from_spectra(g["cl_tt"], g["cl_te"], g["cl_ee"], g["cal"])
+    # same algorithm in the same precision class; only the summation order of BLAS / segment sums differs
+    np.testing.assert_allclose(ll, g["loglkl_ref_f32"], rtol=2e-5)
+
+
+def test_float64_oracle_matches_its_golden_and_the_float32_reference():
+    g = _golden()
+    o64 = planck_lite_np.PlanckLiteOracle()
+    ll = o64.loglike_from_spectra(g["cl_tt"], g["cl_te"], g["cl_ee"], g["cal"])
+    np.testing.assert_allclose(ll, g["loglkl_np64"], rtol=1e-10)
+    np.testing.assert_allclose(ll, g["loglkl_ref_f32"], rtol=1e-4)        # the reference's own float32 rounding
+    masked = o64.loglkl(ll, g["prodpri"])
+    np.testing.assert_allclose(masked, g["loglkl_masked_ref"], rtol=1e-4)
+    assert (masked[g["prodpri"].reshape(-1) == 0] == -1e12).all()
+
+
+def test_host_tables_equal_the_oracles():
+    d = planck_lite_np.load_data()
+    first, start, window, indices, indices_rep = pl.binning_tables(d["blmin"], d["blmax"], d["bin_w"].astype(np.float32))
+    o = planck_lite_np.PlanckLiteOracle()
+    assert np.array_equal(indices, o.indices) and np.array_equal(indices_rep, o.indices_rep)
+    assert np.array_equal(window, o.window.astype(np.float32))
+    assert start[0] == 0 and start[-1] == indices.size == 6413 and len(first) == 613
+    # a bin is one contiguous run of multipoles
+    for b in (0, 100, 214, 215, 413, 414, 612):
+        assert np.array_equal(indices[start[b]:start[b + 1]], first[b] + np.arange(start[b + 1] - start[b]))
+    f = pl.fisher_from_covariance(d["cov"])
+    np.testing.assert_allclose(f, o.fisher, rtol=2e-6, atol=1e-30)
+    assert f.dtype == np.float32 and np.abs(f - f.T).max() <= 1e-6 * np.abs(f).max()
+
+
+def test_segment_sum_is_a_window_average():
+    # every window sums to one (bweight.dat is normalised per bin): a flat spectrum bins to itself
+    o = planck_lite_np.PlanckLiteOracle()
+    flat = np.full((1, planck_lite_np.N_ELL), 3.0 / o.units_factor)
+    binned = o.bin_spectra(flat, flat, flat)
+    np.testing.assert_allclose(binned, 3.0, rtol=1e-6)

@@ -1,0 +1,57 @@
+"""Device time of the Planck-lite likelihood tail and of the full emulators + likelihood call.  (B200 only)
+Usage: python tools/time_likelihood.py [rows]"""
+import json
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import torch  # noqa: E402
+import cosmopower_b200 as cp  # noqa: E402
+from cosmopower_b200 import priors, standins  # noqa: E402
+from cosmopower_b200.likelihoods import tf_planck2018_lite  # noqa: E402
+
+
+def timed(fn, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def main():
+    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
+    models = {}
+    for key, name in (("tt", "cmb_TT_NN"), ("te", "cmb_TE_PCAplusNN"), ("ee", "cmb_EE_NN")):
+        kind, path = standins.model_path(name)
+        models[key] = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
+    params = list(models["tt"].parameters)
+    like = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"])
+    x = priors.sample_prior(params, rows, seed=5, dtype=np.float32)
+    full = torch.from_numpy(np.concatenate([x, np.ones((rows, 1), np.float32)], axis=1)).cuda()
+    cosmo = full[:, :len(params)].contiguous()
+    cl_tt = models["tt"].ten_to_predictions_tf(cosmo)
+    cl_te = models["te"].predictions_tf(cosmo)
+    cl_ee = models["ee"].ten_to_predictions_tf(cosmo)
+    cal = full[:, -1].contiguous()
+    ms_tail = timed(lambda: like._engine.loglike_torch(cl_tt, cl_te, cl_ee, cal))
+    ms_emu = timed(lambda: (models["tt"].ten_to_predictions_tf(cosmo), models["te"].predictions_tf(cosmo), models["ee"].ten_to_predictions_tf(cosmo)))
+    ms_all = timed(lambda: like.get_loglkl(full))
+    n_ell, nb = 2507, 613
+    out = {"rows": rows, "likelihood_tail_ms": ms_tail, "three_emulators_ms": ms_emu, "get_loglkl_ms": ms_all,
+           "tail_hbm_gbs": rows * (3 * n_ell + 2 * 640) * 4 / ms_tail / 1e6,
+           "tail_quadform_tflops_dense_equiv": rows * 2.0 * nb * nb / ms_tail / 1e9,
+           "loglike_per_s": rows / ms_all * 1e3}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
