@@ -663,10 +663,9 @@ struct cpb200_plik {
     int device = 0;
     int n_ell = 0, n_bins = 0, n_gather = 0, pad = 0, n_jt = 0, num_sms = 0;
     float units_factor = 0.f;
-    int* d_bin_start = nullptr;
-    int* d_gather_first = nullptr;
-    float* d_window = nullptr;
-    float* d_x_data = nullptr;
+    cpb::PlikSlot* d_slots = nullptr;   // runs of <= PLIK_SEG consecutive multipoles of one bin (plik_bin_kernel)
+    int n_passes = 0;
+    size_t bin_smem = 0;
     float* d_fprime = nullptr;          // pad x pad: strict upper triangle of F + half its diagonal, zero elsewhere
     float* d_diff = nullptr;            // chunk_rows x pad
     float* d_partial = nullptr;         // chunk_rows x n_jt
@@ -677,7 +676,7 @@ struct cpb200_plik {
 namespace {
 void plik_free(cpb200_plik* p) {
     if (!p) return;
-    cudaFree(p->d_bin_start); cudaFree(p->d_gather_first); cudaFree(p->d_window); cudaFree(p->d_x_data);
+    cudaFree(p->d_slots);
     cudaFree(p->d_fprime); cudaFree(p->d_diff); cudaFree(p->d_partial);
     delete p;
 }
@@ -706,8 +705,35 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     DeviceGuard guard(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (static_cast<size_t>(3 * d->n_ell) * sizeof(float) > prop.sharedMemPerBlockOptin)
-        return fail(CPB200_E_UNSUPPORTED, "3 x %d multipoles do not fit one block's shared memory", d->n_ell);
+    // split the bins into slots of at most PLIK_SEG multipoles (plik_bin_kernel); a bin's slots sit on neighbouring
+    // lanes of one warp (dummy slots pad to the next warp when they would straddle it)
+    const int rs = round_up(d->n_ell, 4);
+    std::vector<cpb::PlikSlot> slots;
+    auto dummy = [] { cpb::PlikSlot s{}; s.bin = -1; return s; };
+    for (int b = 0; b < d->n_bins; ++b) {
+        const int len = d->bin_start[b + 1] - d->bin_start[b];
+        const int ns = (len + cpb::PLIK_SEG - 1) / cpb::PLIK_SEG;
+        if (ns < 1 || ns > cpb::PLIK_MAX_SLOTS_PER_BIN)
+            return fail(CPB200_E_UNSUPPORTED, "bin %d gathers %d multipoles; 1 .. %d are supported", b, len, cpb::PLIK_SEG * cpb::PLIK_MAX_SLOTS_PER_BIN);
+        while (static_cast<int>(slots.size() % 32) + ns > 32) slots.push_back(dummy());
+        const int sp = d->gather_first[b] / d->n_ell, lo = d->gather_first[b] % d->n_ell;
+        for (int k = 0; k < ns; ++k) {
+            cpb::PlikSlot s = dummy();
+            const int j0 = d->bin_start[b] + k * cpb::PLIK_SEG, j1 = std::min(j0 + cpb::PLIK_SEG, d->bin_start[b + 1]);
+            s.off = sp * rs + lo + k * cpb::PLIK_SEG;
+            s.last = j1 - j0 - 1;
+            for (int u = 0; u < j1 - j0; ++u) s.w[u] = d->window[j0 + u];
+            if (k == 0) { s.bin = b; s.n_slots = ns; s.x_data = d->x_data[b]; }
+            slots.push_back(s);
+        }
+    }
+    while (slots.size() % cpb::PLIK_BIN_THREADS) slots.push_back(dummy());
+    const int n_passes = static_cast<int>(slots.size() / cpb::PLIK_BIN_THREADS);
+    if (n_passes > cpb::PLIK_MAX_PASSES)
+        return fail(CPB200_E_UNSUPPORTED, "%zu window slots exceed %d", slots.size(), cpb::PLIK_MAX_PASSES * cpb::PLIK_BIN_THREADS);
+    const size_t bin_smem = static_cast<size_t>(cpb::PLIK_RING) * 3 * rs * sizeof(float);
+    if (bin_smem > prop.sharedMemPerBlockOptin)
+        return fail(CPB200_E_UNSUPPORTED, "the row ring of 3 x %d multipoles does not fit one block's shared memory", d->n_ell);
     cpb200_plik* p = new cpb200_plik();
     auto bail = [&](int rc) { plik_free(p); return rc; };
     p->device = device;
@@ -717,10 +743,9 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     p->pad = round_up(d->n_bins, cpb::PLIK_QF_BN);
     p->n_jt = p->pad / cpb::PLIK_QF_BN;
     int rc;
-    if ((rc = upload(&p->d_bin_start, d->bin_start, static_cast<size_t>(d->n_bins) + 1))) return bail(rc);
-    if ((rc = upload(&p->d_gather_first, d->gather_first, static_cast<size_t>(d->n_bins)))) return bail(rc);
-    if ((rc = upload(&p->d_window, d->window, static_cast<size_t>(d->n_gather)))) return bail(rc);
-    if ((rc = upload(&p->d_x_data, d->x_data, static_cast<size_t>(d->n_bins)))) return bail(rc);
+    p->n_passes = n_passes;
+    p->bin_smem = bin_smem;
+    if ((rc = upload(&p->d_slots, slots.data(), slots.size()))) return bail(rc);
     {   // F' = strict upper triangle of the symmetrised F + half its diagonal: chi^2 = 2 d^T F' d
         std::vector<float> fp(static_cast<size_t>(p->pad) * p->pad, 0.f);
         for (int i = 0; i < d->n_bins; ++i)
@@ -736,8 +761,10 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     if (cudaMalloc(reinterpret_cast<void**>(&p->d_diff), static_cast<size_t>(p->chunk_rows) * p->pad * sizeof(float)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&p->d_partial), static_cast<size_t>(p->chunk_rows) * p->n_jt * sizeof(float)) != cudaSuccess)
         return bail(fail(CPB200_E_CUDA, "likelihood scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
-    if (cudaFuncSetAttribute(cpb::plik_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(3 * d->n_ell * sizeof(float))) != cudaSuccess)
+    // the padding columns n_bins .. pad-1 of the difference vectors are never written: zero them once
+    if (cudaMemset(p->d_diff, 0, static_cast<size_t>(p->chunk_rows) * p->pad * sizeof(float)) != cudaSuccess)
+        return bail(fail(CPB200_E_CUDA, "memset failed"));
+    if (cudaFuncSetAttribute(cpb::plik_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bin_smem)) != cudaSuccess)
         return bail(fail(CPB200_E_CUDA, "cannot size the binning kernel's shared memory"));
     *out = p;
     return 0;
@@ -762,13 +789,13 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
     if (binned && binned_pitch < p->n_bins) return fail(CPB200_E_INVALID, "binned_pitch < n_bins");
     DeviceGuard guard(p->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t smem = static_cast<size_t>(3) * p->n_ell * sizeof(float);
+    const size_t smem = p->bin_smem;
     for (int64_t r0 = 0; r0 < n_rows; r0 += p->chunk_rows) {
         const int64_t m = std::min<int64_t>(p->chunk_rows, n_rows - r0);
-        const int grid_bin = static_cast<int>(std::min<int64_t>(m, static_cast<int64_t>(p->num_sms) * 7 * 4));
+        const int grid_bin = static_cast<int>(std::min<int64_t>(m, static_cast<int64_t>(p->num_sms) * 3));
         cpb::plik_bin_kernel<<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
-            cl_tt + r0 * pitch, cl_te + r0 * pitch, cl_ee + r0 * pitch, pitch, cal + r0, m, p->n_ell, p->d_bin_start,
-            p->d_gather_first, p->d_window, p->d_x_data, p->n_bins, p->units_factor, p->d_diff, p->pad,
+            cl_tt + r0 * pitch, cl_te + r0 * pitch, cl_ee + r0 * pitch, pitch, cal + r0, m, p->n_ell,
+            p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,
             binned ? binned + r0 * binned_pitch : nullptr, binned_pitch);
         dim3 grid_qf(static_cast<unsigned>(p->n_jt), static_cast<unsigned>((m + cpb::PLIK_QF_BM - 1) / cpb::PLIK_QF_BM));
         cpb::plik_quadform_kernel<<<grid_qf, 256, 0, st>>>(p->d_diff, p->pad, p->d_fprime, p->pad, m, p->d_partial, p->n_jt);

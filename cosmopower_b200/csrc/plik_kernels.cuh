@@ -9,9 +9,9 @@
 //   plik_bin_kernel        HBM-bound: reads 3 x n_ell floats per row once (coalesced, staged in shared memory),
 //                          writes the 640-float padded difference vector
 //   plik_quadform_kernel   (n_rows x 640) x (640 x 640) with the dot product against d fused into the epilogue;
-//                          F is symmetric, so only the upper-triangular 64-wide blocks are visited (F' = strict
-//                          upper triangle + half the diagonal, chi^2 = 2 d^T F' d): 55 % of the dense flops
-//   plik_finish_kernel     sums the 10 column-block partials per row (fixed order: deterministic)
+//                          F is symmetric, so only the upper-triangular 128-wide blocks are visited (F' = strict
+//                          upper triangle + half the diagonal, chi^2 = 2 d^T F' d): 60 % of the dense flops
+//   plik_finish_kernel     sums the 5 column-block partials per row (fixed order: deterministic)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,115 +19,194 @@
 namespace cpb {
 
 constexpr int PLIK_BIN_THREADS = 256;
-constexpr int PLIK_QF_BM = 128, PLIK_QF_BN = 64, PLIK_QF_BK = 16;
+constexpr int PLIK_QF_BM = 128, PLIK_QF_BN = 128, PLIK_QF_BK = 16;
 
-// One block per row (grid-stride).  smem: the row's three spectra, concatenated as the reference does.
-__global__ void __launch_bounds__(PLIK_BIN_THREADS)
+// Persistent blocks (three per SM) walking rows with a PLIK_RING-deep shared-memory ring: while a row is being binned
+// the next row's three spectra are already on their way (16-byte cp.async, each spectrum starting 16-byte aligned in
+// shared memory).  A slot is a run of at most PLIK_SEG consecutive multipoles of one bin; the host splits the 5 ... 33
+// wide bins into slots so that the per-thread work is short, balanced and fully unrolled, and lays a bin's slots out on
+// neighbouring lanes of one warp.  Every thread owns the same <= PLIK_MAX_PASSES slots for every row, so their window
+// weights live in registers; the lane holding a bin's first slot adds the other partial sums (at most
+// PLIK_MAX_SLOTS_PER_BIN - 1 shuffles, fixed order: deterministic) and writes d = X_data - model.
+constexpr int PLIK_SEG = 9;
+constexpr int PLIK_MAX_PASSES = 3;
+constexpr int PLIK_MAX_SLOTS_PER_BIN = 4;
+constexpr int PLIK_RING = 2;
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+
+struct PlikSlot {          // one per slot, built by cpb200_plik_create
+    int off;               // shared-memory offset of the slot's first multipole (spectrum s starts at s * round_up(n_ell, 4))
+    int last;              // index of the slot's last multipole (loads beyond it re-read that one, with weight 0)
+    int bin;               // the bin this slot opens, or -1
+    int n_slots;           // slots of that bin (1 .. PLIK_MAX_SLOTS_PER_BIN) when bin >= 0
+    float x_data;          // data band power of that bin
+    float w[PLIK_SEG];     // window weights, zero beyond the slot's end
+};
+
+__global__ void __launch_bounds__(PLIK_BIN_THREADS, 3)
 plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te, const float* __restrict__ cl_ee,
                 long long pitch, const float* __restrict__ cal, long long n_rows, int n_ell,
-                const int* __restrict__ bin_start, const int* __restrict__ gather_first,
-                const float* __restrict__ window, const float* __restrict__ x_data, int n_bins, float units_factor,
+                const PlikSlot* __restrict__ slots, int n_passes, float units_factor,
                 float* __restrict__ diff, int diff_pitch, float* __restrict__ binned, long long binned_pitch)
 {
-    extern __shared__ float row[];                 // 3 * n_ell
+    extern __shared__ __align__(16) float plik_smem[];
+    const int rs = (n_ell + 3) & ~3;               // shared-memory stride of one spectrum
+    const int row_floats = 3 * rs;
     const bool vec = (pitch & 3) == 0 &&
                      ((reinterpret_cast<uintptr_t>(cl_tt) | reinterpret_cast<uintptr_t>(cl_te) | reinterpret_cast<uintptr_t>(cl_ee)) & 15) == 0;
-    for (long long r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        const float* src[3] = {cl_tt + r * pitch, cl_te + r * pitch, cl_ee + r * pitch};
-        __syncthreads();                           // previous row's readers are done
+
+    PlikSlot my[PLIK_MAX_PASSES];
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            float* dst = row + s * n_ell;
-            if (vec) {
-                // rows start 16-byte aligned; the shared copy of spectrum s starts at s * n_ell floats, so go through
-                // registers and store scalars (shared memory stores are cheap, global loads are the 16-byte ones)
-                const int n4 = n_ell >> 2;
-                for (int i = threadIdx.x; i < n4; i += PLIK_BIN_THREADS) {
-                    const float4 v = __ldcs(reinterpret_cast<const float4*>(src[s]) + i);
-                    dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+    for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
+        if (p < n_passes) my[p] = slots[p * PLIK_BIN_THREADS + threadIdx.x];
+        else { my[p].off = 0; my[p].last = 0; my[p].bin = -1; my[p].n_slots = 0; my[p].x_data = 0.f;
+#pragma unroll
+               for (int j = 0; j < PLIK_SEG; ++j) my[p].w[j] = 0.f; }
+    }
+
+    auto fetch = [&](long long r, int buf) {                    // always commits a group (empty past the last row)
+        if (r < n_rows) {
+            float* dst0 = plik_smem + buf * row_floats;
+            const float* src[3] = {cl_tt + r * pitch, cl_te + r * pitch, cl_ee + r * pitch};
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                float* dst = dst0 + s * rs;
+                if (vec) {
+                    const int n4 = n_ell >> 2;
+                    for (int i = threadIdx.x; i < n4; i += PLIK_BIN_THREADS) cp_async_16(dst + 4 * i, src[s] + 4 * i);
+                    for (int i = (n4 << 2) + threadIdx.x; i < n_ell; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src[s] + i);
+                } else {
+                    for (int i = threadIdx.x; i < n_ell; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src[s] + i);
                 }
-                for (int i = (n4 << 2) + threadIdx.x; i < n_ell; i += PLIK_BIN_THREADS) dst[i] = __ldcs(src[s] + i);
-            } else {
-                for (int i = threadIdx.x; i < n_ell; i += PLIK_BIN_THREADS) dst[i] = __ldcs(src[s] + i);
             }
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const long long stride = gridDim.x;
+    long long r = blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < PLIK_RING - 1; ++i) fetch(r + i * stride, i);
+    int buf = 0;
+    for (; r < n_rows; r += stride) {
+        // refill the buffer whose row was consumed in the previous iteration (its readers passed that iteration's
+        // barrier), then wait until only the PLIK_RING - 1 younger groups may still be pending
+        fetch(r + (PLIK_RING - 1) * stride, buf == 0 ? PLIK_RING - 1 : buf - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(PLIK_RING - 1) : "memory");
         const float c = cal[r];
         const float scale = units_factor / (c * c);
-        for (int b = threadIdx.x; b < diff_pitch; b += PLIK_BIN_THREADS) {
-            float d = 0.f;
-            if (b < n_bins) {
-                const int j0 = bin_start[b], j1 = bin_start[b + 1];
-                const float* p = row + gather_first[b];          // a bin gathers one contiguous run of multipoles
+        __syncthreads();                                         // row r has landed for every thread
+        const float* row = plik_smem + buf * row_floats;
+#pragma unroll
+        for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
+            if (p < n_passes) {                                  // uniform across the block
+                const float* q = row + my[p].off;
+                float v[PLIK_SEG];
+#pragma unroll
+                for (int j = 0; j < PLIK_SEG; ++j) v[j] = q[min(j, my[p].last)];
                 float acc = 0.f;
-                for (int j = j0; j < j1; ++j) acc = fmaf(p[j - j0], window[j], acc);
-                const float model = acc * scale;
-                if (binned) binned[r * binned_pitch + b] = model;
-                d = x_data[b] - model;
+#pragma unroll
+                for (int j = 0; j < PLIK_SEG; ++j) acc = fmaf(v[j], my[p].w[j], acc);
+                float sum = acc;
+#pragma unroll
+                for (int k = 1; k < PLIK_MAX_SLOTS_PER_BIN; ++k) {
+                    const float o = __shfl_down_sync(0xffffffffu, acc, k);
+                    if (k < my[p].n_slots) sum += o;
+                }
+                if (my[p].bin >= 0) {
+                    const float model = sum * scale;
+                    if (binned) binned[r * binned_pitch + my[p].bin] = model;
+                    diff[r * diff_pitch + my[p].bin] = my[p].x_data - model;
+                }
             }
-            diff[r * diff_pitch + b] = d;
         }
+        __syncthreads();                                         // this row buffer may be overwritten
+        buf = buf + 1 == PLIK_RING ? 0 : buf + 1;
     }
 }
 
-// partial[r][jt] = sum over the 64 columns n of block jt of d[r][n] * (sum_{k <= last row of block jt} d[r][k] F'[k][n])
+// partial[r][jt] = sum over the 128 columns n of block jt of d[r][n] * (sum_{k <= last row of block jt} d[r][k] F'[k][n])
+// 128 x 128 output tile, 16-deep K steps double-buffered through registers, 8 x 8 accumulators per thread.
 __global__ void __launch_bounds__(256)
 plik_quadform_kernel(const float* __restrict__ D, int ldd, const float* __restrict__ Fp, int ldf, long long n_rows,
                      float* __restrict__ partial, int n_jt)
 {
-    __shared__ float As[PLIK_QF_BK][PLIK_QF_BM + 4];
-    __shared__ float Bs[PLIK_QF_BK][PLIK_QF_BN + 4];
+    __shared__ __align__(16) float As[2][PLIK_QF_BK][PLIK_QF_BM + 4];
+    __shared__ __align__(16) float Bs[2][PLIK_QF_BK][PLIK_QF_BN + 4];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads: 4 columns x 8 rows each
+    const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads; rows ty*4.. and 64+ty*4.., columns tx*4.. and 64+tx*4..
     const int jt = blockIdx.x;
     const long long row0 = static_cast<long long>(blockIdx.y) * PLIK_QF_BM;
     const int col0 = jt * PLIK_QF_BN;
     const int k_end = col0 + PLIK_QF_BN;               // F' is upper triangular: rows k beyond this block's columns are zero
+    const int n_kt = k_end / PLIK_QF_BK;
 
-    float acc[8][4];
+    float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < k_end; k0 += PLIK_QF_BK) {
-        {   // A tile: 128 rows x 16 k = 512 float4, two per thread
+    // global -> register staging: A tile 128 rows x 16 k (2 float4 per thread), B tile 16 k x 128 n (2 float4 per thread)
+    float4 ra[2], rb[2];
+    auto load_tiles = [&](int kt) {
+        const int k0 = kt * PLIK_QF_BK;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int f = tid + u * 256, r = f >> 2, kq = (f & 3) * 4;
-                const long long gr = row0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (gr < n_rows) v = *reinterpret_cast<const float4*>(D + gr * ldd + k0 + kq);
-                As[kq][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
-            }
+        for (int u = 0; u < 2; ++u) {
+            const int f = tid + u * 256, r = f >> 2, kq = (f & 3) * 4;
+            const long long gr = row0 + r;
+            ra[u] = gr < n_rows ? *reinterpret_cast<const float4*>(D + gr * ldd + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int kk = f >> 5, nq = (f & 31) * 4;
+            rb[u] = *reinterpret_cast<const float4*>(Fp + static_cast<long long>(k0 + kk) * ldf + col0 + nq);
         }
-        {   // B tile: 16 k x 64 n = 256 float4, one per thread
-            const int kk = tid >> 4, nq = (tid & 15) * 4;
-            *reinterpret_cast<float4*>(&Bs[kk][nq]) = *reinterpret_cast<const float4*>(Fp + static_cast<long long>(k0 + kk) * ldf + col0 + nq);
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int f = tid + u * 256, r = f >> 2, kq = (f & 3) * 4;
+            As[buf][kq][r] = ra[u].x; As[buf][kq + 1][r] = ra[u].y; As[buf][kq + 2][r] = ra[u].z; As[buf][kq + 3][r] = ra[u].w;
+            const int kk = f >> 5, nq = (f & 31) * 4;
+            *reinterpret_cast<float4*>(&Bs[buf][kk][nq]) = rb[u];
         }
-        __syncthreads();
+    };
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < n_kt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < n_kt) load_tiles(kt + 1);
 #pragma unroll
         for (int kk = 0; kk < PLIK_QF_BK; ++kk) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float w[4] = {b.x, b.y, b.z, b.w};
+            const float w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
         }
+        if (kt + 1 < n_kt) store_tiles(buf ^ 1);
         __syncthreads();
     }
     // epilogue: dot with this block's columns of d, reduce over the 16 threads that share a row
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const long long gr = row0 + ty * 8 + i;
+        const long long gr = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         float s = 0.f;
         if (gr < n_rows) {
-            const float4 d = *reinterpret_cast<const float4*>(D + gr * ldd + col0 + tx * 4);
-            s = acc[i][0] * d.x + acc[i][1] * d.y + acc[i][2] * d.z + acc[i][3] * d.w;
+            const float4 d0 = *reinterpret_cast<const float4*>(D + gr * ldd + col0 + tx * 4);
+            const float4 d1 = *reinterpret_cast<const float4*>(D + gr * ldd + col0 + 64 + tx * 4);
+            s = acc[i][0] * d0.x + acc[i][1] * d0.y + acc[i][2] * d0.z + acc[i][3] * d0.w +
+                acc[i][4] * d1.x + acc[i][5] * d1.y + acc[i][6] * d1.z + acc[i][7] * d1.w;
         }
 #pragma unroll
         for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
