@@ -54,6 +54,7 @@ SYMBOLS = [
     ("cpb200_engine_info", ctypes.c_int, [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 4),
     ("cpb200_engine_launch_count", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_engine_last_kernel_ms", ctypes.c_float, [ctypes.c_void_p]),
+    ("cpb200_engine_last_kernel_cycles", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_engine_set_timing", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     ("cpb200_engine_debug_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
@@ -259,6 +260,9 @@ class Engine:
         if n < 0:
             _check(n)
         return np.frombuffer(buf, dtype=np.int64).reshape(-1, 16).copy()
+
+    def last_kernel_cycles(self):
+        return int(self._lib.cpb200_engine_last_kernel_cycles(self._h))
 
     def last_kernel_ms(self):
         return float(self._lib.cpb200_engine_last_kernel_ms(self._h))

@@ -80,6 +80,7 @@ struct cpb200_engine {
     unsigned long long um_scratch_cta = 0;
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
     int* d_error_flag = nullptr;
+    unsigned long long* d_max_cycles = nullptr;   // fused kernel: SM cycles of the slowest CTA of the latest launch
     std::vector<unsigned> jobs;         // job table of the fused kernel (build_jobs), passed in the kernel parameters
     int n_jobs = 0;
     long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
@@ -336,6 +337,8 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     for (int i = 0; i < e->n_jobs; ++i) p.jobs[i] = e->jobs[i];
     p.n_jobs = e->n_jobs;
     p.error_flag = e->d_error_flag;
+    p.max_cycles = e->d_max_cycles;
+    cudaMemsetAsync(e->d_max_cycles, 0, sizeof(unsigned long long), st);
     p.counters = e->d_counters;
     int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     if (const char* cap = getenv("CPB200_DEBUG_MAX_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(cap)));  // tuning aid
@@ -458,7 +461,9 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
             return bail(fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
         if (cudaMemset(e->um_scratch, 0, total) != cudaSuccess) return bail(fail(CPB200_E_CUDA, "memset failed"));
         if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
-            cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess)
+            cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&e->d_max_cycles), sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
             return bail(fail(CPB200_E_CUDA, "error flag allocation failed"));
         if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  cpb::UM_SMEM_BYTES) != cudaSuccess ||
@@ -486,7 +491,7 @@ int cpb200_destroy(cpb200_engine* e) {
     }
     cudaFree(e->d_pmean); cudaFree(e->d_pstd);
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
-    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_counters);
+    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_max_cycles); cudaFree(e->d_counters);
     for (int i = 0; i < 2; ++i) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);
@@ -634,6 +639,15 @@ int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int
 }
 
 int64_t cpb200_engine_launch_count(const cpb200_engine* e) { return e ? e->launches : 0; }
+
+int64_t cpb200_engine_last_kernel_cycles(cpb200_engine* e) {
+    if (!e || !e->d_max_cycles) return -1;
+    DeviceGuard guard(e->device);
+    unsigned long long v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(&v, e->d_max_cycles, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return static_cast<int64_t>(v);
+}
 
 int cpb200_engine_set_timing(cpb200_engine* e, int enabled) {
     if (!e) return fail(CPB200_E_INVALID, "null engine");

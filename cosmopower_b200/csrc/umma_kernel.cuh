@@ -108,6 +108,7 @@ struct UmmaParams {
                                   // constant bank with the other parameters, so every role decodes it with uniform loads
     int n_jobs;
     int* error_flag;           // set to a code by the watchdog before trapping
+    unsigned long long* max_cycles;   // every launch: max over CTAs of the SM cycles between kernel entry and exit
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
 };
 
@@ -505,6 +506,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         return 0;
     };
     auto now = []() -> long long { return PROF ? clock64() : 0; };
+    const long long t_kernel0 = clock64();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -880,6 +882,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     tc_fence_before();
     __syncthreads();
     if (UM_CLUSTER > 1) cluster_sync_all();      // no CTA leaves while a peer can still multicast into it / arrive on it
+    if (threadIdx.x == 0 && P.max_cycles) atomicMax(P.max_cycles, static_cast<unsigned long long>(clock64() - t_kernel0));
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }

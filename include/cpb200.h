@@ -125,6 +125,9 @@ int64_t cpb200_engine_launch_count(const cpb200_engine* e);
 /* Device time of the most recent cpb200_forward_device/_host kernel section, in ms
  * (CUDA events recorded on the launching stream); < 0 if none. Synchronises on those events. */
 float cpb200_engine_last_kernel_ms(cpb200_engine* e);
+/* SM cycles the slowest CTA of the most recent fused-kernel launch spent between entry and exit (a clock-independent
+ * cost figure: wall time also depends on the SM clock the power cap leaves); -1 if none.  Synchronises the device. */
+int64_t cpb200_engine_last_kernel_cycles(cpb200_engine* e);
 /* Turn per-call kernel timing events on/off (off by default: they serialise nothing but cost two
  * event records per call). */
 int cpb200_engine_set_timing(cpb200_engine* e, int enabled);

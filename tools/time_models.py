@@ -33,7 +33,8 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts))
-        print("%-18s rows=%d: %.3f ms (median of 5, min %.3f), %.3g spectra/s" % (name, rows, ms, min(ts), rows / ms * 1e3), flush=True)
+        print("%-18s rows=%d: %.3f ms (median of 5, min %.3f), %.3g spectra/s, %.3f M SM cycles (slowest CTA)" % (
+            name, rows, ms, min(ts), rows / ms * 1e3, eng.last_kernel_cycles() / 1e6), flush=True)
         m.close()
 
 
