@@ -58,6 +58,7 @@ struct Gemm {
     // device, UMMA path
     int k_pad = 0, k_stages = 0, nc = 0, n_chunks = 0;
     float acc_scale = 1.f;         // 1 / (weight scale * input-activation scale), a power of two
+    bool tri = false;              // upper-triangular weights (quadratic form): chunk c skips the K stages past its columns
     __half* dwpack = nullptr;
     float4* depi = nullptr;
 };
@@ -81,6 +82,12 @@ struct cpb200_engine {
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
     int* d_error_flag = nullptr;
     unsigned long long* d_max_cycles = nullptr;   // fused kernel: SM cycles of the slowest CTA of the latest launch
+    // quadratic-form use of the fused kernel (Planck-lite): set by the caller before launch_umma
+    const uint8_t* qf_ext_a0 = nullptr;
+    const float* qf_d = nullptr;
+    long long qf_pitch = 0;
+    int qf_cols = 0;
+    float* qf_partial = nullptr;
     std::vector<unsigned> jobs;         // job table of the fused kernel (build_jobs), passed in the kernel parameters
     int n_jobs = 0;
     long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
@@ -234,9 +241,9 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
                 // a = acc*acc_scale + b;  h*s_out = ((1-beta)*s_out * sigmoid + beta*s_out) * a
                 dst = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
                                   beta * s_out, (1.f - beta) * s_out);
-            } else {
+            } else if (g.epi == cpb::EPI_AFFINE) {
                 dst = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
-            }
+            }                                   // EPI_QUADFORM: no per-column constants
         }
     }
     if (int rc = upload(&g.dwpack, pack.data(), pack.size())) return rc;
@@ -312,6 +319,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
         p.g[i].n_chunks = g.n_chunks;
         p.g[i].epi_kind = g.epi;
         p.g[i].acc_scale = g.acc_scale;
+        p.g[i].tri = g.tri ? 1 : 0;
     }
     p.n_parameters = e->P;
     p.n_modes = e->n_modes;
@@ -338,6 +346,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.n_jobs = e->n_jobs;
     p.error_flag = e->d_error_flag;
     p.max_cycles = e->d_max_cycles;
+    p.ext_a0 = e->qf_ext_a0; p.qf_d = e->qf_d; p.qf_pitch = e->qf_pitch; p.qf_cols = e->qf_cols; p.qf_partial = e->qf_partial;
     cudaMemsetAsync(e->d_max_cycles, 0, sizeof(unsigned long long), st);
     p.counters = e->d_counters;
     int max_clusters = e->num_sms / cpb::UM_CLUSTER;
@@ -357,6 +366,50 @@ int forward_async(cpb200_engine* e, const float* params, int64_t n, float* out, 
     return launch_umma(e, params, n, out, pitch, flags, st);
 }
 
+}  // namespace
+
+namespace {
+// Tensor-core path set-up shared by the emulator engines and the likelihood's quadratic form: pack every
+// contraction, size the per-CTA scratch, build the job table, opt in to the kernel's shared memory.
+int setup_umma(cpb200_engine* e) {
+    int rc;
+        int k_pad = round_up(e->P, cpb::UM_KS);
+        unsigned max_stages = 1;
+        for (size_t i = 0; i < e->gemms.size(); ++i) {
+            Gemm& g = e->gemms[i];
+            const float s_in = i == 0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
+            if ((rc = pack_umma(g, k_pad, s_in, cpb::UM_ACT_SCALE))) return rc;
+            if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
+            k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
+        }
+        e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
+        e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
+        e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes;
+        if (e->gemms.size() == 1 && e->gemms[0].epi == cpb::EPI_QUADFORM) e->um_scratch_cta = 1024;   // operand tiles are prebuilt elsewhere
+        {
+            std::vector<unsigned> jobs = build_jobs(e->gemms);
+            if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
+                return (fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
+            e->n_jobs = static_cast<int>(jobs.size());
+            e->jobs = jobs;
+        }
+        const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
+        if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
+            return (fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+        if (cudaMemset(e->um_scratch, 0, total) != cudaSuccess) return (fail(CPB200_E_CUDA, "memset failed"));
+        if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
+            cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&e->d_max_cycles), sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
+            return (fail(CPB200_E_CUDA, "error flag allocation failed"));
+        if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 cpb::UM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 cpb::UM_SMEM_BYTES) != cudaSuccess)
+            return (fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
+                             cudaGetErrorString(cudaGetLastError())));
+        return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -437,40 +490,7 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
             if (cudaMalloc(reinterpret_cast<void**>(&e->simt_buf[i]), sizeof(float) * e->simt_rows * width) != cudaSuccess)
                 return bail(fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
     } else {
-        int k_pad = round_up(e->P, cpb::UM_KS);
-        unsigned max_stages = 1;
-        for (size_t i = 0; i < e->gemms.size(); ++i) {
-            Gemm& g = e->gemms[i];
-            const float s_in = i == 0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
-            if ((rc = pack_umma(g, k_pad, s_in, cpb::UM_ACT_SCALE))) return bail(rc);
-            if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
-            k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
-        }
-        e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
-        e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
-        e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes;
-        {
-            std::vector<unsigned> jobs = build_jobs(e->gemms);
-            if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
-                return bail(fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
-            e->n_jobs = static_cast<int>(jobs.size());
-            e->jobs = jobs;
-        }
-        const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
-        if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
-            return bail(fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
-        if (cudaMemset(e->um_scratch, 0, total) != cudaSuccess) return bail(fail(CPB200_E_CUDA, "memset failed"));
-        if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
-            cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess ||
-            cudaMalloc(reinterpret_cast<void**>(&e->d_max_cycles), sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
-            return bail(fail(CPB200_E_CUDA, "error flag allocation failed"));
-        if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 cpb::UM_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 cpb::UM_SMEM_BYTES) != cudaSuccess)
-            return bail(fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
-                             cudaGetErrorString(cudaGetLastError())));
+        if ((rc = setup_umma(e))) return bail(rc);
     }
     for (auto& g : e->gemms) { g.W.clear(); g.W.shrink_to_fit(); }
     if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess)
@@ -682,7 +702,12 @@ struct cpb200_plik {
     size_t bin_smem = 0;
     float* d_fprime = nullptr;          // pad x pad: strict upper triangle of F + half its diagonal, zero elsewhere
     float* d_diff = nullptr;            // chunk_rows x pad
-    float* d_partial = nullptr;         // chunk_rows x n_jt
+    float* d_partial = nullptr;         // chunk_rows x n_jt (fp32 path) or x 2 n_chunks (tensor path)
+    // tensor-core quadratic form: the fused kernel with one upper-triangular contraction and the EPI_QUADFORM epilogue
+    cpb200_engine* qf = nullptr;
+    uint8_t* d_tiles = nullptr;         // split-fp16 operand tiles of one row chunk (written by plik_bin_kernel)
+    float* d_row_scale = nullptr;       // chunk_rows
+    int n_part = 0;
     int64_t chunk_rows = 0;
     int64_t launches = 0;
 };
@@ -691,7 +716,8 @@ namespace {
 void plik_free(cpb200_plik* p) {
     if (!p) return;
     cudaFree(p->d_slots);
-    cudaFree(p->d_fprime); cudaFree(p->d_diff); cudaFree(p->d_partial);
+    cudaFree(p->d_fprime); cudaFree(p->d_diff); cudaFree(p->d_partial); cudaFree(p->d_tiles); cudaFree(p->d_row_scale);
+    if (p->qf) cpb200_destroy(p->qf);
     delete p;
 }
 }  // namespace
@@ -737,7 +763,10 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
             s.off = sp * rs + lo + k * cpb::PLIK_SEG;
             s.last = j1 - j0 - 1;
             for (int u = 0; u < j1 - j0; ++u) s.w[u] = d->window[j0 + u];
-            if (k == 0) { s.bin = b; s.n_slots = ns; s.x_data = d->x_data[b]; }
+            if (k == 0) {
+                s.bin = b; s.n_slots = ns; s.x_data = d->x_data[b];
+                s.sqrt_f = std::sqrt(std::max(0.f, d->fisher[static_cast<size_t>(b) * d->n_bins + b]));
+            }
             slots.push_back(s);
         }
     }
@@ -745,7 +774,7 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     const int n_passes = static_cast<int>(slots.size() / cpb::PLIK_BIN_THREADS);
     if (n_passes > cpb::PLIK_MAX_PASSES)
         return fail(CPB200_E_UNSUPPORTED, "%zu window slots exceed %d", slots.size(), cpb::PLIK_MAX_PASSES * cpb::PLIK_BIN_THREADS);
-    const size_t bin_smem = static_cast<size_t>(cpb::PLIK_RING) * 3 * rs * sizeof(float);
+    const size_t bin_smem = (static_cast<size_t>(cpb::PLIK_RING) * 3 * rs + round_up(d->n_bins, cpb::PLIK_QF_BN) + 8) * sizeof(float);
     if (bin_smem > prop.sharedMemPerBlockOptin)
         return fail(CPB200_E_UNSUPPORTED, "the row ring of 3 x %d multipoles does not fit one block's shared memory", d->n_ell);
     cpb200_plik* p = new cpb200_plik();
@@ -772,8 +801,43 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
         if ((rc = upload(&p->d_fprime, fp.data(), fp.size()))) return bail(rc);
     }
     p->chunk_rows = 131072;
+    if (getenv("CPB200_PLIK_FP32") == nullptr) {
+        // Tensor-core quadratic form.  With s_i = sqrt(F_ii): chi^2 = 2 v^T G v, v_i = d_i s_i, G = triu(F,1)/(s_i s_j) +
+        // I/2 - a correlation-like matrix with entries in [-1, 1], well inside the split-fp16 range; the rows of v are
+        // brought to [0.5, 1) by a power of two in plik_bin_kernel.  The contraction runs in the fused kernel
+        // (one upper-triangular 640 x 640 contraction, EPI_QUADFORM epilogue) on operand tiles the binning kernel prebuilds.
+        cpb200_engine* q = new cpb200_engine();
+        p->qf = q;
+        q->device = device; q->precision = CPB200_PREC_F16X3; q->P = p->pad; q->n_modes = p->pad; q->num_sms = p->num_sms;
+        Gemm g;
+        g.K = p->pad; g.N = p->pad; g.epi = cpb::EPI_QUADFORM; g.tri = true;
+        g.W.assign(static_cast<size_t>(p->pad) * p->pad, 0.f);
+        g.p0.assign(p->pad, 0.f); g.p1.assign(p->pad, 0.f); g.p2.assign(p->pad, 0.f);
+        for (int i = 0; i < d->n_bins; ++i) {
+            const double si = std::sqrt(static_cast<double>(d->fisher[static_cast<size_t>(i) * d->n_bins + i]));
+            if (!(si > 0.0) || !std::isfinite(si)) return bail(fail(CPB200_E_RANGE, "Fisher diagonal element %d is not positive", i));
+            for (int j = i; j < d->n_bins; ++j) {
+                const double sj = std::sqrt(static_cast<double>(d->fisher[static_cast<size_t>(j) * d->n_bins + j]));
+                const double fij = 0.5 * (static_cast<double>(d->fisher[static_cast<size_t>(i) * d->n_bins + j]) +
+                                          static_cast<double>(d->fisher[static_cast<size_t>(j) * d->n_bins + i]));
+                g.W[static_cast<size_t>(i) * p->pad + j] = static_cast<float>(i == j ? 0.5 : fij / (si * sj));
+            }
+        }
+        q->gemms.push_back(std::move(g));
+        if ((rc = setup_umma(q))) return bail(rc);
+        for (auto& gg : q->gemms) { gg.W.clear(); gg.W.shrink_to_fit(); }
+        if (cudaEventCreate(&q->ev0) != cudaSuccess || cudaEventCreate(&q->ev1) != cudaSuccess)
+            return bail(fail(CPB200_E_CUDA, "event creation failed"));
+        p->n_part = 2 * q->gemms[0].n_chunks;
+        const size_t n_tiles = static_cast<size_t>(round_up(static_cast<int>((p->chunk_rows + 127) / 128), 4));
+        if (cudaMalloc(reinterpret_cast<void**>(&p->d_tiles), n_tiles * q->um_a0_bytes) != cudaSuccess ||
+            cudaMemset(p->d_tiles, 0, n_tiles * q->um_a0_bytes) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&p->d_row_scale), static_cast<size_t>(p->chunk_rows) * sizeof(float)) != cudaSuccess)
+            return bail(fail(CPB200_E_CUDA, "likelihood tile allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    const int partial_cols = std::max(p->n_jt, p->n_part);
     if (cudaMalloc(reinterpret_cast<void**>(&p->d_diff), static_cast<size_t>(p->chunk_rows) * p->pad * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&p->d_partial), static_cast<size_t>(p->chunk_rows) * p->n_jt * sizeof(float)) != cudaSuccess)
+        cudaMalloc(reinterpret_cast<void**>(&p->d_partial), static_cast<size_t>(p->chunk_rows) * partial_cols * sizeof(float)) != cudaSuccess)
         return bail(fail(CPB200_E_CUDA, "likelihood scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
     // the padding columns n_bins .. pad-1 of the difference vectors are never written: zero them once
     if (cudaMemset(p->d_diff, 0, static_cast<size_t>(p->chunk_rows) * p->pad * sizeof(float)) != cudaSuccess)
@@ -810,10 +874,18 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
         cpb::plik_bin_kernel<<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
             cl_tt + r0 * pitch, cl_te + r0 * pitch, cl_ee + r0 * pitch, pitch, cal + r0, m, p->n_ell,
             p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,
-            binned ? binned + r0 * binned_pitch : nullptr, binned_pitch);
-        dim3 grid_qf(static_cast<unsigned>(p->n_jt), static_cast<unsigned>((m + cpb::PLIK_QF_BM - 1) / cpb::PLIK_QF_BM));
-        cpb::plik_quadform_kernel<<<grid_qf, 256, 0, st>>>(p->d_diff, p->pad, p->d_fprime, p->pad, m, p->d_partial, p->n_jt);
-        cpb::plik_finish_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(p->d_partial, p->n_jt, m, loglike + r0);
+            binned ? binned + r0 * binned_pitch : nullptr, binned_pitch, p->qf ? p->d_tiles : nullptr, p->d_row_scale);
+        if (p->qf) {
+            cpb200_engine* q = p->qf;
+            q->qf_ext_a0 = p->d_tiles; q->qf_d = p->d_diff; q->qf_pitch = p->pad; q->qf_cols = p->pad; q->qf_partial = p->d_partial;
+            if (int rc = launch_umma(q, nullptr, m, nullptr, 0, 0, st)) return rc;
+            cpb::plik_finish_tensor_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(
+                p->d_partial, p->n_part, p->d_row_scale, q->gemms[0].acc_scale, m, loglike + r0);
+        } else {
+            dim3 grid_qf(static_cast<unsigned>(p->n_jt), static_cast<unsigned>((m + cpb::PLIK_QF_BM - 1) / cpb::PLIK_QF_BM));
+            cpb::plik_quadform_kernel<<<grid_qf, 256, 0, st>>>(p->d_diff, p->pad, p->d_fprime, p->pad, m, p->d_partial, p->n_jt);
+            cpb::plik_finish_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(p->d_partial, p->n_jt, m, loglike + r0);
+        }
         p->launches += 3;
     }
     CU(cudaGetLastError());

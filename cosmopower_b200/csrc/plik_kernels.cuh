@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cuda_fp16.h>
 
 namespace cpb {
 
@@ -31,7 +32,7 @@ constexpr int PLIK_QF_BM = 128, PLIK_QF_BN = 128, PLIK_QF_BK = 16;
 constexpr int PLIK_SEG = 9;
 constexpr int PLIK_MAX_PASSES = 3;
 constexpr int PLIK_MAX_SLOTS_PER_BIN = 4;
-constexpr int PLIK_RING = 2;
+constexpr int PLIK_RING = 2;             // row buffers per block: one being binned, one in flight
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
@@ -40,12 +41,22 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
 }
 
+// fp16 hi/lo split of two floats (same arithmetic as the fused kernel's split2)
+__device__ __forceinline__ void plik_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 struct PlikSlot {          // one per slot, built by cpb200_plik_create
     int off;               // shared-memory offset of the slot's first multipole (spectrum s starts at s * round_up(n_ell, 4))
     int last;              // index of the slot's last multipole (loads beyond it re-read that one, with weight 0)
     int bin;               // the bin this slot opens, or -1
     int n_slots;           // slots of that bin (1 .. PLIK_MAX_SLOTS_PER_BIN) when bin >= 0
     float x_data;          // data band power of that bin
+    float sqrt_f;          // sqrt(F[bin][bin]): scales the difference for the tensor-core quadratic form
     float w[PLIK_SEG];     // window weights, zero beyond the slot's end
 };
 
@@ -53,11 +64,16 @@ __global__ void __launch_bounds__(PLIK_BIN_THREADS, 3)
 plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te, const float* __restrict__ cl_ee,
                 long long pitch, const float* __restrict__ cal, long long n_rows, int n_ell,
                 const PlikSlot* __restrict__ slots, int n_passes, float units_factor,
-                float* __restrict__ diff, int diff_pitch, float* __restrict__ binned, long long binned_pitch)
+                float* __restrict__ diff, int diff_pitch, float* __restrict__ binned, long long binned_pitch,
+                uint8_t* __restrict__ tiles, float* __restrict__ row_scale)
 {
     extern __shared__ __align__(16) float plik_smem[];
     const int rs = (n_ell + 3) & ~3;               // shared-memory stride of one spectrum
     const int row_floats = 3 * rs;
+    // tensor-core mode (tiles != nullptr): the row's scaled differences, then the per-warp maxima
+    float* vrow = plik_smem + PLIK_RING * row_floats;
+    float* wmax = vrow + diff_pitch;
+    if (tiles) for (int i = threadIdx.x; i < diff_pitch; i += PLIK_BIN_THREADS) vrow[i] = 0.f;     // padding columns stay zero
     const bool vec = (pitch & 3) == 0 &&
                      ((reinterpret_cast<uintptr_t>(cl_tt) | reinterpret_cast<uintptr_t>(cl_te) | reinterpret_cast<uintptr_t>(cl_ee)) & 15) == 0;
 
@@ -91,17 +107,16 @@ plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te
 
     const long long stride = gridDim.x;
     long long r = blockIdx.x;
-#pragma unroll
-    for (int i = 0; i < PLIK_RING - 1; ++i) fetch(r + i * stride, i);
+    fetch(r, 0);
     int buf = 0;
     for (; r < n_rows; r += stride) {
-        // refill the buffer whose row was consumed in the previous iteration (its readers passed that iteration's
-        // barrier), then wait until only the PLIK_RING - 1 younger groups may still be pending
-        fetch(r + (PLIK_RING - 1) * stride, buf == 0 ? PLIK_RING - 1 : buf - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(PLIK_RING - 1) : "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         const float c = cal[r];
         const float scale = units_factor / (c * c);
-        __syncthreads();                                         // row r has landed for every thread
+        float vmax = 0.f;
+        __syncthreads();                                         // row r has landed for every thread, and every thread has
+                                                                 // finished the previous row (its buffer, vrow, wmax are free)
+        fetch(r + stride, buf ^ 1);                              // the next row streams in while this one is binned
         const float* row = plik_smem + buf * row_floats;
 #pragma unroll
         for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
@@ -122,12 +137,43 @@ plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te
                 if (my[p].bin >= 0) {
                     const float model = sum * scale;
                     if (binned) binned[r * binned_pitch + my[p].bin] = model;
-                    diff[r * diff_pitch + my[p].bin] = my[p].x_data - model;
+                    const float d = my[p].x_data - model;
+                    if (tiles) { const float v = d * my[p].sqrt_f; vrow[my[p].bin] = v; vmax = fmaxf(vmax, fabsf(v)); }
+                    else diff[r * diff_pitch + my[p].bin] = d;
                 }
             }
         }
-        __syncthreads();                                         // this row buffer may be overwritten
-        buf = buf + 1 == PLIK_RING ? 0 : buf + 1;
+        if (tiles) {
+            // Tensor-core quadratic form: v_i = d_i sqrt(F_ii), scaled by a power of two q so that max |v_i| q lies in
+            // [0.5, 1).  Written twice: fp32 (the epilogue's dot product) and as the contraction's A operand - split
+            // fp16 hi/lo of 1024 q v in the swizzled K-major tile layout the fused kernel's loader streams.
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = vmax;
+            __syncthreads();
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < PLIK_BIN_THREADS / 32; ++i) m = fmaxf(m, wmax[i]);
+            float q = 1.f;
+            if (m > 0.f && m < 3.0e38f) { int ex; frexpf(m, &ex); q = ldexpf(1.f, -ex); }
+            for (int k = threadIdx.x; k < diff_pitch; k += PLIK_BIN_THREADS) diff[r * diff_pitch + k] = vrow[k] * q;
+            if (threadIdx.x < diff_pitch / 8) {
+                const int ch = threadIdx.x, stage = ch >> 2, kchunk = ch & 3;
+                const int rt = static_cast<int>(r & 127);
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = vrow[8 * ch + j] * q * 1024.f;
+                uint4 hi, lo;
+                plik_split2(x[0], x[1], hi.x, lo.x); plik_split2(x[2], x[3], hi.y, lo.y);
+                plik_split2(x[4], x[5], hi.z, lo.z); plik_split2(x[6], x[7], hi.w, lo.w);
+                uint8_t* t = tiles + (r >> 7) * (static_cast<long long>(diff_pitch / 32) * 16384) + stage * 16384
+                           + rt * 64 + ((kchunk ^ (rt >> 1)) & 3) * 16;
+                *reinterpret_cast<uint4*>(t) = hi;
+                *reinterpret_cast<uint4*>(t + 8192) = lo;
+            }
+            if (threadIdx.x == 0) row_scale[r] = q;
+        }
+        buf ^= 1;
     }
 }
 
@@ -222,6 +268,19 @@ __global__ void plik_finish_kernel(const float* __restrict__ partial, int n_jt, 
     float s = 0.f;
     for (int j = 0; j < n_jt; ++j) s += partial[r * n_jt + j];
     loglike[r] = -s;
+}
+
+
+// tensor-core quadratic form: loglike = -0.5 chi^2 = -(acc_scale / q^2) * (sum of the row's partial dot products)
+__global__ void plik_finish_tensor_kernel(const float* __restrict__ partial, int n_part, const float* __restrict__ row_scale,
+                                          float acc_scale, long long n_rows, float* __restrict__ loglike)
+{
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    float s = 0.f;
+    for (int j = 0; j < n_part; ++j) s += partial[r * n_part + j];
+    const float q = row_scale[r];
+    loglike[r] = -(s * acc_scale) / (q * q);
 }
 
 }  // namespace cpb

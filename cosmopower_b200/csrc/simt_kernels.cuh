@@ -13,7 +13,8 @@ namespace cpb {
 enum Epilogue : int {
     EPI_ACT = 0,     // h = (beta + (1-beta) * sigmoid(alpha * a)) * a,  a = acc + b   (NN.py:375-378)
     EPI_AFFINE = 1,  // h = acc * scale + shift   (PCA coefficient rescale, PCAplusNN.py:381, inner part)
-    EPI_OUT = 2      // y = acc * scale + shift, optional 10**y   (NN.py:381-384,425)
+    EPI_OUT = 2,     // y = acc * scale + shift, optional 10**y   (NN.py:381-384,425)
+    EPI_QUADFORM = 3 // tensor-core path only: row-wise dot of the accumulator with the operand rows (Planck-lite chi^2)
 };
 
 constexpr int SIMT_BM = 64, SIMT_BN = 64, SIMT_BK = 16;

@@ -81,6 +81,7 @@ struct UmmaGemm {
     int n_chunks;
     int epi_kind;          // cpb::Epilogue
     float acc_scale;       // undoes the power-of-two operand pre-scales on the accumulator (EPI_ACT)
+    int tri;               // upper-triangular weights: chunk c only needs the K stages up to its last column
 };
 
 struct UmmaParams {
@@ -108,7 +109,15 @@ struct UmmaParams {
                                   // constant bank with the other parameters, so every role decodes it with uniform loads
     int n_jobs;
     int* error_flag;           // set to a code by the watchdog before trapping
-    unsigned long long* max_cycles;   // every launch: max over CTAs of the SM cycles between kernel entry and exit
+    unsigned long long* max_cycles;
+    // quadratic-form mode (EPI_QUADFORM, single contraction): the layer-0 operand tiles are prebuilt in global memory
+    // (tile i at ext_a0 + i * a0_bytes, the layout the standardiser would write), qf_d holds the same rows in fp32
+    // (row pitch qf_pitch, qf_cols valid columns) and qf_partial receives 2 * n_chunks partial sums per row
+    const uint8_t* ext_a0;
+    const float* qf_d;
+    long long qf_pitch;
+    int qf_cols;
+    float* qf_partial;   // every launch: max over CTAs of the SM cycles between kernel entry and exit
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
 };
 
@@ -491,6 +500,44 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     }
 }
 
+// quadratic form: partial[row] = sum over this warp's columns of acc[row][col] * d[row][col], where d is the fp32 copy
+// of the operand rows (the contraction's own A operand).  Columns follow the operand packing: a lane owns 8 consecutive
+// logical columns, so d is read 32 bytes at a time, four lanes covering a 128-byte line of a row.
+__device__ __forceinline__ void epi_chunk_quadform(const EpiCtx& E, const float* drow0, long long pitch, long long rows_left,
+                                                   int n_cols, float* part0, int part_pitch, int lane) {
+    const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
+    constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};                 // rows tq, tq + 8, tq + 16, tq + 24 of this lane quarter
+    const int row_in_q = E.q * 32 + E.tq;
+    uint32_t va[16], vb[16];
+    for (int pc = E.cw * UM_PIECE; pc < E.nc; pc += kStep) {
+        const int gc = E.chunk_col0 + pc + 8 * E.tr;
+        tmem_ld_16x256b_x4(E.t_addr0 + pc, va);
+        tmem_ld_16x256b_x4(t_addr1 + pc, vb);
+        tmem_ld_wait16(va);
+        tmem_ld_wait16(vb);
+        if (gc + 8 <= n_cols) {
+#pragma unroll
+            for (int rw = 0; rw < 4; ++rw) {
+                if (row_in_q + 8 * rw < rows_left) {
+                    float d[8];
+                    ldg_v8(drow0 + static_cast<long long>(8 * rw) * pitch + gc, d);
+                    const uint32_t (&v)[16] = rw < 2 ? va : vb;
+                    const int rr = rw & 1;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sum[rw] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), d[j], sum[rw]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int rw = 0; rw < 4; ++rw) {
+        sum[rw] += __shfl_xor_sync(0xffffffffu, sum[rw], 1);
+        sum[rw] += __shfl_xor_sync(0xffffffffu, sum[rw], 2);
+        if ((lane & 3) == 0 && row_in_q + 8 * rw < rows_left) part0[static_cast<long long>(8 * rw) * part_pitch] = sum[rw];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -561,6 +608,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     // behind the previous pair's output phase instead of stalling the tensor pipe at every pair start
     const long long n_my_pg = P.n_pairgroups > pg_first ? (P.n_pairgroups - pg_first + pg_step - 1) / pg_step : 0;
     const int n_jobs = P.n_jobs;
+    // K stages job (g, c) runs: all of them, or - for upper-triangular weights - those up to the chunk's last column
+    auto job_stages = [&](const UmmaGemm& L, int c) { return L.tri ? min(L.k_stages, ((c + 1) * L.nc) / UM_KS) : L.k_stages; };
 
     uint8_t* cta_scratch = P.scratch + static_cast<unsigned long long>(blockIdx.x) * P.scratch_cta_bytes;
     auto a0_buf = [&](int t) { return cta_scratch + static_cast<size_t>(t) * P.a0_bytes; };
@@ -608,14 +657,15 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             int job = 0;
             UM_FOR_EACH_JOB({
                 const UmmaGemm& L = P.g[g];
-                const int k_stages = L.k_stages;
+                const int k_stages = job_stages(L, c);
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
                 const long long j_t0 = now(), j_we0 = w_empty, j_wa0 = w_aready;
-                if (c == 0) {                                     // the whole K extent of this tile's operand must be written
+                if (c == 0 && !(g == 0 && P.ext_a0)) {            // the whole K extent of this tile's operand must be written
                     if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), (ph_a0ready >> t) & 1, P.error_flag, 101); ph_a0ready ^= 1u << t; }
                     else { w_aready += mbar_wait(bar_aready(t), (ph_aready >> t) & 1, P.error_flag, 102); ph_aready ^= 1u << t; }
                 }
-                const uint8_t* a_src = g == 0 ? a0_buf(t) : in_buf(g, t, pidx);
+                const uint8_t* a_src = g != 0 ? in_buf(g, t, pidx)
+                                     : P.ext_a0 ? P.ext_a0 + static_cast<size_t>(pair * 2 + t) * P.a0_bytes : a0_buf(t);
                 {   // this chunk's per-column epilogue constants -> shared memory (ring indexed by the job count)
                     const int pb = job & (UM_PAR_SLOTS - 1);
                     w_empty += mbar_wait(bar_parempty(pb), (ph_parempty >> pb) & 1, P.error_flag, 104); ph_parempty ^= 1u << pb;
@@ -630,7 +680,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     }
                 }
                 // this CTA's half of each weight stage ([hi | lo] of its nc/2 columns)
-                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack) + static_cast<size_t>(c) * k_stages * b_bytes
+                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack) + static_cast<size_t>(c) * L.k_stages * b_bytes
                                      + cta_rank * (b_bytes / 2);
                 // an activation tile is dead after its last chunk has streamed it
                 const uint64_t pol_a = c == L.n_chunks - 1 ? pol_stream : pol_keep;
@@ -671,7 +721,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const uint32_t leader_full0 = map_to_cta(bar_full(0), 0);     // the leader's full barriers
             UM_FOR_EACH_JOB({
                 (void)t;
-                const int ks = P.g[g].k_stages;
+                const int ks = job_stages(P.g[g], c);
                 for (int i = 0; i < ks; ++i) {
                     mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
                     if (elect_one()) mbar_arrive_remote_relaxed(leader_full0 + 8u * stage);
@@ -689,7 +739,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const uint64_t b_hi0 = umma_desc(base + UM_SMEM_STAGES + UM_A_STAGE_BYTES);
             UM_FOR_EACH_JOB({
                 const UmmaGemm& L = P.g[g];
-                const int k_stages = L.k_stages;
+                const int k_stages = job_stages(L, c);
                 const uint32_t idesc = umma_idesc(L.nc);
                 const uint64_t b_lo_off = static_cast<uint64_t>((static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u) >> 4);   // (hi -> lo half tile) >> 4
                 const int buf = job & 1;
@@ -743,7 +793,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         uint32_t ph_a0free[2] = {1, 1};
         long long w_in = 0; const long long t_begin = now();
         const int np = P.n_parameters;
-        for (long long pgi = 0; pgi < n_my_pg; ++pgi) {
+        for (long long pgi = 0; pgi < (P.ext_a0 ? 0 : n_my_pg); ++pgi) {      // (prebuilt operand tiles: nothing to do)
             const long long pair = (pg_first + pgi * pg_step) * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding
             for (int t = 0; t < 2; ++t) {
                 w_in += mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
@@ -824,6 +874,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             } else
             if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, out_buf(g, t, pidx));
             else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, out_buf(g, t, pidx));
+            else if (L.epi_kind == EPI_QUADFORM)
+                epi_chunk_quadform(E, P.qf_d + (row0 + q * 32 + tq) * P.qf_pitch, P.qf_pitch, P.n_rows - row0, P.qf_cols,
+                                   P.qf_partial + (row0 + q * 32 + tq) * (2 * L.n_chunks) + 2 * c + cw, 2 * L.n_chunks, lane);
             else {
                 const bool rows_ok = row0 + UM_TILE_M <= P.n_rows;
                 // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
@@ -845,7 +898,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 else mbar_arrive_remote_relaxed(accempty_leader0 + 8u * buf);   // TMEM reads are complete (wait::ld)
                 mbar_arrive(bar_parempty(pb));
             }
-            if (L.epi_kind != EPI_OUT && c == L.n_chunks - 1) {
+            if (L.epi_kind <= EPI_AFFINE && c == L.n_chunks - 1) {     // operand-producing kinds
                 // the next layer's loader may only read the scratch once every chunk of this layer is
                 // written: one fence per thread before the last chunk's arrive covers all its stores
                 UM_SCRATCH_FENCE(); fence_proxy_async();
@@ -862,7 +915,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const uint8_t* dead = in_buf(g, t, pidx) + (lane >> 4) * UM_A_HALF_BYTES + q * 2048 + (lane & 15) * 128;
                 for (int sd = cw; sd < L.k_stages; sd += UM_EPI_WARPS / 4) l2_discard_line(dead + static_cast<size_t>(sd) * UM_A_STAGE_BYTES);
             }
-            if (L.epi_kind == EPI_OUT) c_out += now() - t_job; else c_act += now() - t_job;
+            if (L.epi_kind >= EPI_OUT) c_out += now() - t_job; else c_act += now() - t_job;
             if (PROF && P.counters && blockIdx.x == 0 && ew == 0 && lane == 0) {
                 long long* jc = P.counters + (gridDim.x + ji) * UM_CNT_SLOTS;
                 const long long j_t1 = now();

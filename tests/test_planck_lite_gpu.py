@@ -82,6 +82,38 @@ def test_ragged_sizes_and_tight_pitch(plik, n):
     assert torch.equal(ll, ll2)                       # the vector and scalar load paths agree bit for bit
 
 
+def test_tensor_core_quadratic_form_against_the_fp32_cuda_core_one(plik):
+    """Two independent implementations of chi^2 (split-fp16 tcgen05 contraction vs fp32 FMA kernel) on 20000 rows whose
+    chi^2 spans twelve decades; both share the binning kernel."""
+    import torch
+    from cosmopower_b200 import _engine
+    from cosmopower_b200.likelihoods import planck2018_lite as pl
+    d = planck_lite_np.load_data()
+    first, start, window, _, _ = pl.binning_tables(d["blmin"], d["blmax"], d["bin_w"].astype(np.float32))
+    os.environ["CPB200_PLIK_FP32"] = "1"
+    try:
+        ref_eng = _engine.PlikEngine(planck_lite_np.N_ELL, start, first, window, d["X_data"].astype(np.float32),
+                                     pl.fisher_from_covariance(d["cov"]), (2.7255e6) ** 2, device=0)
+    finally:
+        del os.environ["CPB200_PLIK_FP32"]
+    n = 20000
+    rng = np.random.default_rng(99)
+    o = planck_lite_np.PlanckLiteOracle()
+    nl = planck_lite_np.N_ELL
+    cl = np.abs(rng.standard_normal((n, 3 * nl))) * 1e-12
+    eps = 10.0 ** rng.uniform(-4, 2, size=(n, 1))
+    cl[:, o.indices] = o.X_data[o.indices_rep] * (1 + eps * rng.standard_normal((n, o.indices.size))) / o.units_factor
+    parts = [_padded(cl[:, i * nl:(i + 1) * nl]) for i in range(3)]
+    cal = torch.ones(n, device="cuda")
+    a = plik.loglike_torch(*parts, cal).cpu().numpy().astype(np.float64)
+    b = ref_eng.loglike_torch(*parts, cal).cpu().numpy().astype(np.float64)
+    ref_eng.close()
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    err = np.abs(a - b)
+    assert (err <= TOL_REL * np.abs(b) + TOL_ABS).all(), float((err / (np.abs(b) + 1)).max())
+    assert -2 * b.max() < 1e3 and -2 * b.min() > 1e9        # the range really was covered
+
+
 def test_empty_batch(plik):
     import torch
     e = torch.empty((0, planck_lite_np.N_ELL), dtype=torch.float32, device="cuda")
