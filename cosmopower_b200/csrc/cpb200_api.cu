@@ -373,42 +373,42 @@ namespace {
 // contraction, size the per-CTA scratch, build the job table, opt in to the kernel's shared memory.
 int setup_umma(cpb200_engine* e) {
     int rc;
-        int k_pad = round_up(e->P, cpb::UM_KS);
-        unsigned max_stages = 1;
-        for (size_t i = 0; i < e->gemms.size(); ++i) {
-            Gemm& g = e->gemms[i];
-            const float s_in = i == 0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
-            if ((rc = pack_umma(g, k_pad, s_in, cpb::UM_ACT_SCALE))) return rc;
-            if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
-            k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
-        }
-        e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
-        e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
-        e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes;
-        if (e->gemms.size() == 1 && e->gemms[0].epi == cpb::EPI_QUADFORM) e->um_scratch_cta = 1024;   // operand tiles are prebuilt elsewhere
-        {
-            std::vector<unsigned> jobs = build_jobs(e->gemms);
-            if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
-                return (fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
-            e->n_jobs = static_cast<int>(jobs.size());
-            e->jobs = jobs;
-        }
-        const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
-        if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
-            return (fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
-        if (cudaMemset(e->um_scratch, 0, total) != cudaSuccess) return (fail(CPB200_E_CUDA, "memset failed"));
-        if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
-            cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess ||
-            cudaMalloc(reinterpret_cast<void**>(&e->d_max_cycles), sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
-            return (fail(CPB200_E_CUDA, "error flag allocation failed"));
-        if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 cpb::UM_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 cpb::UM_SMEM_BYTES) != cudaSuccess)
-            return (fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
-                             cudaGetErrorString(cudaGetLastError())));
-        return 0;
+    int k_pad = round_up(e->P, cpb::UM_KS);
+    unsigned max_stages = 1;
+    for (size_t i = 0; i < e->gemms.size(); ++i) {
+        Gemm& g = e->gemms[i];
+        const float s_in = i == 0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
+        if ((rc = pack_umma(g, k_pad, s_in, cpb::UM_ACT_SCALE))) return rc;
+        if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
+        k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
+    }
+    e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
+    e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
+    e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes;
+    if (e->gemms.size() == 1 && e->gemms[0].epi == cpb::EPI_QUADFORM) e->um_scratch_cta = 1024;   // operand tiles are prebuilt elsewhere
+    {
+        std::vector<unsigned> jobs = build_jobs(e->gemms);
+        if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
+            return (fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
+        e->n_jobs = static_cast<int>(jobs.size());
+        e->jobs = jobs;
+    }
+    const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
+    if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
+        return (fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaMemset(e->um_scratch, 0, total) != cudaSuccess) return (fail(CPB200_E_CUDA, "memset failed"));
+    if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
+        cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&e->d_max_cycles), sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
+        return (fail(CPB200_E_CUDA, "error flag allocation failed"));
+    if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             cpb::UM_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             cpb::UM_SMEM_BYTES) != cudaSuccess)
+        return (fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
+                         cudaGetErrorString(cudaGetLastError())));
+    return 0;
 }
 }  // namespace
 
@@ -789,7 +789,8 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     p->n_passes = n_passes;
     p->bin_smem = bin_smem;
     if ((rc = upload(&p->d_slots, slots.data(), slots.size()))) return bail(rc);
-    {   // F' = strict upper triangle of the symmetrised F + half its diagonal: chi^2 = 2 d^T F' d
+    if (getenv("CPB200_PLIK_FP32") != nullptr) {   // fp32 cross-check path: F' = strict upper triangle of the symmetrised F
+        // + half its diagonal, chi^2 = 2 d^T F' d
         std::vector<float> fp(static_cast<size_t>(p->pad) * p->pad, 0.f);
         for (int i = 0; i < d->n_bins; ++i)
             for (int j = i; j < d->n_bins; ++j) {
