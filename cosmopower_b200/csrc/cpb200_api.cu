@@ -871,7 +871,7 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
     const size_t smem = p->bin_smem;
     for (int64_t r0 = 0; r0 < n_rows; r0 += p->chunk_rows) {
         const int64_t m = std::min<int64_t>(p->chunk_rows, n_rows - r0);
-        const int grid_bin = static_cast<int>(std::min<int64_t>(m, static_cast<int64_t>(p->num_sms) * 3));
+        const int grid_bin = static_cast<int>(std::min<int64_t>(m, static_cast<int64_t>(p->num_sms) * cpb::PLIK_BLOCKS_PER_SM));
         cpb::plik_bin_kernel<<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
             cl_tt + r0 * pitch, cl_te + r0 * pitch, cl_ee + r0 * pitch, pitch, cal + r0, m, p->n_ell,
             p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,

@@ -32,7 +32,8 @@ constexpr int PLIK_QF_BM = 128, PLIK_QF_BN = 128, PLIK_QF_BK = 16;
 constexpr int PLIK_SEG = 9;
 constexpr int PLIK_MAX_PASSES = 3;
 constexpr int PLIK_MAX_SLOTS_PER_BIN = 4;
-constexpr int PLIK_RING = 2;             // row buffers per block: one being binned, one in flight
+constexpr int PLIK_RING = 3;             // row buffers per block: one being binned, two in flight
+constexpr int PLIK_BLOCKS_PER_SM = 2;
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
@@ -60,7 +61,7 @@ struct PlikSlot {          // one per slot, built by cpb200_plik_create
     float w[PLIK_SEG];     // window weights, zero beyond the slot's end
 };
 
-__global__ void __launch_bounds__(PLIK_BIN_THREADS, 3)
+__global__ void __launch_bounds__(PLIK_BIN_THREADS, PLIK_BLOCKS_PER_SM)
 plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te, const float* __restrict__ cl_ee,
                 long long pitch, const float* __restrict__ cal, long long n_rows, int n_ell,
                 const PlikSlot* __restrict__ slots, int n_passes, float units_factor,
@@ -107,16 +108,17 @@ plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te
 
     const long long stride = gridDim.x;
     long long r = blockIdx.x;
-    fetch(r, 0);
+#pragma unroll
+    for (int i = 0; i < PLIK_RING - 1; ++i) fetch(r + i * stride, i);
     int buf = 0;
     for (; r < n_rows; r += stride) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(PLIK_RING - 2) : "memory");    // row r has landed; younger rows may be in flight
         const float c = cal[r];
         const float scale = units_factor / (c * c);
         float vmax = 0.f;
-        __syncthreads();                                         // row r has landed for every thread, and every thread has
-                                                                 // finished the previous row (its buffer, vrow, wmax are free)
-        fetch(r + stride, buf ^ 1);                              // the next row streams in while this one is binned
+        __syncthreads();                                         // ... for every thread, and every thread has finished the
+                                                                 // previous row (its buffer, vrow, wmax are free)
+        fetch(r + (PLIK_RING - 1) * stride, buf == 0 ? PLIK_RING - 1 : buf - 1);     // refill the buffer of the previous row
         const float* row = plik_smem + buf * row_floats;
 #pragma unroll
         for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
@@ -173,7 +175,7 @@ plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te
             }
             if (threadIdx.x == 0) row_scale[r] = q;
         }
-        buf ^= 1;
+        buf = buf + 1 == PLIK_RING ? 0 : buf + 1;
     }
 }
 
