@@ -420,11 +420,12 @@ __device__ __forceinline__ void ldg_v8(const float* p, float (&y)[8]) {
 }
 
 // store mode of one lane's 8 consecutive output columns
-enum { OUT_SCALAR = 0, OUT_VEC16 = 1, OUT_VEC32 = 2 };
+enum { OUT_NONE = -1, OUT_SCALAR = 0, OUT_VEC16 = 1, OUT_VEC32 = 2 };
 
 template <bool TEN_TO, bool ACC>
 __device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const float2 (&pp)[8], float* drow, long long pitch,
                                                 int mode, int row_in_q, long long rows_left, int gc, int n_modes, int dbg) {
+    if (mode == OUT_NONE) return;
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
         float y[8];
@@ -479,8 +480,10 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
     int pc = E.cw * UM_PIECE;
     uint32_t va[16], vb[16];
-    if (pc < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);            // TMEM reads run one half piece ahead of the math
-    for (; pc < E.nc; pc += kStep) {
+    // the last chunk of a layer is usually not full: pieces that start beyond the last mode are skipped altogether
+    const int nc_valid = min(E.nc, n_modes - E.chunk_col0);
+    if (pc < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);        // TMEM reads run one half piece ahead of the math
+    for (; pc < nc_valid; pc += kStep) {
         float2 pp[8];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
@@ -489,13 +492,13 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
             pp[2 * m + 1] = make_float2(q4.z, q4.w);
         }
         const int gc = E.chunk_col0 + pc + 8 * E.tr;
-        const int mode = gc + 8 <= n_modes ? vec_mode : OUT_SCALAR;
+        const int mode = gc + 8 <= n_modes ? vec_mode : gc < n_modes ? OUT_SCALAR : OUT_NONE;   // OUT_NONE: nothing of this lane's is a mode
         float* drow = orow0 + gc;                                       // row 32q + tq of the tile
         tmem_ld_wait16(va);
         tmem_ld_16x256b_x4(t_addr1 + pc, vb);
         epi_output_half<TEN_TO, ACC>(va, pp, drow, pitch, mode, E.q * 32 + E.tq, rows_left, gc, n_modes, E.dbg);
         tmem_ld_wait16(vb);
-        if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
+        if (pc + kStep < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
         epi_output_half<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, pitch, mode, E.q * 32 + E.tq + 16, rows_left, gc, n_modes, E.dbg);
     }
 }
