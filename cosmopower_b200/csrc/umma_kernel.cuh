@@ -20,15 +20,19 @@
 // the other; the order of jobs is a host-built table (layer 0 of the next pair is merged into the
 // current pair's output phase).
 //
-// Warp roles (384 threads): warp 0 loader (bulk copies), warp 1 MMA issuer (one thread of the leader
-// CTA; relay thread in the peer), warp 2 TMEM allocator + parameter standardiser, warp 3 idle (or,
-// with warp 2, the optional CUDA-core first layer), warps 4..11 epilogue (2 warps per TMEM lane
-// quarter, 32-column pieces dealt alternately, TMEM reads software-pipelined half a piece ahead).
+// Warp roles (384 threads): warp 0 loader (bulk copies), warp 1 MMA issuer (leader CTA; stage relay in
+// the peer) - both walk their loops as whole warps with warp-uniform values and let one elected lane
+// issue, so addresses and descriptors stay in uniform registers -, warp 2 TMEM allocator + parameter
+// standardiser, warp 3 idle, warps 4..11 epilogue (2 warps per TMEM lane quarter, 32-column pieces
+// dealt alternately, TMEM reads software-pipelined half a piece ahead).
 // The epilogue reads accumulators with tcgen05.ld.16x256b, whose fragment gives a thread 2 adjacent
 // columns of 2 rows; the weight columns are packed in that order, so 4 neighbouring lanes hold one
 // 64-byte tile row and the next layer's operand is written with full 128-byte lines - no
 // shared-memory transpose (the shared-memory data pipe is the scarce resource: the tensor core's
 // operand reads and the bulk copies already use most of it).
+//
+// The same pipeline also evaluates the Planck-lite chi^2 (EPI_QUADFORM): one upper-triangular contraction
+// whose layer-0 operand tiles are prebuilt by plik_bin_kernel (UmmaParams::ext_a0), see plik_kernels.cuh.
 //
 // Reference math: cosmopower/cosmopower_NN.py:371-384,425 and
 // cosmopower/cosmopower_PCAplusNN.py:368-381,421.
@@ -837,7 +841,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
     } else if (warp >= UM_EPI_WARP0) {
         // ===================== epilogue warps =====================
-        const int ew = warp - UM_EPI_WARP0;          // 0..15
+        const int ew = warp - UM_EPI_WARP0;          // 0..7
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int cw = ew >> 2;                      // which of the lane quarter's warps: takes every (UM_EPI_WARPS/4)-th 32-column piece
         const float4* epipar = reinterpret_cast<const float4*>(sbase + UM_SMEM_EPIPAR);
