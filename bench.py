@@ -148,8 +148,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "spectra/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cmb_TT_NN + cmb_EE_NN ten_to_predictions_np, 1M-batch config timed on a bounded sample",
-                   "models": "synthetic stand-ins (documented architecture 6-512x4-2507)", "sample_rows_per_model": sample},
+        "config": {"workload": "cmb_TT_NN + cmb_EE_NN, ten_to_predictions, %d-row batch per model per GPU" % (1 << 20),
+                   "models": "synthetic stand-ins (documented architecture 6-512x4-2507; pickles stripped upstream)",
+                   "timed_on": "a bounded sample of that batch: %d rows per model per step" % sample, "sample_rows_per_model": sample},
         "cpu_baseline": {"value": v, "unit": "spectra/s", "cores": cores, "kind": "port",
                          "sample": "%d rows per model per step, float64 inputs, NumPy/OpenBLAS oracle port of "
                                    "cosmopower_NN.ten_to_predictions_np (the reference checkout is absent on the GPU box)" % sample},
