@@ -114,6 +114,32 @@ def test_tensor_core_quadratic_form_against_the_fp32_cuda_core_one(plik):
     assert -2 * b.max() < 1e3 and -2 * b.min() > 1e9        # the range really was covered
 
 
+def test_calibration_scaling_property_at_full_chunk_size(plik):
+    """X_model = C_bin / A_planck^2 (tf_planck2018_lite.py:294): scaling every spectrum by a^2 and the calibration by a
+    must not change the log-likelihood.  150 000 rows (more than one engine chunk), a = 2 is exact in binary."""
+    import torch
+    n = 150000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    o = planck_lite_np.PlanckLiteOracle()
+    nl = planck_lite_np.N_ELL
+    base = torch.zeros((1, 3 * nl), dtype=torch.float32, device="cuda")
+    base[0, torch.from_numpy(o.indices).cuda()] = torch.from_numpy((o.X_data[o.indices_rep] / o.units_factor).astype(np.float32)).cuda()
+    noise = 1 + 0.05 * torch.randn((n, 3 * nl), generator=g, device="cuda")
+    cl = base * noise
+    parts = []
+    for i in range(3):
+        buf = torch.empty((n, 2512), dtype=torch.float32, device="cuda")[:, :nl]
+        buf.copy_(cl[:, i * nl:(i + 1) * nl])
+        parts.append(buf)
+    cal = 1 + 0.0025 * torch.randn(n, generator=g, device="cuda")
+    ll1 = plik.loglike_torch(*parts, cal)
+    for p in parts:
+        p.mul_(4.0)
+    ll2 = plik.loglike_torch(*parts, cal * 2.0)
+    assert torch.isfinite(ll1).all()
+    assert torch.equal(ll1, ll2)          # powers of two commute with every rounding on the path
+
+
 def test_empty_batch(plik):
     import torch
     e = torch.empty((0, planck_lite_np.N_ELL), dtype=torch.float32, device="cuda")
