@@ -35,7 +35,7 @@ class ModelDesc(ctypes.Structure):
 class PlikDesc(ctypes.Structure):
     _fields_ = [("n_ell", ctypes.c_int32), ("n_bins", ctypes.c_int32), ("n_gather", ctypes.c_int32),
                 ("bin_start", ctypes.POINTER(ctypes.c_int32)), ("gather_first", ctypes.POINTER(ctypes.c_int32)),
-                ("window", _fp), ("x_data", _fp), ("fisher", _fp), ("units_factor", ctypes.c_float)]
+                ("window", _fp), ("x_data", _fp), ("fisher", _fp), ("units_factor", ctypes.c_float), ("te_binned", ctypes.c_int32)]
 
 
 # every symbol include/cpb200.h declares: (name, restype, argtypes)
@@ -61,8 +61,8 @@ SYMBOLS = [
     ("cpb200_plik_create", ctypes.c_int, [ctypes.POINTER(PlikDesc), ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     ("cpb200_plik_destroy", ctypes.c_int, [ctypes.c_void_p]),
     ("cpb200_plik_loglike_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
-                                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+                                                  ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     ("cpb200_plik_launch_count", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_last_error", ctypes.c_char_p, []),
 ]
@@ -271,7 +271,7 @@ class Engine:
 class PlikEngine:
     """Device-side Planck-lite likelihood tail (cpb200_plik_*): band-power binning + Fisher quadratic form."""
 
-    def __init__(self, n_ell, bin_start, gather_first, window, x_data, fisher, units_factor, device=0):
+    def __init__(self, n_ell, bin_start, gather_first, window, x_data, fisher, units_factor, device=0, te_binned=False):
         lib = load_library()
         self._lib = lib
         self._keep = [np.ascontiguousarray(bin_start, dtype=np.int32), np.ascontiguousarray(gather_first, dtype=np.int32),
@@ -282,7 +282,9 @@ class PlikEngine:
             raise ValueError("inconsistent likelihood tables")
         ip = ctypes.POINTER(ctypes.c_int32)
         desc = PlikDesc(self.n_ell, self.n_bins, int(w.size), bs.ctypes.data_as(ip), gf.ctypes.data_as(ip),
-                        _ptr(w), _ptr(xd), _ptr(f), float(units_factor))
+                        _ptr(w), _ptr(xd), _ptr(f), float(units_factor), 1 if te_binned else 0)
+        self.te_binned = bool(te_binned)
+        self.n_te_bins = int(np.sum(gf // self.n_ell == 1))
         h = ctypes.c_void_p()
         _check(lib.cpb200_plik_create(ctypes.byref(desc), self.device, ctypes.byref(h)))
         self._h = h
@@ -307,12 +309,12 @@ class PlikEngine:
         Returns loglike (N,) [and the (N, n_bins) model band powers]."""
         import torch
         n = int(cl_tt.shape[0])
-        for t in (cl_tt, cl_te, cl_ee):
-            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape == cl_tt.shape and
-                    t.shape[1] == self.n_ell and t.stride(1) == 1 and t.stride(0) == cl_tt.stride(0) and
-                    t.device.index == self.device):
-                raise ValueError("spectra must be CUDA float32 (N, %d) tensors on device %d with a common row stride"
-                                 % (self.n_ell, self.device))
+        for t, width in ((cl_tt, self.n_ell), (cl_te, self.n_te_bins if self.te_binned else self.n_ell), (cl_ee, self.n_ell)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[0] == n and t.shape[1] == width and
+                    t.stride(1) == 1 and t.device.index == self.device):
+                raise ValueError("inputs must be CUDA float32 (N, %d) tensors on device %d" % (width, self.device))
+        if cl_tt.stride(0) != cl_ee.stride(0) or (not self.te_binned and cl_te.stride(0) != cl_tt.stride(0)):
+            raise ValueError("the spectra must share one row stride")
         cal = cal.to(device=cl_tt.device, dtype=torch.float32).contiguous().reshape(-1)
         if cal.numel() != n:
             raise ValueError("cal must hold one A_planck per row")
@@ -321,6 +323,6 @@ class PlikEngine:
         stream = torch.cuda.current_stream(cl_tt.device).cuda_stream
         _check(self._lib.cpb200_plik_loglike_device(
             self._h, cl_tt.data_ptr(), cl_te.data_ptr(), cl_ee.data_ptr(), int(cl_tt.stride(0)) if n else self.n_ell,
-            cal.data_ptr(), n, out.data_ptr(), binned.data_ptr() if return_binned else None,
+            int(cl_te.stride(0)) if n else self.n_ell, cal.data_ptr(), n, out.data_ptr(), binned.data_ptr() if return_binned else None,
             self.n_bins, ctypes.c_void_p(stream)))
         return (out, binned) if return_binned else out

@@ -179,6 +179,9 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
     ex = std::max(-10, std::min(14, ex));
     const float s_w = std::ldexp(1.f, ex);
     if (wmax * s_w > 60000.f) return fail(CPB200_E_RANGE, "weight %g outside the fp16 split range", static_cast<double>(wmax));
+    if (wmax > 0.f && wmax * s_w < 1024.f)      // the scale is capped at 2^14: a tinier matrix would lose its lo parts to fp16 underflow
+        return fail(CPB200_E_RANGE, "largest weight %g of a layer is below the fp16 split range; rescale the layer "
+                    "(fold the factor into features_std_ / the next layer)", static_cast<double>(wmax));
     // The tensor core truncates (does not round) the fp32 accumulator after each of the 3*K/16 MMA steps,
     // which shrinks |acc| by about half an ulp per step; (1 + bias_ulps * 2^-24) undoes the mean of that.
     float bias_ulps = cpb::UM_TRUNC_BIAS_ULPS_PER_STEP * 3.f * static_cast<float>(k_pad / 16);
@@ -696,6 +699,8 @@ float cpb200_engine_last_kernel_ms(cpb200_engine* e) {
 struct cpb200_plik {
     int device = 0;
     int n_ell = 0, n_bins = 0, n_gather = 0, pad = 0, n_jt = 0, num_sms = 0;
+    int in_len[3] = {0, 0, 0};          // floats per input row: n_ell, or the TE bin count when TE arrives binned
+    bool te_binned = false;
     float units_factor = 0.f;
     cpb::PlikSlot* d_slots = nullptr;   // runs of <= PLIK_SEG consecutive multipoles of one bin (plik_bin_kernel)
     int n_passes = 0;
@@ -747,26 +752,39 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     CU(cudaGetDeviceProperties(&prop, device));
     // split the bins into slots of at most PLIK_SEG multipoles (plik_bin_kernel); a bin's slots sit on neighbouring
     // lanes of one warp (dummy slots pad to the next warp when they would straddle it)
-    const int rs = round_up(d->n_ell, 4);
+    const bool te_binned = d->te_binned != 0;
+    // which spectrum a bin belongs to, and the bins of TE (needed when TE arrives binned)
+    int te_bin0 = -1, te_bins = 0;
+    for (int b = 0; b < d->n_bins; ++b)
+        if (d->gather_first[b] / d->n_ell == 1) { if (te_bin0 < 0) te_bin0 = b; ++te_bins; }
+    if (te_binned && te_bins == 0) return fail(CPB200_E_INVALID, "te_binned set, but no bin gathers from the TE spectrum");
+    const int in_len[3] = {d->n_ell, te_binned ? te_bins : d->n_ell, d->n_ell};
+    const int in_off[3] = {0, round_up(in_len[0], 4), round_up(in_len[0], 4) + round_up(in_len[1], 4)};
+    const int row_floats = in_off[2] + round_up(in_len[2], 4);
     std::vector<cpb::PlikSlot> slots;
     auto dummy = [] { cpb::PlikSlot s{}; s.bin = -1; return s; };
     for (int b = 0; b < d->n_bins; ++b) {
+        const int sp = d->gather_first[b] / d->n_ell, lo = d->gather_first[b] % d->n_ell;
+        const float sqrt_f = std::sqrt(std::max(0.f, d->fisher[static_cast<size_t>(b) * d->n_bins + b]));
+        if (sp == 1 && te_binned) {          // one element, already the band power
+            cpb::PlikSlot s = dummy();
+            s.off = in_off[1] + (b - te_bin0); s.last = 0; s.w[0] = 1.f;
+            s.bin = b; s.n_slots = 1; s.x_data = d->x_data[b]; s.sqrt_f = sqrt_f;
+            slots.push_back(s);
+            continue;
+        }
         const int len = d->bin_start[b + 1] - d->bin_start[b];
         const int ns = (len + cpb::PLIK_SEG - 1) / cpb::PLIK_SEG;
         if (ns < 1 || ns > cpb::PLIK_MAX_SLOTS_PER_BIN)
             return fail(CPB200_E_UNSUPPORTED, "bin %d gathers %d multipoles; 1 .. %d are supported", b, len, cpb::PLIK_SEG * cpb::PLIK_MAX_SLOTS_PER_BIN);
         while (static_cast<int>(slots.size() % 32) + ns > 32) slots.push_back(dummy());
-        const int sp = d->gather_first[b] / d->n_ell, lo = d->gather_first[b] % d->n_ell;
         for (int k = 0; k < ns; ++k) {
             cpb::PlikSlot s = dummy();
             const int j0 = d->bin_start[b] + k * cpb::PLIK_SEG, j1 = std::min(j0 + cpb::PLIK_SEG, d->bin_start[b + 1]);
-            s.off = sp * rs + lo + k * cpb::PLIK_SEG;
+            s.off = in_off[sp] + lo + k * cpb::PLIK_SEG;
             s.last = j1 - j0 - 1;
             for (int u = 0; u < j1 - j0; ++u) s.w[u] = d->window[j0 + u];
-            if (k == 0) {
-                s.bin = b; s.n_slots = ns; s.x_data = d->x_data[b];
-                s.sqrt_f = std::sqrt(std::max(0.f, d->fisher[static_cast<size_t>(b) * d->n_bins + b]));
-            }
+            if (k == 0) { s.bin = b; s.n_slots = ns; s.x_data = d->x_data[b]; s.sqrt_f = sqrt_f; }
             slots.push_back(s);
         }
     }
@@ -774,7 +792,7 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     const int n_passes = static_cast<int>(slots.size() / cpb::PLIK_BIN_THREADS);
     if (n_passes > cpb::PLIK_MAX_PASSES)
         return fail(CPB200_E_UNSUPPORTED, "%zu window slots exceed %d", slots.size(), cpb::PLIK_MAX_PASSES * cpb::PLIK_BIN_THREADS);
-    const size_t bin_smem = (static_cast<size_t>(cpb::PLIK_RING) * 3 * rs + round_up(d->n_bins, cpb::PLIK_QF_BN) + 8) * sizeof(float);
+    const size_t bin_smem = (static_cast<size_t>(cpb::PLIK_RING) * row_floats + round_up(d->n_bins, cpb::PLIK_QF_BN) + 8) * sizeof(float);
     if (bin_smem > prop.sharedMemPerBlockOptin)
         return fail(CPB200_E_UNSUPPORTED, "the row ring of 3 x %d multipoles does not fit one block's shared memory", d->n_ell);
     cpb200_plik* p = new cpb200_plik();
@@ -782,6 +800,8 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     p->device = device;
     p->num_sms = prop.multiProcessorCount;
     p->n_ell = d->n_ell; p->n_bins = d->n_bins; p->n_gather = d->n_gather;
+    p->te_binned = te_binned;
+    for (int i = 0; i < 3; ++i) p->in_len[i] = in_len[i];
     p->units_factor = d->units_factor;
     p->pad = round_up(d->n_bins, cpb::PLIK_QF_BN);
     p->n_jt = p->pad / cpb::PLIK_QF_BN;
@@ -858,13 +878,14 @@ int cpb200_plik_destroy(cpb200_plik* p) {
 }
 
 int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* cl_te, const float* cl_ee,
-                               int64_t pitch, const float* cal, int64_t n_rows, float* loglike, float* binned,
-                               int64_t binned_pitch, void* stream) {
+                               int64_t pitch, int64_t te_pitch, const float* cal, int64_t n_rows, float* loglike,
+                               float* binned, int64_t binned_pitch, void* stream) {
     if (!p) return fail(CPB200_E_INVALID, "null likelihood");
     if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
     if (n_rows == 0) return 0;
     if (!cl_tt || !cl_te || !cl_ee || !cal || !loglike) return fail(CPB200_E_INVALID, "null device pointer");
     if (pitch < p->n_ell) return fail(CPB200_E_INVALID, "pitch %lld < n_ell %d", static_cast<long long>(pitch), p->n_ell);
+    if (te_pitch < p->in_len[1]) return fail(CPB200_E_INVALID, "te_pitch %lld < %d", static_cast<long long>(te_pitch), p->in_len[1]);
     if (binned && binned_pitch < p->n_bins) return fail(CPB200_E_INVALID, "binned_pitch < n_bins");
     DeviceGuard guard(p->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -872,9 +893,12 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
     for (int64_t r0 = 0; r0 < n_rows; r0 += p->chunk_rows) {
         const int64_t m = std::min<int64_t>(p->chunk_rows, n_rows - r0);
         const int grid_bin = static_cast<int>(std::min<int64_t>(m, static_cast<int64_t>(p->num_sms) * cpb::PLIK_BLOCKS_PER_SM));
+        cpb::PlikInputs in;
+        in.ptr[0] = cl_tt + r0 * pitch; in.ptr[1] = cl_te + r0 * te_pitch; in.ptr[2] = cl_ee + r0 * pitch;
+        in.pitch[0] = pitch; in.pitch[1] = te_pitch; in.pitch[2] = pitch;
+        for (int i = 0; i < 3; ++i) in.len[i] = p->in_len[i];
         cpb::plik_bin_kernel<<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
-            cl_tt + r0 * pitch, cl_te + r0 * pitch, cl_ee + r0 * pitch, pitch, cal + r0, m, p->n_ell,
-            p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,
+            in, cal + r0, m, p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,
             binned ? binned + r0 * binned_pitch : nullptr, binned_pitch, p->qf ? p->d_tiles : nullptr, p->d_row_scale);
         if (p->qf) {
             cpb200_engine* q = p->qf;

@@ -52,7 +52,7 @@ __device__ __forceinline__ void plik_split2(float a, float b, uint32_t& hi, uint
 }
 
 struct PlikSlot {          // one per slot, built by cpb200_plik_create
-    int off;               // shared-memory offset of the slot's first multipole (spectrum s starts at s * round_up(n_ell, 4))
+    int off;               // shared-memory offset of the slot's first element (input s starts 16-byte aligned after input s-1)
     int last;              // index of the slot's last multipole (loads beyond it re-read that one, with weight 0)
     int bin;               // the bin this slot opens, or -1
     int n_slots;           // slots of that bin (1 .. PLIK_MAX_SLOTS_PER_BIN) when bin >= 0
@@ -61,22 +61,31 @@ struct PlikSlot {          // one per slot, built by cpb200_plik_create
     float w[PLIK_SEG];     // window weights, zero beyond the slot's end
 };
 
+// The three inputs of a row: TT, TE, EE.  Each is either a spectrum of n_ell multipoles or - TE, when its emulator was
+// built with the binning folded into its (linear) PCA basis - that spectrum's band powers already.
+struct PlikInputs {
+    const float* ptr[3];
+    long long pitch[3];
+    int len[3];            // floats per row
+};
+
 __global__ void __launch_bounds__(PLIK_BIN_THREADS, PLIK_BLOCKS_PER_SM)
-plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te, const float* __restrict__ cl_ee,
-                long long pitch, const float* __restrict__ cal, long long n_rows, int n_ell,
+plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                 const PlikSlot* __restrict__ slots, int n_passes, float units_factor,
                 float* __restrict__ diff, int diff_pitch, float* __restrict__ binned, long long binned_pitch,
                 uint8_t* __restrict__ tiles, float* __restrict__ row_scale)
 {
     extern __shared__ __align__(16) float plik_smem[];
-    const int rs = (n_ell + 3) & ~3;               // shared-memory stride of one spectrum
-    const int row_floats = 3 * rs;
+    // shared-memory layout of one row: the three inputs back to back, each starting 16-byte aligned
+    const int off1 = (in.len[0] + 3) & ~3, off2 = off1 + ((in.len[1] + 3) & ~3);
+    const int row_floats = off2 + ((in.len[2] + 3) & ~3);
     // tensor-core mode (tiles != nullptr): the row's scaled differences, then the per-warp maxima
     float* vrow = plik_smem + PLIK_RING * row_floats;
     float* wmax = vrow + diff_pitch;
     if (tiles) for (int i = threadIdx.x; i < diff_pitch; i += PLIK_BIN_THREADS) vrow[i] = 0.f;     // padding columns stay zero
-    const bool vec = (pitch & 3) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(cl_tt) | reinterpret_cast<uintptr_t>(cl_te) | reinterpret_cast<uintptr_t>(cl_ee)) & 15) == 0;
+    bool vec[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) vec[s] = (in.pitch[s] & 3) == 0 && (reinterpret_cast<uintptr_t>(in.ptr[s]) & 15) == 0;
 
     PlikSlot my[PLIK_MAX_PASSES];
 #pragma unroll
@@ -90,16 +99,17 @@ plik_bin_kernel(const float* __restrict__ cl_tt, const float* __restrict__ cl_te
     auto fetch = [&](long long r, int buf) {                    // always commits a group (empty past the last row)
         if (r < n_rows) {
             float* dst0 = plik_smem + buf * row_floats;
-            const float* src[3] = {cl_tt + r * pitch, cl_te + r * pitch, cl_ee + r * pitch};
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                float* dst = dst0 + s * rs;
-                if (vec) {
-                    const int n4 = n_ell >> 2;
-                    for (int i = threadIdx.x; i < n4; i += PLIK_BIN_THREADS) cp_async_16(dst + 4 * i, src[s] + 4 * i);
-                    for (int i = (n4 << 2) + threadIdx.x; i < n_ell; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src[s] + i);
+                const float* src = in.ptr[s] + r * in.pitch[s];
+                float* dst = dst0 + (s == 0 ? 0 : s == 1 ? off1 : off2);
+                const int len = in.len[s];
+                if (vec[s]) {
+                    const int n4 = len >> 2;
+                    for (int i = threadIdx.x; i < n4; i += PLIK_BIN_THREADS) cp_async_16(dst + 4 * i, src + 4 * i);
+                    for (int i = (n4 << 2) + threadIdx.x; i < len; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src + i);
                 } else {
-                    for (int i = threadIdx.x; i < n_ell; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src[s] + i);
+                    for (int i = threadIdx.x; i < len; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src + i);
                 }
             }
         }

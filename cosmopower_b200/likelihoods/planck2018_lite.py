@@ -64,6 +64,35 @@ def fisher_from_covariance(cov):
     return np.linalg.solve(L.T, y).T.astype(np.float32)
 
 
+def fold_binning_into_pca_emulator(attrs, first, start, window, bin0, n_bins_te, n_ell):
+    """Attributes of a cosmopower_PCAplusNN emulator that predicts the band powers of its (linear) spectrum directly.
+
+    predictions = (c . pca_std + pca_mean) . P . features_std + features_mean   (cosmopower_PCAplusNN.py:381) is linear in
+    the PCA coefficients c, and so is the binning sum_l w_l C_l (tf_planck2018_lite.py:284-291): folding the window
+    functions into the basis, P'[p][b] = sum_{l in b} P[p][l] features_std[l] w_l and mean'[b] = sum_{l in b}
+    features_mean[l] w_l, gives a 12x narrower output contraction and band powers that never exist as multipoles."""
+    P = np.asarray(attrs["pca_transform_matrix_"], dtype=np.float64)
+    fs = np.asarray(attrs["features_std_"], dtype=np.float64)
+    fm = np.asarray(attrs["features_mean_"], dtype=np.float64)
+    Pb = np.zeros((P.shape[0], n_bins_te))
+    mb = np.zeros(n_bins_te)
+    for b in range(n_bins_te):
+        lo = int(first[bin0 + b]) - n_ell                    # TE is the second block of the concatenated row
+        w = np.asarray(window[start[bin0 + b]:start[bin0 + b + 1]], dtype=np.float64)
+        sl = slice(lo, lo + w.size)
+        Pb[:, b] = (P[:, sl] * fs[sl]) @ w
+        mb[b] = fm[sl] @ w
+    col = np.abs(Pb).max(axis=0)
+    col[col == 0] = 1.0
+    out = dict(attrs)
+    out["pca_transform_matrix_"] = (Pb / col).astype(np.float32)
+    out["features_mean_"] = mb.astype(np.float32)
+    out["features_std_"] = col.astype(np.float32)
+    out["n_modes"] = n_bins_te
+    out["modes"] = np.arange(n_bins_te)
+    return out
+
+
 class _Prior:
     """Product of independent uniform / gaussian densities (reference set_priors, :331-346, without tfp)."""
 
@@ -90,7 +119,7 @@ class _Prior:
 class tf_planck2018_lite:
     def __init__(self, parameters=None, tf_planck2018_lite_path=None, spectra="TTTEEE", use_low_ell_bins=False,
                  units_factor=(2.7255e6) ** 2, tt_emu_model=None, te_emu_model=None, ee_emu_model=None, device=None,
-                 chunk_rows=262144):
+                 chunk_rows=262144, fold_te=True):
         self.parameters = parameters
         self.priors = _Prior(parameters) if parameters is not None else None
         self.spectra = spectra
@@ -143,8 +172,15 @@ class tf_planck2018_lite:
         self.fisher = self.get_inverse_covmat(d["cov"])
         self.device = device if device is not None else (getattr(tt_emu_model, "_device", None) or 0)
         self.chunk_rows = int(chunk_rows)
+        # A linear PCA emulator for TE gets the window functions folded into its basis (fold_te=True, the default):
+        # it then predicts the 199 TE band powers directly and the likelihood kernel never sees TE multipoles.
+        self._te_binned = None
+        if fold_te and hasattr(te_emu_model, "_attrs") and "pca_transform_matrix_" in te_emu_model._attrs():
+            folded = fold_binning_into_pca_emulator(te_emu_model._attrs(), first, start, self.window_ttteee.reshape(-1),
+                                                    self.nbintt, self.nbinte, n_ell)
+            self._te_binned = _engine.Engine(folded, device=self.device, precision=getattr(te_emu_model, "_precision", "f16x3"))
         self._engine = _engine.PlikEngine(n_ell, start, first, self.window_ttteee.reshape(-1), x_data, self.fisher,
-                                          units_factor, device=self.device)
+                                          units_factor, device=self.device, te_binned=self._te_binned is not None)
 
     # ===== INVERSE COVARIANCE ======  (:206-230)
     def get_inverse_covmat(self, cov):
@@ -169,7 +205,7 @@ class tf_planck2018_lite:
         for r0 in range(0, n, self.chunk_rows):
             x = cosmo[r0:r0 + self.chunk_rows]
             cl_tt = self.tt_emu_model.ten_to_predictions_tf(x)
-            cl_te = self.te_emu_model.predictions_tf(x)
+            cl_te = self._te_binned.forward_torch(x, ten_to=False) if self._te_binned is not None else self.te_emu_model.predictions_tf(x)
             cl_ee = self.ee_emu_model.ten_to_predictions_tf(x)
             out[r0:r0 + x.shape[0], 0] = self._engine.loglike_torch(cl_tt, cl_te, cl_ee, cal[r0:r0 + x.shape[0]])
         return out
@@ -193,6 +229,8 @@ class tf_planck2018_lite:
 
     def close(self):
         self._engine.close()
+        if self._te_binned is not None:
+            self._te_binned.close()
 
 
 

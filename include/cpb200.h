@@ -160,6 +160,9 @@ typedef struct {
     const float* x_data;        /* n_bins data vector (:107-109) */
     const float* fisher;        /* n_bins x n_bins, row-major, symmetric (:206-230) */
     float units_factor;         /* (T_CMB in muK)^2 (:45, :281) */
+    int32_t te_binned;          /* != 0: the TE input of cpb200_plik_loglike_device holds that spectrum's band powers (bins
+                                   215 .. 413 of the vector, before units and calibration) instead of multipoles - for a TE
+                                   emulator whose linear PCA basis was folded with the window functions on the host */
 } cpb200_plik_desc;
 
 int cpb200_plik_create(const cpb200_plik_desc* desc, int32_t device, cpb200_plik** out);
@@ -168,13 +171,15 @@ int cpb200_plik_destroy(cpb200_plik* p);
 /*
  * loglike_dev[r] = -0.5 * chi^2 of row r, for r < n_rows.  cl_tt / cl_te / cl_ee are device float32
  * (n_rows, n_ell) arrays with a common row pitch in elements (the emulators' outputs: TT and EE from
- * ten_to_predictions, TE from predictions, :276-278); cal_dev holds A_planck per row (:270).
+ * ten_to_predictions, TE from predictions, :276-278; TE has its own row pitch te_pitch, and holds band powers when
+ * the object was created with te_binned); cal_dev holds A_planck per row (:270).
  * binned_dev, when non-NULL, receives the (n_rows, n_bins) model band powers X_model (:294) with row pitch
  * binned_pitch.  Asynchronous on `stream`; rows are processed in engine-owned chunks.
  */
 int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt_dev, const float* cl_te_dev,
-                               const float* cl_ee_dev, int64_t pitch, const float* cal_dev, int64_t n_rows,
-                               float* loglike_dev, float* binned_dev, int64_t binned_pitch, void* stream);
+                               const float* cl_ee_dev, int64_t pitch, int64_t te_pitch, const float* cal_dev,
+                               int64_t n_rows, float* loglike_dev, float* binned_dev, int64_t binned_pitch,
+                               void* stream);
 /* Kernels launched by this object since creation. */
 int64_t cpb200_plik_launch_count(const cpb200_plik* p);
 

@@ -166,8 +166,11 @@ def test_chunk_boundaries_and_determinism(plik):
     assert torch.equal(ll_big, plik.loglike_torch(*big, torch.ones(n, device="cuda")))
 
 
-def test_end_to_end_class_against_the_oracle_pipeline():
-    """tf_planck2018_lite mirror: emulators + likelihood on the device vs oracle emulators + oracle likelihood."""
+@pytest.mark.parametrize("fold_te", [True, False])
+def test_end_to_end_class_against_the_oracle_pipeline(fold_te):
+    """tf_planck2018_lite mirror: emulators + likelihood on the device vs oracle emulators + oracle likelihood.
+    fold_te=True (default): the TE emulator predicts its 199 band powers directly (window functions folded into its
+    PCA basis); False: it writes multipoles like TT and EE."""
     import torch
     import cosmopower_b200 as cp
     from cosmopower_b200 import priors, standins
@@ -180,7 +183,9 @@ def test_end_to_end_class_against_the_oracle_pipeline():
     params = list(models["tt"].parameters)
     spec = {k: (lo, hi, "uniform") for k, (lo, hi) in priors.prior_for(params).items()}
     spec["A_planck"] = (1.0, 0.0025, "gaussian")
-    like = tf_planck2018_lite(parameters=spec, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"])
+    like = tf_planck2018_lite(parameters=spec, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"],
+                              fold_te=fold_te)
+    assert (like._te_binned is not None) == fold_te
     n = 2048
     x = priors.sample_prior(params, n, seed=11)
     x[:8, 0] = 1.0                                     # omega_b outside its prior: zero prior probability
@@ -198,6 +203,12 @@ def test_end_to_end_class_against_the_oracle_pipeline():
     # emulator tolerance (1e-5 in log10 C_ell) enters chi^2 twice: allow 1e-3 relative end to end
     rel = np.abs(ll[8:] - ref[8:]) / np.abs(ref[8:])          # the first 8 rows are far outside the prior (overflow)
     assert rel.max() <= 1e-3, rel.max()
+    if fold_te:
+        # the folded TE emulator against the oracle's TE spectrum binned in float64 (before units and calibration)
+        te_b = like._te_binned.forward_torch(torch.from_numpy(full[:, :len(params)]).cuda(), ten_to=False).cpu().numpy()
+        ref_b = o.bin_spectra(np.zeros_like(cl_te), cl_te, np.zeros_like(cl_te))[:, 215:414] / o.units_factor
+        peak = np.abs(ref_b[8:]).max(axis=1, keepdims=True)
+        assert te_b.shape == (n, 199) and (np.abs(te_b[8:] - ref_b[8:]) / peak).max() <= 1e-4
     post = like.posterior(torch.from_numpy(full).cuda()).cpu().numpy()
     assert (post[:8] <= -1e12).all() and np.isfinite(post[8:]).all()
     pr = like.priors.prob(torch.from_numpy(full).cuda()).cpu().numpy()

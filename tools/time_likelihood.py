@@ -34,20 +34,23 @@ def main():
         kind, path = standins.model_path(name)
         models[key] = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
     params = list(models["tt"].parameters)
-    like = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"])
+    fold = os.environ.get("CPB200_FOLD_TE", "1") != "0"
+    like = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"], fold_te=fold)
     x = priors.sample_prior(params, rows, seed=5, dtype=np.float32)
     full = torch.from_numpy(np.concatenate([x, np.ones((rows, 1), np.float32)], axis=1)).cuda()
     cosmo = full[:, :len(params)].contiguous()
     cl_tt = models["tt"].ten_to_predictions_tf(cosmo)
-    cl_te = models["te"].predictions_tf(cosmo)
+    te = (lambda: like._te_binned.forward_torch(cosmo, ten_to=False)) if fold else (lambda: models["te"].predictions_tf(cosmo))
+    cl_te = te()
     cl_ee = models["ee"].ten_to_predictions_tf(cosmo)
     cal = full[:, -1].contiguous()
     ms_tail = timed(lambda: like._engine.loglike_torch(cl_tt, cl_te, cl_ee, cal))
-    ms_emu = timed(lambda: (models["tt"].ten_to_predictions_tf(cosmo), models["te"].predictions_tf(cosmo), models["ee"].ten_to_predictions_tf(cosmo)))
+    ms_emu = timed(lambda: (models["tt"].ten_to_predictions_tf(cosmo), te(), models["ee"].ten_to_predictions_tf(cosmo)))
     ms_all = timed(lambda: like.get_loglkl(full))
     n_ell, nb = 2507, 613
-    out = {"rows": rows, "likelihood_tail_ms": ms_tail, "three_emulators_ms": ms_emu, "get_loglkl_ms": ms_all,
-           "tail_hbm_gbs": rows * (3 * n_ell + 2 * 640) * 4 / ms_tail / 1e6,
+    te_len = cl_te.shape[1]
+    out = {"rows": rows, "fold_te": fold, "likelihood_tail_ms": ms_tail, "three_emulators_ms": ms_emu, "get_loglkl_ms": ms_all,
+           "tail_hbm_gbs": rows * (2 * n_ell + te_len + 2 * 640) * 4 / ms_tail / 1e6,
            "tail_quadform_tflops_dense_equiv": rows * 2.0 * nb * nb / ms_tail / 1e9,
            "loglike_per_s": rows / ms_all * 1e3}
     print(json.dumps(out))
