@@ -23,8 +23,8 @@ constexpr int PLIK_BIN_THREADS = 256;
 constexpr int PLIK_QF_BM = 128, PLIK_QF_BN = 128, PLIK_QF_BK = 16;
 
 // Persistent blocks (three per SM) walking rows with a PLIK_RING-deep shared-memory ring: while a row is being binned
-// the next row's three spectra are already on their way (16-byte cp.async, each spectrum starting 16-byte aligned in
-// shared memory).  A slot is a run of at most PLIK_SEG consecutive multipoles of one bin; the host splits the 5 ... 33
+// the next two rows are already on their way (one bulk copy per input and row, completion on the buffer's mbarrier;
+// each input starts 16-byte aligned in shared memory).  A slot is a run of at most PLIK_SEG consecutive multipoles of one bin; the host splits the 5 ... 33
 // wide bins into slots so that the per-thread work is short, balanced and fully unrolled, and lays a bin's slots out on
 // neighbouring lanes of one warp.  Every thread owns the same <= PLIK_MAX_PASSES slots for every row, so their window
 // weights live in registers; the lane holding a bin's first slot adds the other partial sums (at most
@@ -33,7 +33,7 @@ constexpr int PLIK_SEG = 9;
 constexpr int PLIK_MAX_PASSES = 3;
 constexpr int PLIK_MAX_SLOTS_PER_BIN = 4;
 constexpr int PLIK_RING = 3;             // row buffers per block: one being binned, two in flight
-constexpr int PLIK_BLOCKS_PER_SM = 2;
+constexpr int PLIK_BLOCKS_PER_SM = 3;      // 80 registers per thread, 3 x 63 KB of shared memory
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
@@ -53,7 +53,7 @@ __device__ __forceinline__ void plik_split2(float a, float b, uint32_t& hi, uint
 
 struct PlikSlot {          // one per slot, built by cpb200_plik_create
     int off;               // shared-memory offset of the slot's first element (input s starts 16-byte aligned after input s-1)
-    int last;              // index of the slot's last multipole (loads beyond it re-read that one, with weight 0)
+    int last;              // index of the slot's last multipole (the kernel always reads PLIK_SEG elements; weights beyond are 0)
     int bin;               // the bin this slot opens, or -1
     int n_slots;           // slots of that bin (1 .. PLIK_MAX_SLOTS_PER_BIN) when bin >= 0
     float x_data;          // data band power of that bin
@@ -69,6 +69,12 @@ struct PlikInputs {
     int len[3];            // floats per row
 };
 
+// Shared memory of one block: PLIK_RING mbarriers (32 bytes), the row ring - each buffer holds the three inputs back to
+// back (every one starting 16-byte aligned) plus PLIK_ROW_PAD zero floats, because a slot always reads PLIK_SEG
+// elements (those beyond its end carry weight 0) -, the row's scaled differences and the per-warp maxima.
+constexpr int PLIK_ROW_PAD = 8;
+constexpr int PLIK_BAR_FLOATS = 8;
+
 __global__ void __launch_bounds__(PLIK_BIN_THREADS, PLIK_BLOCKS_PER_SM)
 plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                 const PlikSlot* __restrict__ slots, int n_passes, float units_factor,
@@ -76,16 +82,32 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                 uint8_t* __restrict__ tiles, float* __restrict__ row_scale)
 {
     extern __shared__ __align__(16) float plik_smem[];
-    // shared-memory layout of one row: the three inputs back to back, each starting 16-byte aligned
     const int off1 = (in.len[0] + 3) & ~3, off2 = off1 + ((in.len[1] + 3) & ~3);
-    const int row_floats = off2 + ((in.len[2] + 3) & ~3);
+    const int buf_floats = off2 + ((in.len[2] + 3) & ~3) + PLIK_ROW_PAD;
+    float* ring = plik_smem + PLIK_BAR_FLOATS;
     // tensor-core mode (tiles != nullptr): the row's scaled differences, then the per-warp maxima
-    float* vrow = plik_smem + PLIK_RING * row_floats;
+    float* vrow = ring + PLIK_RING * buf_floats;
     float* wmax = vrow + diff_pitch;
-    if (tiles) for (int i = threadIdx.x; i < diff_pitch; i += PLIK_BIN_THREADS) vrow[i] = 0.f;     // padding columns stay zero
+    const uint32_t bar0 = static_cast<uint32_t>(__cvta_generic_to_shared(plik_smem));
+    // zero everything once: the pads between and after the inputs stay zero for the whole launch
+    for (int i = threadIdx.x; i < PLIK_RING * buf_floats + diff_pitch; i += PLIK_BIN_THREADS) ring[i] = 0.f;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < PLIK_RING; ++i) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill is ordered before the bulk copies' writes
+    __syncthreads();
+
+    // An input whose rows are 16-byte aligned arrives by one bulk copy per row (issued by thread 0, completion counted on
+    // the buffer's mbarrier) plus at most three 4-byte cp.async for the elements beyond the last multiple of four; any
+    // other input is gathered 4 bytes at a time by the whole block.
     bool vec[3];
+    uint32_t bulk_bytes = 0;
 #pragma unroll
-    for (int s = 0; s < 3; ++s) vec[s] = (in.pitch[s] & 3) == 0 && (reinterpret_cast<uintptr_t>(in.ptr[s]) & 15) == 0;
+    for (int s = 0; s < 3; ++s) {
+        vec[s] = (in.pitch[s] & 3) == 0 && (reinterpret_cast<uintptr_t>(in.ptr[s]) & 15) == 0;
+        if (vec[s]) bulk_bytes += static_cast<uint32_t>(in.len[s] >> 2) * 16u;
+    }
 
     PlikSlot my[PLIK_MAX_PASSES];
 #pragma unroll
@@ -98,7 +120,11 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
 
     auto fetch = [&](long long r, int buf) {                    // always commits a group (empty past the last row)
         if (r < n_rows) {
-            float* dst0 = plik_smem + buf * row_floats;
+            float* dst0 = ring + buf * buf_floats;
+            const uint32_t bar = bar0 + 8u * buf;
+            if (threadIdx.x == 0) {
+                if (bulk_bytes) mbar_arrive_expect_tx(bar, bulk_bytes); else mbar_arrive(bar);
+            }
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
                 const float* src = in.ptr[s] + r * in.pitch[s];
@@ -106,8 +132,10 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                 const int len = in.len[s];
                 if (vec[s]) {
                     const int n4 = len >> 2;
-                    for (int i = threadIdx.x; i < n4; i += PLIK_BIN_THREADS) cp_async_16(dst + 4 * i, src + 4 * i);
-                    for (int i = (n4 << 2) + threadIdx.x; i < len; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src + i);
+                    if (threadIdx.x == 0 && n4)
+                        bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(dst)), src, static_cast<uint32_t>(n4) * 16u, bar);
+                    const int i = (n4 << 2) + static_cast<int>(threadIdx.x) - 32 * (s + 1);     // warp s + 1 fetches the tail
+                    if (i >= (n4 << 2) && i < len) cp_async_4(dst + i, src + i);
                 } else {
                     for (int i = threadIdx.x; i < len; i += PLIK_BIN_THREADS) cp_async_4(dst + i, src + i);
                 }
@@ -121,22 +149,25 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
 #pragma unroll
     for (int i = 0; i < PLIK_RING - 1; ++i) fetch(r + i * stride, i);
     int buf = 0;
+    uint32_t phases = 0;                                         // one parity bit per ring buffer
     for (; r < n_rows; r += stride) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(PLIK_RING - 2) : "memory");    // row r has landed; younger rows may be in flight
+        asm volatile("cp.async.wait_group %0;" ::"n"(PLIK_RING - 2) : "memory");    // this thread's 4-byte copies of row r have landed
+        while (!mbar_try_wait(bar0 + 8u * buf, (phases >> buf) & 1u)) { }          // ... and the row's bulk copies
+        phases ^= 1u << buf;
         const float c = cal[r];
         const float scale = units_factor / (c * c);
         float vmax = 0.f;
-        __syncthreads();                                         // ... for every thread, and every thread has finished the
-                                                                 // previous row (its buffer, vrow, wmax are free)
+        __syncthreads();                                         // row r is complete for every thread, and every thread has
+                                                                 // finished the previous row (its buffer, vrow, wmax are free)
         fetch(r + (PLIK_RING - 1) * stride, buf == 0 ? PLIK_RING - 1 : buf - 1);     // refill the buffer of the previous row
-        const float* row = plik_smem + buf * row_floats;
+        const float* row = ring + buf * buf_floats;
 #pragma unroll
         for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
             if (p < n_passes) {                                  // uniform across the block
                 const float* q = row + my[p].off;
                 float v[PLIK_SEG];
 #pragma unroll
-                for (int j = 0; j < PLIK_SEG; ++j) v[j] = q[min(j, my[p].last)];
+                for (int j = 0; j < PLIK_SEG; ++j) v[j] = q[j];  // beyond the slot's end: neighbouring data or zero pad, weight 0
                 float acc = 0.f;
 #pragma unroll
                 for (int j = 0; j < PLIK_SEG; ++j) acc = fmaf(v[j], my[p].w[j], acc);

@@ -230,6 +230,11 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// global-only form: orders this thread's generic-proxy global stores before async-proxy (bulk copy) reads of them.
+// SASS: a single FENCE.VIEW.ASYNC.G, where the unqualified form is MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC.S.
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // 2-CTA MMA: D[256 x N] (128 rows in each CTA's TMEM) += A[256 x 16] (128 rows from each CTA's smem)
@@ -329,7 +334,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
 // ---------------------------------------------------------------------------------------------
 // epilogue of one accumulator chunk for one warp (templated on the layer kind so that the inner
 // loops carry exactly one code path)
@@ -348,34 +352,33 @@ struct EpiCtx {
 // contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
 // One half piece = 16 TMEM lanes (rows tq, tq+8 of this warp's lower or upper 16 rows) x 32 accumulator columns:
 // v[4i + 2rr + cc] = (row 8rr + tq, lane value j = 2i + cc).
+// both row groups (rr = 0, 1) of the half piece walk the activation stage by stage together: 16 independent chains,
+// so the special-function unit always has a queued instruction while the FMA pipe works on the other stages
 template <int KIND>
 __device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const float4 (&pp)[8], float acc_scale,
                                                  uint8_t* dst, uint64_t pol_keep, int dbg) {
+    float hv[16];                                  // hv[8rr + j]
+    if (KIND == EPI_ACT) {
+        float z[16], e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int rr = i >> 3, j = i & 7; z[i] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), acc_scale, pp[j].x); }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = ex2_approx(z[i] * pp[i & 7].y);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = rcp_approx(1.f + e[i]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hv[i] = fmaf(pp[i & 7].w, e[i], pp[i & 7].z) * z[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int rr = i >> 3, j = i & 7; hv[i] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), pp[j].x, pp[j].y); }
+    }
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-        // written stage by stage (all 8 values through each step) so that the MUFU latencies of the
-        // 8 independent chains overlap instead of being serialised value after value
-        float hv[8];
-        if (KIND == EPI_ACT) {
-            float z[8], e[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) z[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), acc_scale, pp[j].x);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = ex2_approx(z[j] * pp[j].y);         // exp(-alpha*z)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = rcp_approx(1.f + e[j]);            // sigmoid; inf -> 0, as numpy
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hv[j] = fmaf(pp[j].w, e[j], pp[j].z) * z[j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hv[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), pp[j].x, pp[j].y);
-        }
         uint4 hi, lo;
-        split2(hv[0], hv[1], hi.x, lo.x);
-        split2(hv[2], hv[3], hi.y, lo.y);
-        split2(hv[4], hv[5], hi.z, lo.z);
-        split2(hv[6], hv[7], hi.w, lo.w);
-        // rows +8rr: 64 B per row; a warp store covers 8 rows x 64 B = 4 full lines
+        split2(hv[8 * rr + 0], hv[8 * rr + 1], hi.x, lo.x);
+        split2(hv[8 * rr + 2], hv[8 * rr + 3], hi.y, lo.y);
+        split2(hv[8 * rr + 4], hv[8 * rr + 5], hi.z, lo.z);
+        split2(hv[8 * rr + 6], hv[8 * rr + 7], hi.w, lo.w);
         if (dbg & 4) { if (hi.x == 0x7fff7fffu && lo.y == 0x12345u) st_global_v4_hint(dst, hi, pol_keep); continue; }
         st_global_v4_hint(dst + rr * 512, hi, pol_keep);
         st_global_v4_hint(dst + rr * 512 + UM_A_HALF_BYTES, lo, pol_keep);
@@ -474,6 +477,38 @@ __device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const f
     }
 }
 
+// the common case of a half piece - 32-byte stores, every column a mode, every row inside the batch - without a
+// branch: both row groups' 16 values go through each step together (FMA, optional 2**y, two 32-byte stores)
+template <bool TEN_TO, bool ACC>
+__device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], const float2 (&pp)[8], float* d0, float* d1, int dbg) {
+    float y0[8], y1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        y0[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + (j & 1)]), pp[j].x, pp[j].y);
+        y1[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 + (j & 1)]), pp[j].x, pp[j].y);
+    }
+    if (ACC) {
+        const float ks = TEN_TO ? 3.3219280948873623f : 1.f;
+        float p0[8], p1[8];
+        ldg_v8(d0, p0);
+        ldg_v8(d1, p1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { y0[j] = fmaf(p0[j], ks, y0[j]); y1[j] = fmaf(p1[j], ks, y1[j]); }
+    }
+    if (TEN_TO) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y0[j] = ex2_approx(y0[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y1[j] = ex2_approx(y1[j]);
+    }
+    if (dbg & 4) {
+        if (y0[0] == 1.2345e-30f && y1[5] == 3.4e29f) stg_cs_v8(d0, y0);
+    } else {
+        stg_cs_v8(d0, y0);                     // 8 rows x 128 B per warp instruction: full lines
+        stg_cs_v8(d1, y1);
+    }
+}
+
 // output layers: de-standardise (+ 10**y) and store rows of the spectrum.  Columns are packed like the operand
 // layers' (a lane owns 8 consecutive logical columns), constants are {scale, shift} pairs, two columns per float4,
 // lane-interleaved (float4 4m + tr of a 32-column block = columns 8tr + 2m, 8tr + 2m + 1).
@@ -483,9 +518,9 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
     constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
     int pc = E.cw * UM_PIECE;
-    uint32_t va[16], vb[16];
     // the last chunk of a layer is usually not full: pieces that start beyond the last mode are skipped altogether
     const int nc_valid = min(E.nc, n_modes - E.chunk_col0);
+    uint32_t va[16], vb[16];
     if (pc < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);        // TMEM reads run one half piece ahead of the math
     for (; pc < nc_valid; pc += kStep) {
         float2 pp[8];
@@ -496,10 +531,19 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
             pp[2 * m + 1] = make_float2(q4.z, q4.w);
         }
         const int gc = E.chunk_col0 + pc + 8 * E.tr;
-        const int mode = gc + 8 <= n_modes ? vec_mode : gc < n_modes ? OUT_SCALAR : OUT_NONE;   // OUT_NONE: nothing of this lane's is a mode
         float* drow = orow0 + gc;                                       // row 32q + tq of the tile
+        // warp-uniform: 32-byte stores, whole tile inside the batch (vec_mode), whole piece inside the spectrum
+        const bool fast = vec_mode == OUT_VEC32 && E.chunk_col0 + pc + UM_PIECE <= n_modes;
         tmem_ld_wait16(va);
         tmem_ld_16x256b_x4(t_addr1 + pc, vb);
+        if (fast) {
+            epi_output_half_fast<TEN_TO, ACC>(va, pp, drow, drow + 8 * pitch, E.dbg);
+            tmem_ld_wait16(vb);
+            if (pc + kStep < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
+            epi_output_half_fast<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, drow + 24 * pitch, E.dbg);
+            continue;
+        }
+        const int mode = gc + 8 <= n_modes ? vec_mode : gc < n_modes ? OUT_SCALAR : OUT_NONE;   // OUT_NONE: nothing of this lane's is a mode
         epi_output_half<TEN_TO, ACC>(va, pp, drow, pitch, mode, E.q * 32 + E.tq, rows_left, gc, n_modes, E.dbg);
         tmem_ld_wait16(vb);
         if (pc + kStep < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
@@ -908,7 +952,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             if (L.epi_kind <= EPI_AFFINE && c == L.n_chunks - 1) {     // operand-producing kinds
                 // the next layer's loader may only read the scratch once every chunk of this layer is
                 // written: one fence per thread before the last chunk's arrive covers all its stores
-                UM_SCRATCH_FENCE(); fence_proxy_async();
+                UM_SCRATCH_FENCE(); fence_proxy_async_global();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_aready(t));
             }
