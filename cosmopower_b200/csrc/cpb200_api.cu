@@ -354,9 +354,26 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.counters = e->d_counters;
     int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     if (const char* cap = getenv("CPB200_DEBUG_MAX_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(cap)));  // tuning aid
-    const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * cpb::UM_CLUSTER;
-    if (p.counters) cpb::fused_mlp_umma_kernel<true><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
-    else cpb::fused_mlp_umma_kernel<false><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+    // Small batches leave most SMs idle: deal the output contraction's chunks (57 % of a cmb_TT pair's cycles) out to
+    // up to n_chunks clusters per pair-group; each of them walks the trunk on its own copy of the activations.
+    p.out_split = 1;
+    {
+        const Gemm& last = e->gemms.back();
+        const int64_t room = max_clusters / std::max<int64_t>(1, p.n_pairgroups);
+        if (e->gemms.size() > 1 && last.epi == cpb::EPI_OUT && last.n_chunks > 1 && room >= 2 && !getenv("CPB200_NO_OUT_SPLIT")) {
+            const int smax = static_cast<int>(std::min<int64_t>(room, last.n_chunks));
+            const int per = (last.n_chunks + smax - 1) / smax;            // chunks per cluster at the widest split
+            p.out_split = (last.n_chunks + per - 1) / per;                // the narrowest split that reaches it
+        }
+    }
+    const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * p.out_split * cpb::UM_CLUSTER;
+    if (p.out_split > 1) {
+        if (p.counters) cpb::fused_mlp_umma_kernel<true, true><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+        else cpb::fused_mlp_umma_kernel<false, true><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+    } else {
+        if (p.counters) cpb::fused_mlp_umma_kernel<true, false><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+        else cpb::fused_mlp_umma_kernel<false, false><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+    }
     ++e->launches;
     CU(cudaGetLastError());
     return 0;
@@ -405,10 +422,10 @@ int setup_umma(cpb200_engine* e) {
         cudaMalloc(reinterpret_cast<void**>(&e->d_max_cycles), sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
         return (fail(CPB200_E_CUDA, "error flag allocation failed"));
-    if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             cpb::UM_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             cpb::UM_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess)
         return (fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
                          cudaGetErrorString(cudaGetLastError())));
     return 0;

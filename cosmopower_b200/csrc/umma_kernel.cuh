@@ -105,6 +105,9 @@ struct UmmaParams {
     long long n_rows;
     long long n_pairs;         // ceil(n_tiles / 2)
     long long n_pairgroups;    // ceil(n_pairs / UM_CLUSTER): one pair per CTA of a cluster, processed in lockstep
+    int out_split;             // small batches: this many clusters share a pair-group - each walks the whole trunk (its own
+                               // copy of the activations) but only every out_split-th chunk of the output contraction, so the
+                               // spectrum's columns are produced by otherwise idle SMs (1 = off; grid = clusters x out_split x 2)
     uint8_t* scratch;          // gridDim.x * scratch_cta_bytes
     unsigned long long scratch_cta_bytes;
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
@@ -594,7 +597,8 @@ __device__ __forceinline__ void epi_chunk_quadform(const EpiCtx& E, const float*
 // ---------------------------------------------------------------------------------------------
 // PROF = true instantiates the per-role cycle counters (cpb200_engine_debug_counters); the production
 // instantiation carries no clock reads on the single-thread issue paths
-template <bool PROF>
+// SPLIT = true instantiates the small-batch variant (UmmaParams::out_split > 1); the throughput kernel carries none of it
+template <bool PROF, bool SPLIT = false>
 __global__ void __cluster_dims__(UM_CLUSTER, 1, 1) __launch_bounds__(UM_THREADS, 1)
 fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 {
@@ -653,7 +657,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t cta_rank = UM_CLUSTER > 1 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0;
-    const long long pg_first = blockIdx.x / UM_CLUSTER, pg_step = gridDim.x / UM_CLUSTER;
+    const int out_split = SPLIT ? P.out_split : 1, split_id = SPLIT ? static_cast<int>(blockIdx.x / UM_CLUSTER) % out_split : 0;
+    const int out_gemm = SPLIT ? P.n_gemms - 1 : -1;       // the contraction whose chunks are dealt out
+    const long long pg_first = (blockIdx.x / UM_CLUSTER) / out_split, pg_step = (gridDim.x / UM_CLUSTER) / out_split;
     // pair-groups this cluster walks; iteration `it` runs the table's "cur" jobs (contractions >= 1) for
     // pair-group it-1 and its "next" jobs (layer 0) for pair-group it, so a pair's layer-0 epilogues hide
     // behind the previous pair's output phase instead of stalling the tensor pipe at every pair start
@@ -688,6 +694,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const int g = jw & 0xff, t = (jw >> 8) & 0xff, c = (jw >> 16) & 0xff;                      \
             const bool is_next = (jw >> 24) != 0;                                                      \
             if (is_next ? !has_next : !has_cur) continue;                                              \
+            if (SPLIT && g == out_gemm && c % out_split != split_id) continue;   /* another cluster's columns */ \
             /* rows beyond n_rows are padding (computed, never stored) */                              \
             const long long pidx = is_next ? it : it - 1;      /* this cluster's running pair number */  \
             const long long pair = (pg_first + pidx * pg_step) * UM_CLUSTER + cta_rank;                \
@@ -711,7 +718,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const int k_stages = job_stages(L, c);
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
                 const long long j_t0 = now(), j_we0 = w_empty, j_wa0 = w_aready;
-                if (c == 0 && !(g == 0 && P.ext_a0)) {            // the whole K extent of this tile's operand must be written
+                if (c == (g == out_gemm ? split_id : 0) && !(g == 0 && P.ext_a0)) {   // first chunk this cluster runs of (g, t): the whole K extent of the tile's operand must be written
                     if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), (ph_a0ready >> t) & 1, P.error_flag, 101); ph_a0ready ^= 1u << t; }
                     else { w_aready += mbar_wait(bar_aready(t), (ph_aready >> t) & 1, P.error_flag, 102); ph_aready ^= 1u << t; }
                 }

@@ -238,3 +238,19 @@ def test_no_write_outside_the_output_rows(name, n):
         if pitch > m.n_modes:
             assert torch.all(big[128:128 + n, m.n_modes:] == -123.0)
         assert torch.all(torch.isfinite(window)) and torch.all(window > 0)
+
+
+@pytest.mark.parametrize("name", ["cmb_TT_NN", "cmb_TE_PCAplusNN", "cmb_PP_PCAplusNN", "PKLIN_NN"])
+@pytest.mark.parametrize("n", [1, 300, 700, 3000, 9000])
+def test_small_batch_output_split_is_bit_identical(name, n, monkeypatch):
+    """Small batches deal the output contraction's chunks out to otherwise idle clusters (UmmaParams::out_split);
+    every element goes through the same arithmetic, so the result must equal the unsplit launch bit for bit."""
+    m, attrs = get_model(name)
+    x = priors.sample_prior(m.parameters, n, seed=1234 + n).astype(np.float32)
+    monkeypatch.delenv("CPB200_NO_OUT_SPLIT", raising=False)
+    y_split = m.forward_pass_np(x)
+    monkeypatch.setenv("CPB200_NO_OUT_SPLIT", "1")
+    y_plain = m.forward_pass_np(x)
+    assert np.array_equal(y_split, y_plain)
+    err = parity.model_error(name, y_split.astype(np.float64), oracle_np.forward_pass(attrs, x.astype(np.float64)))
+    assert err <= parity.model_tol(name), (name, n, err)
