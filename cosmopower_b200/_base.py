@@ -79,8 +79,8 @@ class _EmulatorBase:
         if x.ndim != 2 or x.shape[1] != int(self.n_parameters):
             raise ValueError("parameters array must have shape (N, %d), got %s" % (self.n_parameters, x.shape))
         out_dtype = np.float32 if x.dtype == np.float32 else np.float64
-        y = self.engine().forward_host(np.ascontiguousarray(x, dtype=np.float32), ten_to=ten_to)
-        return y if out_dtype == np.float32 else y.astype(np.float64)
+        # float64 results are widened inside the library while they are copied out (cpb200_forward_host_f64)
+        return self.engine().forward_host(np.ascontiguousarray(x, dtype=np.float32), ten_to=ten_to, dtype=out_dtype)
 
     def predictions_np(self, parameters_dict):
         """reference cosmopower_NN.py:388-405 / cosmopower_PCAplusNN.py:384-401."""

@@ -49,6 +49,7 @@ SYMBOLS = [
                                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
     ("cpb200_forward_host", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    ("cpb200_forward_host_f64", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     ("cpb200_host_alloc", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
     ("cpb200_host_free", ctypes.c_int, [ctypes.c_void_p]),
     ("cpb200_engine_info", ctypes.c_int, [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 4),
@@ -227,17 +228,20 @@ class Engine:
         return out
 
     # -- host path --------------------------------------------------------------------------
-    def forward_host(self, params, out=None, ten_to=False):
-        """params: float32 C-contiguous (N, P) host array -> float32 (N, n_modes) host array."""
+    def forward_host(self, params, out=None, ten_to=False, dtype=np.float32):
+        """params: float32 C-contiguous (N, P) host array -> (N, n_modes) host array, float32 or - widened by the
+        library's host threads on the way out - float64 (`dtype`, or the dtype of `out`)."""
         params = np.ascontiguousarray(params, dtype=np.float32)
         if params.ndim != 2 or params.shape[1] != self.n_parameters:
             raise ValueError("expected an array of shape (N, %d), got %s" % (self.n_parameters, params.shape))
         n = params.shape[0]
         if out is None:
-            out = np.empty((n, self.n_modes), dtype=np.float32)
-        _check(self._lib.cpb200_forward_host(self._h, ctypes.c_void_p(params.ctypes.data), n,
-                                             ctypes.c_void_p(out.ctypes.data), out.strides[0] // 4 if n > 1 else self.n_modes,
-                                             FLAG_TEN_TO if ten_to else 0))
+            out = np.empty((n, self.n_modes), dtype=dtype)
+        if out.dtype not in (np.float32, np.float64) or out.ndim != 2 or out.shape != (n, self.n_modes) or (n > 0 and out.strides[1] != out.itemsize):
+            raise ValueError("out must be a float32 or float64 (N, %d) array with contiguous rows" % self.n_modes)
+        fn = self._lib.cpb200_forward_host if out.dtype == np.float32 else self._lib.cpb200_forward_host_f64
+        _check(fn(self._h, ctypes.c_void_p(params.ctypes.data), n, ctypes.c_void_p(out.ctypes.data),
+                  out.strides[0] // out.itemsize if n > 1 else self.n_modes, FLAG_TEN_TO if ten_to else 0))
         return out
 
     # -- introspection ---------------------------------------------------------------------------

@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/cpb200.h"
@@ -590,8 +592,42 @@ static bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_rows, float* out_host,
-                        int64_t out_pitch, int flags) {
+}  // extern "C"
+
+namespace {
+// Host threads used to copy results out of the pinned bounce buffers (CPB200_HOST_THREADS overrides; at most 32).
+int host_threads() {
+    static const int n = [] {
+        const char* s = getenv("CPB200_HOST_THREADS");
+        const int v = s ? atoi(s) : static_cast<int>(std::thread::hardware_concurrency());
+        return std::max(1, std::min(v, 32));
+    }();
+    return n;
+}
+
+// rows of float32 in a pinned bounce buffer -> the caller's (pageable) rows of float32 or float64.  Fresh NumPy arrays are
+// untouched memory: the page faults of the first write dominate a single-threaded copy (3-4 GB/s), so the rows are split
+// over the host threads - at least 1 MB of input per thread.
+template <typename T>
+void copy_rows_out(T* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t rows, int cols) {
+    auto work = [=](int64_t r0, int64_t r1) {
+        for (int64_t r = r0; r < r1; ++r) {
+            const float* s = src + r * src_pitch;
+            T* d = dst + r * dst_pitch;
+            if (std::is_same<T, float>::value) memcpy(d, s, sizeof(float) * cols);
+            else for (int j = 0; j < cols; ++j) d[j] = static_cast<T>(s[j]);
+        }
+    };
+    const int nt = static_cast<int>(std::min<int64_t>(host_threads(), rows * cols / (1 << 18)));
+    if (nt <= 1) { work(0, rows); return; }
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work, rows * t / nt, rows * (t + 1) / nt);
+    for (std::thread& th : pool) th.join();
+}
+
+template <typename T>
+int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows, T* out_host, int64_t out_pitch, int flags) {
     if (!e) return fail(CPB200_E_INVALID, "null engine");
     if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
     if (n_rows == 0) return 0;
@@ -599,9 +635,14 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
     if (out_pitch < e->n_modes) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d", static_cast<long long>(out_pitch), e->n_modes);
     DeviceGuard guard(e->device);
     if (int rc = ensure_host_pipeline(e)) return rc;
-    const bool pin_in = is_pinned(params_host), pin_out = is_pinned(out_host);
+    // float32 results in pinned memory are written by the DMA engine directly; anything else is copied (and widened)
+    // out of the pinned bounce buffers by the host threads while the next chunk is in flight
+    const bool pin_in = is_pinned(params_host), pin_out = std::is_same<T, float>::value && is_pinned(out_host);
     if (!(pin_in && pin_out)) if (int rc = ensure_bounce(e)) return rc;
-    const int64_t R = e->chunk_rows;
+    // chunk size: the engine's (128 MB of output) for direct DMA; with a host copy behind it, about an eighth of the
+    // batch (>= 2048 rows), so that the copy-out of one chunk overlaps the transfer of the next
+    int64_t R = e->chunk_rows;
+    if (!pin_out) R = std::min<int64_t>(R, std::max<int64_t>(2048, (n_rows + 7) / 8 + 255) / 256 * 256);
     const int64_t n_chunks = (n_rows + R - 1) / R;
     const size_t row_bytes = sizeof(float) * e->n_modes;
     // two slots, each with its own stream: H2D -> kernel -> D2H; slot reuse waits for its stream
@@ -610,10 +651,7 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
         if (c >= 2) {   // retire chunk c-2 of this slot
             CU(cudaStreamSynchronize(e->hstream[slot]));
             const int64_t r0 = (c - 2) * R, m = std::min<int64_t>(R, n_rows - r0);
-            if (!pin_out) {
-                if (out_pitch == e->n_modes) memcpy(out_host + r0 * out_pitch, e->h_out[slot], m * row_bytes);
-                else for (int64_t r = 0; r < m; ++r) memcpy(out_host + (r0 + r) * out_pitch, e->h_out[slot] + r * e->n_modes, row_bytes);
-            }
+            if (!pin_out) copy_rows_out(out_host + r0 * out_pitch, out_pitch, e->h_out[slot], e->n_modes, m, e->n_modes);
         }
         if (c < n_chunks) {
             const int64_t r0 = c * R, m = std::min<int64_t>(R, n_rows - r0);
@@ -624,7 +662,7 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
             if (int rc = forward_async(e, e->d_in[slot], m, e->d_out[slot], e->dpitch, flags, e->hstream[slot])) return rc;
             CU(cudaEventRecord(e->kdone[slot], e->hstream[slot]));
             if (pin_out) {
-                CU(cudaMemcpy2DAsync(out_host + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot],
+                CU(cudaMemcpy2DAsync(reinterpret_cast<float*>(out_host) + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot],
                                      sizeof(float) * e->dpitch, row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[slot]));
             } else {
                 CU(cudaMemcpy2DAsync(e->h_out[slot], row_bytes, e->d_out[slot], sizeof(float) * e->dpitch, row_bytes, m,
@@ -633,6 +671,19 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
         }
     }
     return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_rows, float* out_host,
+                        int64_t out_pitch, int flags) {
+    return forward_host_impl<float>(e, params_host, n_rows, out_host, out_pitch, flags);
+}
+
+int cpb200_forward_host_f64(cpb200_engine* e, const float* params_host, int64_t n_rows, double* out_host,
+                            int64_t out_pitch, int flags) {
+    return forward_host_impl<double>(e, params_host, n_rows, out_host, out_pitch, flags);
 }
 
 int cpb200_host_alloc(void** ptr, uint64_t bytes) {

@@ -113,6 +113,15 @@ int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_r
 int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_rows,
                         float* out_host, int64_t out_pitch, int flags);
 
+/*
+ * The same call with a float64 result: the reference computes in the dtype NumPy promotion gives its input
+ * (cosmopower_NN.py:371-384, cosmopower_PCAplusNN.py:368-381: float64 for dicts of lists / float64 arrays), so
+ * predictions_np returns float64 there.  The device result (float32) is widened while it is copied out of the pinned
+ * bounce buffers, rows split over the host threads (CPB200_HOST_THREADS, default all, at most 32); out_pitch in doubles.
+ */
+int cpb200_forward_host_f64(cpb200_engine* e, const float* params_host, int64_t n_rows,
+                            double* out_host, int64_t out_pitch, int flags);
+
 /* Pinned host memory for zero-bounce cpb200_forward_host calls. */
 int cpb200_host_alloc(void** ptr, uint64_t bytes);
 int cpb200_host_free(void* ptr);

@@ -254,3 +254,21 @@ def test_small_batch_output_split_is_bit_identical(name, n, monkeypatch):
     assert np.array_equal(y_split, y_plain)
     err = parity.model_error(name, y_split.astype(np.float64), oracle_np.forward_pass(attrs, x.astype(np.float64)))
     assert err <= parity.model_tol(name), (name, n, err)
+
+
+@pytest.mark.parametrize("name,n", [("cmb_TT_NN", 1), ("cmb_TT_NN", 5000), ("PKLIN_NN", 20000), ("cmb_PP_PCAplusNN", 20011)])
+def test_float64_host_path_is_the_widened_float32_result(name, n):
+    """cpb200_forward_host_f64 (what predictions_np returns for float64 / list inputs) widens the device's float32 result
+    with the host threads while copying it out, in smaller pipeline chunks than the float32 call: same values exactly,
+    also into a caller-provided array with a row pitch."""
+    m, _ = get_model(name)
+    eng = m.engine()
+    x = priors.sample_prior(m.parameters, n, seed=77).astype(np.float32)
+    y32 = eng.forward_host(x, ten_to=True)
+    y64 = eng.forward_host(x, ten_to=True, dtype=np.float64)
+    assert y64.dtype == np.float64 and np.array_equal(y64, y32.astype(np.float64))
+    wide = np.full((n, m.n_modes + 5), -1.0, dtype=np.float64)
+    eng.forward_host(x, out=wide[:, :m.n_modes], ten_to=True)
+    assert np.array_equal(wide[:, :m.n_modes], y64) and (wide[:, m.n_modes:] == -1.0).all()
+    d = {k: x[:, i].astype(np.float64) for i, k in enumerate(m.parameters)}
+    assert np.array_equal(m.ten_to_predictions_np(d), y64)
