@@ -102,8 +102,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_path(sample_rows, steps, warmup):
-    """The reference's CPU implementation of the path (oracle port: NumPy, all BLAS threads)."""
+def cpu_path(sample_rows, steps, warmup, dtype=np.float64):
+    """The reference's CPU implementation of the path (oracle port: NumPy, all BLAS threads).  float64 inputs are the
+    reference's documented usage (dicts of lists); float32 arrays make its whole pass float32."""
     from cosmopower_b200 import priors, standins
     from oracle import oracle_np
     models = []
@@ -111,7 +112,7 @@ def cpu_path(sample_rows, steps, warmup):
         kind, path = standins.model_path(name)
         attrs = standins.load_attrs(kind, path)
         x = priors.sample_prior(attrs["parameters"], sample_rows, seed=20260101 + i)
-        d = {k: x[:, j] for j, k in enumerate(attrs["parameters"])}
+        d = {k: x[:, j].astype(dtype) for j, k in enumerate(attrs["parameters"])}
         models.append((attrs, d))
 
     def step():
@@ -275,8 +276,10 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, _, cores = cpu_path(8192, 2, 1)
+            v32, _, _ = cpu_path(8192, 2, 1, dtype=np.float32)
             cpu = {"value": v, "unit": "spectra/s", "cores": cores, "kind": "port",
-                   "sample": "8192 rows per model x 2 steps, float64 inputs, NumPy/OpenBLAS oracle port of ten_to_predictions_np"}
+                   "sample": "8192 rows per model x 2 steps, float64 inputs, NumPy/OpenBLAS oracle port of ten_to_predictions_np",
+                   "value_float32_inputs": v32}
         line = {
             "metric": METRIC, "value": value, "unit": "spectra/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
