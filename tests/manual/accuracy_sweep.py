@@ -1,12 +1,12 @@
 """Max parity error of the tensor-core path against the float64 oracle over a large in-prior batch
-(B200 + host CPU).  Usage: python tools/accuracy_sweep.py [rows]"""
+(B200 + host CPU).  Usage: python tests/manual/accuracy_sweep.py [rows]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 import cosmopower_b200 as cp  # noqa: E402
 from cosmopower_b200 import priors, standins  # noqa: E402

@@ -1,12 +1,12 @@
 """Diagnostic run on a B200: parity of one precision mode against the oracle on all six models,
-plus a quick timing.  Usage: python tools/gpu_check.py <fp32|f16x3> [rows]"""
+plus a quick timing.  Usage: python tests/manual/gpu_check.py <fp32|f16x3> [rows]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 import cosmopower_b200 as cp  # noqa: E402
 from cosmopower_b200 import priors, standins  # noqa: E402

@@ -1,12 +1,12 @@
 """Latency of the reference-facing NumPy API (dict in, ndarray out: ten_to_predictions_np) for small batches, next to the
-NumPy/OpenBLAS oracle port on the host cores.  (B200 only)   Usage: python tools/latency_host_api.py [model]"""
+NumPy/OpenBLAS oracle port on the host cores.  (B200 only)   Usage: python tests/manual/latency_host_api.py [model]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 import cosmopower_b200 as cp  # noqa: E402
 from cosmopower_b200 import priors, standins  # noqa: E402
