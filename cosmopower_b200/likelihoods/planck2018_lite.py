@@ -172,6 +172,9 @@ class tf_planck2018_lite:
         self.fisher = self.get_inverse_covmat(d["cov"])
         self.device = device if device is not None else (getattr(tt_emu_model, "_device", None) or 0)
         self.chunk_rows = int(chunk_rows)
+        # batches up to this size leave most SMs idle: the three emulators then run side by side on three streams
+        self.concurrent_rows = 8192
+        self._side_streams = None
         # A linear PCA emulator for TE gets the window functions folded into its basis (fold_te=True, the default):
         # it then predicts the 199 TE band powers directly and the likelihood kernel never sees TE multipoles.
         self._te_binned = None
@@ -196,6 +199,32 @@ class tf_planck2018_lite:
         cols = [keys.index(k) for k in self.tt_emu_model.parameters]
         return parameters, parameters[:, cols].contiguous(), cal
 
+    def _emulate(self, x):
+        """TT, TE and EE for the rows x (:276-278).  A small batch occupies a few clusters per emulator (the engine's
+        small-batch mode), so the three launches go to three streams and share the device instead of queueing."""
+        import torch
+        te = (lambda: self._te_binned.forward_torch(x, ten_to=False)) if self._te_binned is not None else (lambda: self.te_emu_model.predictions_tf(x))
+        if x.shape[0] > self.concurrent_rows:
+            return self.tt_emu_model.ten_to_predictions_tf(x), te(), self.ee_emu_model.ten_to_predictions_tf(x)
+        main = torch.cuda.current_stream(x.device)
+        if self._side_streams is None:
+            self._side_streams = [torch.cuda.Stream(device=x.device), torch.cuda.Stream(device=x.device)]
+        s1, s2 = self._side_streams
+        s1.wait_stream(main)                       # x is ready
+        s2.wait_stream(main)
+        cl_tt = self.tt_emu_model.ten_to_predictions_tf(x)
+        with torch.cuda.stream(s1):
+            cl_te = te()
+        with torch.cuda.stream(s2):
+            cl_ee = self.ee_emu_model.ten_to_predictions_tf(x)
+        main.wait_stream(s1)
+        main.wait_stream(s2)
+        for t in (cl_te, cl_ee):
+            t.record_stream(main)                  # allocated on a side stream, consumed on the caller's
+        x.record_stream(s1)
+        x.record_stream(s2)
+        return cl_tt, cl_te, cl_ee
+
     def get_loglkl(self, parameters):
         """(N, len(parameter_keys)) -> (N, 1) log-likelihood, as the reference's get_loglkl (:257-304)."""
         import torch
@@ -204,9 +233,7 @@ class tf_planck2018_lite:
         out = torch.empty((n, 1), dtype=torch.float32, device=cosmo.device)
         for r0 in range(0, n, self.chunk_rows):
             x = cosmo[r0:r0 + self.chunk_rows]
-            cl_tt = self.tt_emu_model.ten_to_predictions_tf(x)
-            cl_te = self._te_binned.forward_torch(x, ten_to=False) if self._te_binned is not None else self.te_emu_model.predictions_tf(x)
-            cl_ee = self.ee_emu_model.ten_to_predictions_tf(x)
+            cl_tt, cl_te, cl_ee = self._emulate(x)
             out[r0:r0 + x.shape[0], 0] = self._engine.loglike_torch(cl_tt, cl_te, cl_ee, cal[r0:r0 + x.shape[0]])
         return out
 
