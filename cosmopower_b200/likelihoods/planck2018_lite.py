@@ -119,7 +119,7 @@ class _Prior:
 class tf_planck2018_lite:
     def __init__(self, parameters=None, tf_planck2018_lite_path=None, spectra="TTTEEE", use_low_ell_bins=False,
                  units_factor=(2.7255e6) ** 2, tt_emu_model=None, te_emu_model=None, ee_emu_model=None, device=None,
-                 chunk_rows=262144, fold_te=True):
+                 chunk_rows=262144, fold_te=True, cuda_graphs=False):
         self.parameters = parameters
         self.priors = _Prior(parameters) if parameters is not None else None
         self.spectra = spectra
@@ -175,6 +175,11 @@ class tf_planck2018_lite:
         # batches up to this size leave most SMs idle: the three emulators then run side by side on three streams
         self.concurrent_rows = 8192
         self._side_streams = None
+        # cuda_graphs=True: get_loglkl for a small batch is captured once per batch size (side-by-side emulators, tail, all
+        # of their launches) and replayed afterwards - a sampler's sequence of single points pays one graph launch per call
+        self.cuda_graphs = bool(cuda_graphs)
+        self._graphs = {}
+        self._cols = None
         # A linear PCA emulator for TE gets the window functions folded into its basis (fold_te=True, the default):
         # it then predicts the 199 TE band powers directly and the likelihood kernel never sees TE multipoles.
         self._te_binned = None
@@ -196,8 +201,9 @@ class tf_planck2018_lite:
         parameters = parameters.to(device="cuda:%d" % self.device, dtype=torch.float32)
         keys = self.parameter_keys
         cal = parameters[:, keys.index("A_planck")]
-        cols = [keys.index(k) for k in self.tt_emu_model.parameters]
-        return parameters, parameters[:, cols].contiguous(), cal
+        if self._cols is None or self._cols.device != parameters.device:     # device-side column index, built once
+            self._cols = torch.tensor([keys.index(k) for k in self.tt_emu_model.parameters], dtype=torch.int64, device=parameters.device)
+        return parameters, parameters.index_select(1, self._cols), cal
 
     def _emulate(self, x):
         """TT, TE and EE for the rows x (:276-278).  A small batch occupies a few clusters per emulator (the engine's
@@ -219,14 +225,49 @@ class tf_planck2018_lite:
             cl_ee = self.ee_emu_model.ten_to_predictions_tf(x)
         main.wait_stream(s1)
         main.wait_stream(s2)
-        for t in (cl_te, cl_ee):
-            t.record_stream(main)                  # allocated on a side stream, consumed on the caller's
-        x.record_stream(s1)
-        x.record_stream(s2)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (cl_te, cl_ee):
+                t.record_stream(main)              # allocated on a side stream, consumed on the caller's
+            x.record_stream(s1)
+            x.record_stream(s2)
         return cl_tt, cl_te, cl_ee
 
     def get_loglkl(self, parameters):
         """(N, len(parameter_keys)) -> (N, 1) log-likelihood, as the reference's get_loglkl (:257-304)."""
+        import torch
+        if self.cuda_graphs and 0 < len(parameters) <= self.concurrent_rows:
+            return self._get_loglkl_graphed(parameters)
+        return self._get_loglkl(parameters)
+
+    def _get_loglkl_graphed(self, parameters):
+        """Replay of the CUDA graph captured for this batch size (captured on first use; at most 8 sizes are kept)."""
+        import torch
+        dev = "cuda:%d" % self.device
+        if not isinstance(parameters, torch.Tensor):
+            parameters = torch.as_tensor(np.asarray(parameters, dtype=np.float32))
+        n = parameters.shape[0]
+        entry = self._graphs.get(n)
+        if entry is None:
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            static_in = torch.empty((n, len(self.parameter_keys)), dtype=torch.float32, device=dev)
+            static_in.copy_(parameters)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(static_in.device))
+            with torch.cuda.stream(side):            # warm-up outside the capture (lazy allocations, first launches)
+                for _ in range(2):
+                    self._get_loglkl(static_in)
+            torch.cuda.current_stream(static_in.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._get_loglkl(static_in)
+            entry = self._graphs[n] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(parameters)
+        graph.replay()
+        return static_out.clone()
+
+    def _get_loglkl(self, parameters):
         import torch
         parameters, cosmo, cal = self._split(parameters)
         n = cosmo.shape[0]

@@ -218,3 +218,33 @@ def test_end_to_end_class_against_the_oracle_pipeline(fold_te):
     like.close()
     for m in models.values():
         m.close()
+
+
+def test_cuda_graph_replay_equals_the_plain_call():
+    """cuda_graphs=True: small batches replay a CUDA graph captured per batch size (emulators on three streams + tail);
+    every replay must equal the plain call bit for bit, for fresh inputs and for several batch sizes."""
+    import torch
+    import cosmopower_b200 as cp
+    from cosmopower_b200 import priors, standins
+    from cosmopower_b200.likelihoods import tf_planck2018_lite
+    models = {}
+    for key, name in (("tt", "cmb_TT_NN"), ("te", "cmb_TE_PCAplusNN"), ("ee", "cmb_EE_NN")):
+        kind, path = standins.model_path(name)
+        models[key] = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
+    params = list(models["tt"].parameters)
+    plain = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"])
+    graphed = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"],
+                                 cuda_graphs=True)
+    for n in (1, 7, 1, 300, 7):
+        for seed in (1, 2, 3):
+            x = priors.sample_prior(params, n, seed=100 * n + seed, dtype=np.float32)
+            full = torch.from_numpy(np.concatenate([x, np.full((n, 1), 1.001, np.float32)], axis=1)).cuda()
+            a = graphed.get_loglkl(full)
+            b = plain.get_loglkl(full)
+            assert a.shape == (n, 1) and torch.equal(a, b), (n, seed)
+    assert sorted(graphed._graphs) == [1, 7, 300]
+    big = torch.from_numpy(np.concatenate([priors.sample_prior(params, 9000, seed=9, dtype=np.float32),
+                                           np.ones((9000, 1), np.float32)], axis=1)).cuda()
+    assert torch.equal(graphed.get_loglkl(big), plain.get_loglkl(big)) and 9000 not in graphed._graphs
+    plain.close()
+    graphed.close()
