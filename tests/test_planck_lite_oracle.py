@@ -57,3 +57,29 @@ def test_segment_sum_is_a_window_average():
     flat = np.full((1, planck_lite_np.N_ELL), 3.0 / o.units_factor)
     binned = o.bin_spectra(flat, flat, flat)
     np.testing.assert_allclose(binned, 3.0, rtol=1e-6)
+
+
+def test_folding_the_windows_into_the_te_basis_is_exact():
+    """fold_binning_into_pca_emulator: the folded emulator's output (oracle forward pass on the folded attributes) equals
+    the binned output of the original TE emulator - both steps are linear, so only float32 storage of the folded basis
+    separates them; the folded basis is well conditioned for the engine's fp16 split (unit-peak columns)."""
+    from cosmopower_b200 import priors, standins
+    from oracle import oracle_np
+    standins.build_standins()
+    kind, path = standins.model_path("cmb_TE_PCAplusNN")
+    attrs = standins.load_attrs(kind, path)
+    d = planck_lite_np.load_data()
+    first, start, window, _, _ = pl.binning_tables(d["blmin"], d["blmax"], d["bin_w"].astype(np.float32))
+    first, start, window = np.asarray(first), np.asarray(start), np.asarray(window).reshape(-1)
+    n_ell = planck_lite_np.N_ELL
+    is_te = first // n_ell == 1
+    bin0, n_te = int(np.argmax(is_te)), int(is_te.sum())
+    folded = pl.fold_binning_into_pca_emulator(attrs, first, start, window, bin0, n_te, n_ell)
+    assert folded["pca_transform_matrix_"].shape == (attrs["pca_transform_matrix_"].shape[0], n_te)
+    assert np.allclose(np.abs(folded["pca_transform_matrix_"]).max(axis=0), 1.0)
+    x = priors.sample_prior(attrs["parameters"], 64, seed=3)
+    y = oracle_np.forward_pass(attrs, x)
+    binned = np.stack([y[:, first[bin0 + b] - n_ell: first[bin0 + b] - n_ell + start[bin0 + b + 1] - start[bin0 + b]]
+                       @ window[start[bin0 + b]:start[bin0 + b + 1]].astype(np.float64) for b in range(n_te)], axis=1)
+    y_folded = oracle_np.forward_pass(folded, x)
+    assert np.abs(y_folded - binned).max() <= 2e-7 * np.abs(binned).max()
