@@ -102,6 +102,10 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def emit(line):          # replaced in main(): writes to the real stdout
+    print(json.dumps(line), flush=True)
+
+
 def cpu_path(sample_rows, steps, warmup, dtype=np.float64):
     """The reference's CPU implementation of the path (oracle port: NumPy, all BLAS threads).  float64 inputs are the
     reference's documented usage (dicts of lists); float32 arrays make its whole pass float32."""
@@ -157,7 +161,7 @@ def run_reference(args):
                                    "cosmopower_NN.ten_to_predictions_np (the reference checkout is absent on the GPU box)" % sample},
         "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -297,7 +301,7 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     for p in pin_in:
         p.free()
     pin_out.free()
@@ -315,6 +319,15 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, for one) is sent to
+    # stderr by pointing file descriptor 1 at stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
