@@ -167,7 +167,8 @@ def test_fused_linear_plus_boost_power_spectrum(precision):
     np.testing.assert_allclose(y, y2, rtol=2e-5)
 
 
-@pytest.mark.parametrize("n_hidden,n_params,n_modes", [([100, 37], 7, 333), ([64], 3, 40), ([], 5, 70), ([512, 512, 512, 512, 512, 512], 6, 2507)])
+@pytest.mark.parametrize("n_hidden,n_params,n_modes", [([100, 37], 7, 333), ([64], 3, 40), ([], 5, 70), ([512, 512, 512, 512, 512, 512], 6, 2507),
+                                                       ([256, 256], 40, 1000), ([32], 1, 8), ([300], 33, 4001)])
 def test_unusual_architectures_against_oracle(n_hidden, n_params, n_modes):
     """Widths that are not multiples of the tile sizes, even/odd numbers of contractions, no hidden layer,
     and a deeper net, built through the non-restore constructor (reference cosmopower_NN.py:71-80)."""
