@@ -36,6 +36,14 @@ def _worker(rank, world, port, n, out_dir):
     assert (lo, hi) == sharding.shard_bounds(n, world, rank) and local.shape == (hi - lo, attrs["n_modes"])
     full = sharding.predict_sharded(fwd, x, attrs["n_modes"], gather=True)
     np.save(os.path.join(out_dir, "full_%d.npy" % rank), full)
+    # tensor path with the shard written straight into its slot of the gathered buffer (forward_into), even and ragged
+    import torch
+    for m in (n - 1, n):
+        xt = torch.from_numpy(x[:m].astype(np.float32))
+        into = lambda rows, out: out.copy_(torch.from_numpy(oracle_np.forward_pass(attrs, rows.numpy().astype(np.float64)).astype(np.float32)))
+        ft = sharding.predict_sharded(None, xt, attrs["n_modes"], gather=True, forward_into=into)
+        ref = oracle_np.forward_pass(attrs, x[:m].astype(np.float32).astype(np.float64)).astype(np.float32)
+        assert tuple(ft.shape) == ref.shape and np.array_equal(ft.numpy(), ref)
     dist.barrier()
     dist.destroy_process_group()
 
