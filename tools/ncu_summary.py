@@ -2,6 +2,8 @@
 and refresh profiles/traffic.json.
 
 usage: python tools/ncu_summary.py gpurun_out/prof_full.ncu-rep r1e
+       python tools/ncu_summary.py gpurun_out/prof_full_pp.ncu-rep r1j_cmb_PP   (any tag with a model suffix: summary only,
+                                                                                 profiles/traffic.json is left alone)
 """
 import csv
 import io
@@ -37,6 +39,10 @@ def main():
     path = f"profiles/{tag}_ncu_full_summary.csv"
     with open(path, "w", newline="") as f:
         csv.writer(f).writerows(out)
+
+    if "_" in tag:          # a capture of another model: bench.py's roofline.traffic stays the cmb_TT figure
+        print(path, len(out) - 1, "metrics")
+        return
 
     def to_bytes(n):
         u, v = vals[n]
