@@ -116,6 +116,25 @@ def test_full_batch_tensor_path_against_cuda_core_path(name):
     assert worst <= parity.TOL_LOG, worst
 
 
+@pytest.mark.parametrize("name", ["cmb_TT_NN", "cmb_PP_PCAplusNN", "PKLIN_NN", "PKNLBOOST_NN"])
+def test_full_batch_sample_against_oracle(name):
+    """SURVEY 8d parity sampling at BASELINE size: one 1 048 576-row launch; a fixed random subset of 4096 rows plus the
+    first and last row of every cluster's share (pair-group boundaries: 512 rows) near both ends and in the middle of
+    the batch, all modes, against the float64 oracle."""
+    import torch
+    n = 1 << 20
+    m, attrs = get_model(name)
+    x64 = priors.sample_prior(m.parameters, n, seed=20260303)
+    x32 = x64.astype(np.float32)
+    y = m.predictions_tf(torch.from_numpy(x32).cuda())
+    rng = np.random.default_rng(4096)
+    edges = np.array([0, 1, 127, 128, 255, 256, 511, 512, n // 2 - 1, n // 2, n - 513, n - 512, n - 129, n - 128, n - 2, n - 1])
+    rows = np.unique(np.concatenate([rng.choice(n, 4096, replace=False), edges]))
+    y_ref = oracle_np.forward_chunked(attrs, x64[rows])          # float64 draws for the oracle, their float32 cast for the GPU
+    got = y[torch.from_numpy(rows).cuda()].cpu().numpy()
+    assert parity.model_error(name, got, y_ref) <= parity.model_tol(name)
+
+
 def test_pinned_host_path_equals_pageable_path():
     m, _ = get_model("PKLIN_NN")
     n = 50000                                   # several pipeline chunks
