@@ -80,8 +80,6 @@ struct cpb200_engine {
     int simt_width = 0;
     // UMMA scratch
     uint8_t* um_scratch = nullptr;
-    float* d_w0 = nullptr;              // W_[0] in fp32, 8 x w0_ld (first layer in the epilogue warps, UmmaParams::l0_epi)
-    int w0_ld = 0;
     unsigned long long um_scratch_cta = 0;
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
     int* d_error_flag = nullptr;
@@ -356,9 +354,6 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.ext_a0 = e->qf_ext_a0; p.qf_d = e->qf_d; p.qf_pitch = e->qf_pitch; p.qf_cols = e->qf_cols; p.qf_partial = e->qf_partial;
     cudaMemsetAsync(e->d_max_cycles, 0, sizeof(unsigned long long), st);
     p.counters = e->d_counters;
-    p.w0 = e->d_w0; p.w0_ld = e->w0_ld;
-    p.l0_epi = 0;                    // measured slower than the tensor-core first layer (profiles/r1j_l0_in_epilogue_variant.txt)
-    if (const char* l0 = getenv("CPB200_L0_EPI")) p.l0_epi = e->d_w0 && atoi(l0);        // tuning aid
     int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     if (const char* cap = getenv("CPB200_DEBUG_MAX_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(cap)));  // tuning aid
     // Small batches leave most SMs idle: deal the output contraction's chunks (57 % of a cmb_TT pair's cycles) out to
@@ -408,15 +403,6 @@ int setup_umma(cpb200_engine* e) {
         if ((rc = pack_umma(g, k_pad, s_in, cpb::UM_ACT_SCALE))) return rc;
         if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
         k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
-    }
-    // first layer in the epilogue warps: an activation layer fed by at most 8 parameters, followed by another contraction
-    if (e->gemms.size() >= 2 && e->gemms[0].epi == cpb::EPI_ACT && e->P <= 8 && e->gemms[0].n_chunks * e->gemms[0].nc <= cpb::UM_W0_MAX_LD) {
-        const Gemm& g0 = e->gemms[0];
-        e->w0_ld = g0.n_chunks * g0.nc;
-        std::vector<float> w0(static_cast<size_t>(8) * e->w0_ld, 0.f);
-        for (int k = 0; k < g0.K; ++k)
-            for (int n = 0; n < g0.N; ++n) w0[static_cast<size_t>(k) * e->w0_ld + n] = g0.W[static_cast<size_t>(k) * g0.N + n];
-        if ((rc = upload(&e->d_w0, w0.data(), w0.size()))) return rc;
     }
     e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
     e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
@@ -547,7 +533,7 @@ int cpb200_destroy(cpb200_engine* e) {
     }
     cudaFree(e->d_pmean); cudaFree(e->d_pstd);
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
-    cudaFree(e->um_scratch); cudaFree(e->d_w0); cudaFree(e->d_error_flag); cudaFree(e->d_max_cycles); cudaFree(e->d_counters);
+    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_max_cycles); cudaFree(e->d_counters);
     for (int i = 0; i < 2; ++i) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
         if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);

@@ -74,9 +74,7 @@ constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + UM_PAR_SLOTS * UM_MAX_NC * 16;
 constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 2 * UM_PAR_SLOTS;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_MAX_JOBS = 96;
-constexpr int UM_SMEM_W0 = UM_SMEM_TMEMPTR + 16;                             // W_[0] in fp32 (UmmaParams::l0_epi): 8 rows x <= 512 columns
-constexpr int UM_W0_MAX_LD = 512;
-constexpr int UM_SMEM_BYTES = UM_SMEM_W0 + 8 * UM_W0_MAX_LD * 4 + 1024;      // + alignment slack
+constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // + alignment slack
 
 struct UmmaGemm {
     const __half* wpack;   // [n_chunks][k_stages][CTA0: hi|lo half tiles][CTA1: hi|lo half tiles], core-matrix order
@@ -128,13 +126,6 @@ struct UmmaParams {
     int qf_cols;
     float* qf_partial;   // every launch: max over CTAs of the SM cycles between kernel entry and exit
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
-    // first layer in the epilogue warps (l0_epi != 0): contraction 0 (K = n_parameters <= 8) is evaluated with fp32 FMAs by
-    // the epilogue warps themselves instead of going through the tensor pipe - a layer-0 job has almost no MMA work, so as
-    // an accumulator job it only makes the next job wait for a TMEM buffer; w0 = W_[0] in fp32, 8 rows (zero beyond
-    // n_parameters) of w0_ld padded columns
-    const float* w0;
-    int w0_ld;
-    int l0_epi;
 };
 
 // debug counter slots (cycles), per CTA
@@ -428,50 +419,6 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
     }
 }
 
-// First layer without the tensor pipe (UmmaParams::l0_epi): this warp's share of one 128-row x nc-column chunk of
-// (x - mean) / std . W_[0] (cosmopower_NN.py:371,375), in fp32, fed into the same activation / split / store path as
-// an accumulator chunk.  x[rw][k]: standardised parameters of rows 32q + tq + 8rw of the tile (0 beyond n_parameters).
-__device__ __forceinline__ void epi_chunk_l0(const EpiCtx& E, const float4* epi_c, const float* w0c, int w0_ld,
-                                             const float (&x)[4][8], int np, uint8_t* a_dst) {
-    const uint64_t pol_keep = policy_evict_last();
-    constexpr int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
-    for (int pc = E.cw * UM_PIECE; pc < E.nc; pc += kStep) {
-        float4 pp[8];                                     // global (L2) loads: issued first, needed after the FMAs
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pp[j] = __ldg(epi_c + pc + 4 * j + E.tr);
-        float acc[4][8];
-#pragma unroll
-        for (int rw = 0; rw < 4; ++rw)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[rw][j] = 0.f;
-        const float* wp = w0c + pc + 8 * E.tr;            // shared memory; this lane's 8 consecutive logical columns
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k < np) {
-                const float4 wa = *reinterpret_cast<const float4*>(wp + k * w0_ld);
-                const float4 wb = *reinterpret_cast<const float4*>(wp + k * w0_ld + 4);
-                const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                for (int rw = 0; rw < 4; ++rw)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[rw][j] = fmaf(x[rw][k], w[j], acc[rw][j]);
-            }
-        }
-        uint32_t va[16], vb[16];                          // the fragment order epi_operand_half expects
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                va[4 * (j >> 1) + 2 * rr + (j & 1)] = __float_as_uint(acc[rr][j]);
-                vb[4 * (j >> 1) + 2 * rr + (j & 1)] = __float_as_uint(acc[2 + rr][j]);
-            }
-        const int kk = E.chunk_col0 + 8 * E.tr + pc;
-        uint8_t* dst = a_dst + static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(E.q * 32 + E.tq, E.tr);
-        epi_operand_half<EPI_ACT>(va, pp, 1.f, dst, pol_keep, 0);
-        epi_operand_half<EPI_ACT>(vb, pp, 1.f, dst + 1024, pol_keep, 0);          // rows +16
-    }
-}
-
 // 32-byte global accesses (sm_100): one lane covers 8 consecutive floats, 4 lanes a full 128-byte line
 __device__ __forceinline__ void stg_cs_v8(float* p, const float (&y)[8]) {
     asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -704,11 +651,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    if (P.l0_epi) {                              // W_[0] (8 x w0_ld fp32) -> shared memory, read by the epilogue warps
-        const float4* src = reinterpret_cast<const float4*>(P.w0);
-        float4* dst = reinterpret_cast<float4*>(sbase + UM_SMEM_W0);
-        for (int i = threadIdx.x; i < 2 * P.w0_ld; i += UM_THREADS) dst[i] = __ldg(src + i);
-    }
     tc_fence_before();
     __syncthreads();
     if (UM_CLUSTER > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive / multicast
@@ -772,7 +714,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
             int job = 0;
             UM_FOR_EACH_JOB({
-                if (g == 0 && P.l0_epi) continue;                 // layer 0 runs in the epilogue warps: not a pipeline job
                 const UmmaGemm& L = P.g[g];
                 const int k_stages = job_stages(L, c);
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
@@ -838,7 +779,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const uint32_t leader_full0 = map_to_cta(bar_full(0), 0);     // the leader's full barriers
             UM_FOR_EACH_JOB({
                 (void)t;
-                if (g == 0 && P.l0_epi) continue;
                 const int ks = job_stages(P.g[g], c);
                 for (int i = 0; i < ks; ++i) {
                     mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
@@ -856,7 +796,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const uint64_t a_lo0 = umma_desc_a(base + UM_SMEM_STAGES + UM_A_HALF_BYTES);
             const uint64_t b_hi0 = umma_desc(base + UM_SMEM_STAGES + UM_A_STAGE_BYTES);
             UM_FOR_EACH_JOB({
-                if (g == 0 && P.l0_epi) continue;
                 const UmmaGemm& L = P.g[g];
                 const int k_stages = job_stages(L, c);
                 const uint32_t idesc = umma_idesc(L.nc);
@@ -912,7 +851,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         uint32_t ph_a0free[2] = {1, 1};
         long long w_in = 0; const long long t_begin = now();
         const int np = P.n_parameters;
-        for (long long pgi = 0; pgi < ((P.ext_a0 || P.l0_epi) ? 0 : n_my_pg); ++pgi) {      // (prebuilt operand tiles / layer 0 in the epilogue warps: nothing to do)
+        for (long long pgi = 0; pgi < (P.ext_a0 ? 0 : n_my_pg); ++pgi) {      // (prebuilt operand tiles: nothing to do)
             const long long pair = (pg_first + pgi * pg_step) * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding
             for (int t = 0; t < 2; ++t) {
                 w_in += mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
@@ -972,27 +911,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const UmmaGemm& L = P.g[g];
             E.nc = L.nc;
             const long long row0 = (pair * 2 + t) * UM_TILE_M;
-            if (g == 0 && P.l0_epi) {
-                // layer 0 of this tile, chunk c, straight from the parameters: no accumulator, no barrier to wait for -
-                // every job before this one in the table has been drained, which is all the slot written here needs
-                const int np = P.n_parameters;
-                float x[4][8];
-#pragma unroll
-                for (int rw = 0; rw < 4; ++rw) {
-                    const long long grow = row0 + q * 32 + tq + 8 * rw;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        x[rw][k] = (k < np && grow < P.n_rows) ? (P.params[grow * np + k] - P.pmean[k]) / P.pstd[k] : 0.f;
-                }
-                E.chunk_col0 = c * L.nc;
-                epi_chunk_l0(E, L.epi + c * L.nc, reinterpret_cast<const float*>(sbase + UM_SMEM_W0) + c * L.nc, P.w0_ld, x, np, out_buf(0, t, pidx));
-                if (c == L.n_chunks - 1) {
-                    UM_SCRATCH_FENCE(); fence_proxy_async_global();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_aready(t));
-                }
-                continue;
-            }
             const int buf = job & 1;
             const int pb = job & (UM_PAR_SLOTS - 1);
             E.par = epipar + pb * UM_MAX_NC;                  // filled by the loader's bulk copy
