@@ -649,7 +649,8 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
     // chunk leaves as ONE contiguous copy - 56.9 GB/s on this pool's boxes against 52.4 GB/s for the pitched 2-D copy of
     // 10028-byte rows (tools/microbench/d2h_copy_bw.cu).  Unaligned rows cost the kernel its vector stores (cmb_TT: 2x the
     // kernel time), but a chunk's kernel (well under a millisecond) hides behind the previous chunk's transfer (2.4 ms).
-    const bool tight = !pin_out || out_pitch == e->n_modes;
+    // Only for transfers that PCIe dominates (>= 256 MB): a mid-size call is a handful of short launches whose latency counts.
+    const bool tight = (!pin_out || out_pitch == e->n_modes) && n_rows * static_cast<int64_t>(row_bytes) >= (256ll << 20);
     const int64_t dev_pitch = tight ? e->n_modes : e->dpitch;
     // two slots, each with its own stream: H2D -> kernel -> D2H; slot reuse waits for its stream
     for (int64_t c = 0; c < n_chunks + 2; ++c) {
@@ -670,9 +671,12 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
             if (tight) {
                 float* dst = pin_out ? reinterpret_cast<float*>(out_host) + r0 * out_pitch : e->h_out[slot];
                 CU(cudaMemcpyAsync(dst, e->d_out[slot], row_bytes * m, cudaMemcpyDeviceToHost, e->hstream[slot]));
-            } else {
+            } else if (pin_out) {
                 CU(cudaMemcpy2DAsync(reinterpret_cast<float*>(out_host) + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot],
                                      sizeof(float) * e->dpitch, row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[slot]));
+            } else {
+                CU(cudaMemcpy2DAsync(e->h_out[slot], row_bytes, e->d_out[slot], sizeof(float) * e->dpitch, row_bytes, m,
+                                     cudaMemcpyDeviceToHost, e->hstream[slot]));
             }
         }
     }

@@ -147,6 +147,26 @@ def test_pinned_host_path_equals_pageable_path():
     pin_in.free(); pin_out.free()
 
 
+def test_large_host_transfer_equals_device_path():
+    """Host calls that move >= 256 MB write tight rows on the device and leave as one contiguous copy per chunk
+    (cpb200_api.cu forward_host_impl): same bits as the device-tensor call, for pageable, pinned and float64 results."""
+    import torch
+    m, _ = get_model("cmb_TT_NN")
+    n = 30011                                   # 301 MB of float32 spectra, three pipeline chunks, ragged last tile
+    x = priors.sample_prior(m.parameters, n, seed=9, dtype=np.float32)
+    y_dev = m.ten_to_predictions_tf(torch.from_numpy(x).cuda()).cpu().numpy()
+    y = m.engine().forward_host(x, ten_to=True)
+    assert np.array_equal(y, y_dev)
+    pin_in, pin_out = _engine.PinnedArray((n, m.n_parameters)), _engine.PinnedArray((n, m.n_modes))
+    pin_in.array[:] = x
+    pin_out.array[:] = -1.0
+    m.engine().forward_host(pin_in.array, out=pin_out.array, ten_to=True)
+    assert np.array_equal(pin_out.array, y_dev)
+    pin_in.free(); pin_out.free()
+    y64 = m.engine().forward_host(x, ten_to=True, dtype=np.float64)
+    assert y64.dtype == np.float64 and np.array_equal(y64, y_dev.astype(np.float64))
+
+
 def test_determinism_and_row_independence():
     m, _ = get_model("cmb_TT_NN")
     x = priors.sample_prior(m.parameters, 1000, seed=77, dtype=np.float32)
