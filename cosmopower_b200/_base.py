@@ -15,6 +15,7 @@ class _EmulatorBase:
         self._device = device
         self._precision = precision
         self._engines = {}
+        self._engines_fp32 = {}
         self.verbose = verbose
 
     def restore(self, filename):
@@ -30,6 +31,7 @@ class _EmulatorBase:
             setattr(self, k, v)
         self._validate()
         self._engines = {}
+        self._engines_fp32 = {}
 
     def _validate(self):
         arch = [int(self.W_[0].shape[0])] + [int(w.shape[1]) for w in self.W_]
@@ -57,9 +59,10 @@ class _EmulatorBase:
         return self._engines[dev]
 
     def close(self):
-        for e in self._engines.values():
+        for e in list(self._engines.values()) + list(self._engines_fp32.values()):
             e.close()
         self._engines = {}
+        self._engines_fp32 = {}
 
     # -- reference API: NumPy in, NumPy out -----------------------------------------------------------
     def dict_to_ordered_arr_np(self, input_dict):
@@ -79,8 +82,19 @@ class _EmulatorBase:
         if x.ndim != 2 or x.shape[1] != int(self.n_parameters):
             raise ValueError("parameters array must have shape (N, %d), got %s" % (self.n_parameters, x.shape))
         out_dtype = np.float32 if x.dtype == np.float32 else np.float64
+        x32 = np.ascontiguousarray(x, dtype=np.float32)
         # float64 results are widened inside the library while they are copied out (cpb200_forward_host_f64)
-        return self.engine().forward_host(np.ascontiguousarray(x, dtype=np.float32), ten_to=ten_to, dtype=out_dtype)
+        try:
+            return self.engine().forward_host(x32, ten_to=ten_to, dtype=out_dtype)
+        except _engine.Cpb200Error as err:
+            if err.code != _engine.E_RANGE:
+                raise
+        # a row beyond the fp16 split range (|z| >= 64 sigma, a huge activation, NaN): the reference evaluates those
+        # without complaint (cosmopower_NN.py:371-384), so the batch is redone on the fp32 CUDA-core kernels
+        eng = self.engine()
+        if eng.device not in self._engines_fp32:
+            self._engines_fp32[eng.device] = _engine.Engine(self._attrs(), device=eng.device, precision="fp32")
+        return self._engines_fp32[eng.device].forward_host(x32, ten_to=ten_to, dtype=out_dtype)
 
     def predictions_np(self, parameters_dict):
         """reference cosmopower_NN.py:388-405 / cosmopower_PCAplusNN.py:384-401."""

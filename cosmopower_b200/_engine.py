@@ -57,6 +57,7 @@ SYMBOLS = [
     ("cpb200_engine_last_kernel_ms", ctypes.c_float, [ctypes.c_void_p]),
     ("cpb200_engine_last_kernel_cycles", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_engine_set_timing", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    ("cpb200_engine_status", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_int]),
     ("cpb200_engine_debug_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
     ("cpb200_plik_create", ctypes.c_int, [ctypes.POINTER(PlikDesc), ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
@@ -90,10 +91,21 @@ def load_library():
     return _lib
 
 
+E_RANGE = -5
+
+
+class Cpb200Error(RuntimeError):
+    """A non-zero return code of the C ABI; `.code` is the CPB200_E_* value."""
+
+    def __init__(self, code, msg):
+        super().__init__("cpb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
 def _check(rc):
     if rc != 0:
         msg = load_library().cpb200_last_error().decode("utf-8", "replace")
-        raise RuntimeError("cpb200 error %d: %s" % (rc, msg))
+        raise Cpb200Error(rc, msg)
 
 
 def _f32(a):
@@ -184,11 +196,15 @@ class Engine:
         self.precision = prec
         self.n_parameters = d.n_parameters
         self.n_modes = d.n_modes
+        # the C ABI asks callers to serialise the host threads that use one engine (launches themselves are
+        # ordered across streams by the library): every call below holds this lock
+        self._call_lock = threading.RLock()
 
     def close(self):
         if self._h is not None:
-            self._lib.cpb200_destroy(self._h)
-            self._h = None
+            with self._call_lock:
+                self._lib.cpb200_destroy(self._h)
+                self._h = None
 
     def __del__(self):
         try:
@@ -199,8 +215,9 @@ class Engine:
     # -- device-resident path -------------------------------------------------------------
     def forward_device_ptr(self, params_ptr, n_rows, out_ptr, out_pitch, ten_to=False, stream=0, accumulate=False):
         flags = (FLAG_TEN_TO if ten_to else 0) | (FLAG_ACCUMULATE if accumulate else 0)
-        _check(self._lib.cpb200_forward_device(self._h, ctypes.c_void_p(params_ptr), int(n_rows),
-                                               ctypes.c_void_p(out_ptr), int(out_pitch), flags, ctypes.c_void_p(stream)))
+        with self._call_lock:
+            _check(self._lib.cpb200_forward_device(self._h, ctypes.c_void_p(params_ptr), int(n_rows),
+                                                   ctypes.c_void_p(out_ptr), int(out_pitch), flags, ctypes.c_void_p(stream)))
 
     def forward_torch(self, params, out=None, ten_to=False, accumulate=False):
         """params: CUDA float32 tensor (N, P) on this engine's device -> CUDA float32 (N, n_modes)."""
@@ -240,9 +257,19 @@ class Engine:
         if out.dtype not in (np.float32, np.float64) or out.ndim != 2 or out.shape != (n, self.n_modes) or (n > 0 and out.strides[1] != out.itemsize):
             raise ValueError("out must be a float32 or float64 (N, %d) array with contiguous rows" % self.n_modes)
         fn = self._lib.cpb200_forward_host if out.dtype == np.float32 else self._lib.cpb200_forward_host_f64
-        _check(fn(self._h, ctypes.c_void_p(params.ctypes.data), n, ctypes.c_void_p(out.ctypes.data),
-                  out.strides[0] // out.itemsize if n > 1 else self.n_modes, FLAG_TEN_TO if ten_to else 0))
+        with self._call_lock:
+            _check(fn(self._h, ctypes.c_void_p(params.ctypes.data), n, ctypes.c_void_p(out.ctypes.data),
+                      out.strides[0] // out.itemsize if n > 1 else self.n_modes, FLAG_TEN_TO if ten_to else 0))
         return out
+
+    def status(self, clear_range=False):
+        """(watchdog_code, range_flag) of the fused kernel (cpb200_engine_status); after an asynchronous
+        forward_torch, call it once the stream is synchronised: range_flag == 1 means a row was outside the
+        fp16 split range and that batch must be recomputed with precision="fp32"."""
+        w, r = ctypes.c_int32(0), ctypes.c_int32(0)
+        with self._call_lock:
+            _check(self._lib.cpb200_engine_status(self._h, ctypes.byref(w), ctypes.byref(r), 1 if clear_range else 0))
+        return int(w.value), int(r.value)
 
     # -- introspection ---------------------------------------------------------------------------
     def launch_count(self):

@@ -82,8 +82,15 @@ struct cpb200_engine {
     uint8_t* um_scratch = nullptr;
     unsigned long long um_scratch_cta = 0;
     unsigned um_a0_bytes = 0, um_abuf_bytes = 0;
-    int* d_error_flag = nullptr;
-    unsigned long long* d_max_cycles = nullptr;   // fused kernel: SM cycles of the slowest CTA of the latest launch
+    // status words in mapped pinned host memory (readable even after a device trap has killed the context):
+    // [0] watchdog role/barrier code, [1] range flag (a split operand left the fp16 range)
+    int* h_status = nullptr;
+    int* d_status = nullptr;                      // device alias of h_status
+    unsigned long long* d_max_cycles = nullptr;   // fused kernel: SM cycles of the slowest CTA of the latest launch (timing on)
+    // launches of one engine share its activation scratch: a launch on another stream than the previous one waits for it
+    cudaEvent_t ev_order = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
     // quadratic-form use of the fused kernel (Planck-lite): set by the caller before launch_umma
     const uint8_t* qf_ext_a0 = nullptr;
     const float* qf_d = nullptr;
@@ -101,7 +108,7 @@ struct cpb200_engine {
     float* d_out[2] = {nullptr, nullptr};
     int64_t chunk_rows = 0;
     int64_t dpitch = 0;                 // row pitch of d_out (n_modes rounded up to 8 floats: 32-byte rows)
-    cudaEvent_t kdone[2] = {nullptr, nullptr};   // serialises the two slots' kernels (they share the scratch)
+    bool pipeline_ready = false, bounce_ready = false;
     // bookkeeping
     int64_t launches = 0;
     bool timing = false;
@@ -186,8 +193,11 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
                     "(fold the factor into features_std_ / the next layer)", static_cast<double>(wmax));
     // The tensor core truncates (does not round) the fp32 accumulator after each of the 3*K/16 MMA steps,
     // which shrinks |acc| by about half an ulp per step; (1 + bias_ulps * 2^-24) undoes the mean of that.
+    // (the constant is pinned by tests/test_parity_gpu.py::test_truncation_bias_calibration)
     float bias_ulps = cpb::UM_TRUNC_BIAS_ULPS_PER_STEP * 3.f * static_cast<float>(k_pad / 16);
+#ifdef CPB200_PROFILING_BUILD
     if (const char* envb = getenv("CPB200_BIAS_ULPS_PER_STEP")) bias_ulps = static_cast<float>(atof(envb)) * 3.f * static_cast<float>(k_pad / 16);
+#endif
     const float inv = (1.f / (s_w * s_in)) * (1.f + bias_ulps * 5.9604645e-8f);
     g.acc_scale = inv;
     g.k_pad = k_pad;
@@ -279,6 +289,63 @@ std::vector<unsigned> build_jobs(const std::vector<Gemm>& gemms) {
     return jobs;
 }
 
+// Every launch of an engine uses the engine's activation scratch, and the entry points are asynchronous on the
+// caller's stream: a launch on a different stream than the previous one is ordered behind it with an event (recorded
+// after each launch; free when the stream does not change).  Inside a stream capture the event would belong to the
+// graph, so captured launches neither record nor wait: a captured engine must not be used eagerly at the same time.
+int order_before(cpb200_engine* e, cudaStream_t st) {
+    if (e->last_valid && e->last_stream != st) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+            CU(cudaStreamWaitEvent(st, e->ev_order, 0));
+    }
+    return 0;
+}
+int order_after(cpb200_engine* e, cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return 0; }
+    if (!e->ev_order) CU(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
+    CU(cudaEventRecord(e->ev_order, st));
+    e->last_stream = st;
+    e->last_valid = true;
+    return 0;
+}
+
+// what the kernel's watchdog code (UmmaParams::error_flag[0]) says: which role was stuck on which barrier
+const char* watchdog_text(int code) {
+    switch (code) {
+        case 0: return "no watchdog code";
+        case 101: return "loader waiting for the layer-0 operand (standardiser)";
+        case 102: return "loader waiting for an activation tile (epilogue of the previous layer)";
+        case 103: return "loader waiting for a free pipeline stage (MMA issuer)";
+        case 104: return "loader waiting for a free epilogue-constant slot (epilogue)";
+        case 201: return "MMA issuer waiting for a free accumulator (epilogue)";
+        case 202: return "MMA issuer waiting for a loaded stage (loader / peer relay)";
+        case 203: return "peer relay waiting for a loaded stage (loader)";
+        case 301: return "standardiser waiting for its operand buffer (MMA issuer)";
+        case 401: return "epilogue waiting for a finished accumulator (MMA issuer)";
+        case 402: return "epilogue waiting for its constants (loader)";
+        default: return "unknown role";
+    }
+}
+
+// a failed synchronisation: the CUDA error plus, when the kernel's watchdog fired, the stuck role
+int fail_sync(cpb200_engine* e, cudaError_t err, const char* what) {
+    const int code = e && e->h_status ? *reinterpret_cast<volatile int*>(e->h_status) : 0;
+    if (code) return fail(CPB200_E_CUDA, "%s failed: %s; fused-kernel watchdog code %d: %s", what, cudaGetErrorString(err), code, watchdog_text(code));
+    return fail(CPB200_E_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
+}
+
+// after a completed batch: was any split operand outside the fp16 range? (clears the flag)
+int check_range(cpb200_engine* e) {
+    if (!e->h_status) return 0;
+    volatile int* f = reinterpret_cast<volatile int*>(e->h_status) + 1;
+    if (*f == 0) return 0;
+    *f = 0;
+    return fail(CPB200_E_RANGE, "a parameter row is more than 64 standard deviations from the training mean (or not finite), or "
+                "an activation left the fp16 split range: the tensor-core result of this batch is invalid; use CPB200_PREC_FP32_SIMT");
+}
+
 int launch_simt(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
                 cudaStream_t st) {
     const int G = static_cast<int>(e->gemms.size());
@@ -349,10 +416,10 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.abuf_bytes = e->um_abuf_bytes;
     for (int i = 0; i < e->n_jobs; ++i) p.jobs[i] = e->jobs[i];
     p.n_jobs = e->n_jobs;
-    p.error_flag = e->d_error_flag;
-    p.max_cycles = e->d_max_cycles;
+    p.error_flag = e->d_status;
+    p.max_cycles = e->timing ? e->d_max_cycles : nullptr;       // the cycle figure costs a memset + one atomic per CTA: timing mode only
     p.ext_a0 = e->qf_ext_a0; p.qf_d = e->qf_d; p.qf_pitch = e->qf_pitch; p.qf_cols = e->qf_cols; p.qf_partial = e->qf_partial;
-    cudaMemsetAsync(e->d_max_cycles, 0, sizeof(unsigned long long), st);
+    if (p.max_cycles) cudaMemsetAsync(e->d_max_cycles, 0, sizeof(unsigned long long), st);
     p.counters = e->d_counters;
     int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     if (const char* cap = getenv("CPB200_DEBUG_MAX_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(cap)));  // tuning aid
@@ -384,8 +451,10 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
 int forward_async(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
                   cudaStream_t st) {
     if (n == 0) return 0;
-    if (e->precision == CPB200_PREC_FP32_SIMT) return launch_simt(e, params, n, out, pitch, flags, st);
-    return launch_umma(e, params, n, out, pitch, flags, st);
+    if (int rc = order_before(e, st)) return rc;
+    if (int rc = e->precision == CPB200_PREC_FP32_SIMT ? launch_simt(e, params, n, out, pitch, flags, st)
+                                                       : launch_umma(e, params, n, out, pitch, flags, st)) return rc;
+    return order_after(e, st);
 }
 
 }  // namespace
@@ -419,11 +488,12 @@ int setup_umma(cpb200_engine* e) {
     if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
         return (fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaMemset(e->um_scratch, 0, total) != cudaSuccess) return (fail(CPB200_E_CUDA, "memset failed"));
-    if (cudaMalloc(reinterpret_cast<void**>(&e->d_error_flag), sizeof(int)) != cudaSuccess ||
-        cudaMemset(e->d_error_flag, 0, sizeof(int)) != cudaSuccess ||
+    if (cudaHostAlloc(reinterpret_cast<void**>(&e->h_status), 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->d_status), e->h_status, 0) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->d_max_cycles), sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
-        return (fail(CPB200_E_CUDA, "error flag allocation failed"));
+        return (fail(CPB200_E_CUDA, "status block allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    memset(e->h_status, 0, 4 * sizeof(int));
     if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
@@ -533,10 +603,11 @@ int cpb200_destroy(cpb200_engine* e) {
     }
     cudaFree(e->d_pmean); cudaFree(e->d_pstd);
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
-    cudaFree(e->um_scratch); cudaFree(e->d_error_flag); cudaFree(e->d_max_cycles); cudaFree(e->d_counters);
+    cudaFree(e->um_scratch); cudaFree(e->d_max_cycles); cudaFree(e->d_counters);
+    if (e->h_status) cudaFreeHost(e->h_status);
+    if (e->ev_order) cudaEventDestroy(e->ev_order);
     for (int i = 0; i < 2; ++i) {
         if (e->hstream[i]) cudaStreamDestroy(e->hstream[i]);
-        if (e->kdone[i]) cudaEventDestroy(e->kdone[i]);
         if (e->h_in[i]) cudaFreeHost(e->h_in[i]);
         if (e->h_out[i]) cudaFreeHost(e->h_out[i]);
         cudaFree(e->d_in[i]); cudaFree(e->d_out[i]);
@@ -564,25 +635,28 @@ int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_r
     return 0;
 }
 
+// (the "ready" markers are set only once every allocation has succeeded; a partial set-up is retried - what was
+// allocated is reused - and released by cpb200_destroy)
 static int ensure_host_pipeline(cpb200_engine* e) {
-    if (e->hstream[0]) return 0;
+    if (e->pipeline_ready) return 0;
     e->chunk_rows = std::max<int64_t>(256, HOST_CHUNK_BYTES / (static_cast<int64_t>(e->n_modes) * 4) / 256 * 256);
     e->dpitch = (e->n_modes + 7) / 8 * 8;             // 32-byte rows: every 8-byte pair store stays inside one sector
     for (int i = 0; i < 2; ++i) {
-        CU(cudaStreamCreateWithFlags(&e->hstream[i], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&e->kdone[i], cudaEventDisableTiming));
-        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[i]), sizeof(float) * e->chunk_rows * e->P));
-        CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[i]), sizeof(float) * e->chunk_rows * e->dpitch));
+        if (!e->hstream[i]) CU(cudaStreamCreateWithFlags(&e->hstream[i], cudaStreamNonBlocking));
+        if (!e->d_in[i]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_in[i]), sizeof(float) * e->chunk_rows * e->P));
+        if (!e->d_out[i]) CU(cudaMalloc(reinterpret_cast<void**>(&e->d_out[i]), sizeof(float) * e->chunk_rows * e->dpitch));
     }
+    e->pipeline_ready = true;
     return 0;
 }
 
 static int ensure_bounce(cpb200_engine* e) {
-    if (e->h_in[0]) return 0;
+    if (e->bounce_ready) return 0;
     for (int i = 0; i < 2; ++i) {
-        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_in[i]), sizeof(float) * e->chunk_rows * e->P));
-        CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_out[i]), sizeof(float) * e->chunk_rows * e->n_modes));
+        if (!e->h_in[i]) CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_in[i]), sizeof(float) * e->chunk_rows * e->P));
+        if (!e->h_out[i]) CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_out[i]), sizeof(float) * e->chunk_rows * e->n_modes));
     }
+    e->bounce_ready = true;
     return 0;
 }
 
@@ -633,6 +707,8 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
     if (n_rows == 0) return 0;
     if (!params_host || !out_host) return fail(CPB200_E_INVALID, "null buffer");
     if (out_pitch < e->n_modes) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d", static_cast<long long>(out_pitch), e->n_modes);
+    if (flags & CPB200_FLAG_ACCUMULATE)
+        return fail(CPB200_E_INVALID, "CPB200_FLAG_ACCUMULATE needs the first emulator's result on the device: device path only");
     DeviceGuard guard(e->device);
     if (int rc = ensure_host_pipeline(e)) return rc;
     // float32 results in pinned memory are written by the DMA engine directly; anything else is copied (and widened)
@@ -652,35 +728,47 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
     // Only for transfers that PCIe dominates (>= 256 MB): a mid-size call is a handful of short launches whose latency counts.
     const bool tight = (!pin_out || out_pitch == e->n_modes) && n_rows * static_cast<int64_t>(row_bytes) >= (256ll << 20);
     const int64_t dev_pitch = tight ? e->n_modes : e->dpitch;
-    // two slots, each with its own stream: H2D -> kernel -> D2H; slot reuse waits for its stream
+    // two slots, each with its own stream: H2D -> kernel -> D2H; slot reuse waits for its stream.  The kernels of the two
+    // slots (and any earlier device-path launch of this engine) are ordered by forward_async: they share the scratch.
+    // One chunk's submission; a failure leaves through `bail`, which drains both streams first (no copy stays in flight
+    // into the caller's buffers).
+    auto submit = [&](int64_t c, int slot) -> int {
+        const int64_t r0 = c * R, m = std::min<int64_t>(R, n_rows - r0);
+        const float* src = params_host + r0 * e->P;
+        if (!pin_in) { memcpy(e->h_in[slot], src, sizeof(float) * m * e->P); src = e->h_in[slot]; }
+        CU(cudaMemcpyAsync(e->d_in[slot], src, sizeof(float) * m * e->P, cudaMemcpyHostToDevice, e->hstream[slot]));
+        if (int rc = forward_async(e, e->d_in[slot], m, e->d_out[slot], dev_pitch, flags, e->hstream[slot])) return rc;
+        if (tight) {
+            float* dst = pin_out ? reinterpret_cast<float*>(out_host) + r0 * out_pitch : e->h_out[slot];
+            CU(cudaMemcpyAsync(dst, e->d_out[slot], row_bytes * m, cudaMemcpyDeviceToHost, e->hstream[slot]));
+        } else if (pin_out) {
+            CU(cudaMemcpy2DAsync(reinterpret_cast<float*>(out_host) + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot],
+                                 sizeof(float) * e->dpitch, row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[slot]));
+        } else {
+            CU(cudaMemcpy2DAsync(e->h_out[slot], row_bytes, e->d_out[slot], sizeof(float) * e->dpitch, row_bytes, m,
+                                 cudaMemcpyDeviceToHost, e->hstream[slot]));
+        }
+        return 0;
+    };
+    auto bail = [&](int rc) {
+        const std::string msg = g_err;                      // the drain below must not replace the first error's message
+        cudaStreamSynchronize(e->hstream[0]);
+        cudaStreamSynchronize(e->hstream[1]);
+        cudaGetLastError();
+        g_err = msg;
+        return rc;
+    };
     for (int64_t c = 0; c < n_chunks + 2; ++c) {
         const int slot = static_cast<int>(c & 1);
         if (c >= 2) {   // retire chunk c-2 of this slot
-            CU(cudaStreamSynchronize(e->hstream[slot]));
+            const cudaError_t err = cudaStreamSynchronize(e->hstream[slot]);
+            if (err != cudaSuccess) return bail(fail_sync(e, err, "cudaStreamSynchronize"));
             const int64_t r0 = (c - 2) * R, m = std::min<int64_t>(R, n_rows - r0);
             if (!pin_out) copy_rows_out(out_host + r0 * out_pitch, out_pitch, e->h_out[slot], e->n_modes, m, e->n_modes);
         }
-        if (c < n_chunks) {
-            const int64_t r0 = c * R, m = std::min<int64_t>(R, n_rows - r0);
-            const float* src = params_host + r0 * e->P;
-            if (!pin_in) { memcpy(e->h_in[slot], src, sizeof(float) * m * e->P); src = e->h_in[slot]; }
-            CU(cudaMemcpyAsync(e->d_in[slot], src, sizeof(float) * m * e->P, cudaMemcpyHostToDevice, e->hstream[slot]));
-            if (c > 0) CU(cudaStreamWaitEvent(e->hstream[slot], e->kdone[slot ^ 1], 0));
-            if (int rc = forward_async(e, e->d_in[slot], m, e->d_out[slot], dev_pitch, flags, e->hstream[slot])) return rc;
-            CU(cudaEventRecord(e->kdone[slot], e->hstream[slot]));
-            if (tight) {
-                float* dst = pin_out ? reinterpret_cast<float*>(out_host) + r0 * out_pitch : e->h_out[slot];
-                CU(cudaMemcpyAsync(dst, e->d_out[slot], row_bytes * m, cudaMemcpyDeviceToHost, e->hstream[slot]));
-            } else if (pin_out) {
-                CU(cudaMemcpy2DAsync(reinterpret_cast<float*>(out_host) + r0 * out_pitch, sizeof(float) * out_pitch, e->d_out[slot],
-                                     sizeof(float) * e->dpitch, row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[slot]));
-            } else {
-                CU(cudaMemcpy2DAsync(e->h_out[slot], row_bytes, e->d_out[slot], sizeof(float) * e->dpitch, row_bytes, m,
-                                     cudaMemcpyDeviceToHost, e->hstream[slot]));
-            }
-        }
+        if (c < n_chunks) if (int rc = submit(c, slot)) return bail(rc);
     }
-    return 0;
+    return check_range(e);
 }
 }  // namespace
 
@@ -741,11 +829,21 @@ int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int
 
 int64_t cpb200_engine_launch_count(const cpb200_engine* e) { return e ? e->launches : 0; }
 
+int cpb200_engine_status(cpb200_engine* e, int32_t* watchdog_code, int32_t* range_flag, int clear_range) {
+    if (!e) return fail(CPB200_E_INVALID, "null engine");
+    volatile int* st = reinterpret_cast<volatile int*>(e->h_status);
+    if (watchdog_code) *watchdog_code = st ? st[0] : 0;
+    if (range_flag) *range_flag = st ? st[1] : 0;
+    if (st && clear_range) st[1] = 0;
+    if (st && st[0]) return fail(CPB200_E_CUDA, "fused-kernel watchdog code %d: %s", st[0], watchdog_text(st[0]));
+    return 0;
+}
+
 int64_t cpb200_engine_last_kernel_cycles(cpb200_engine* e) {
     if (!e || !e->d_max_cycles) return -1;
     DeviceGuard guard(e->device);
     unsigned long long v = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess ||
+    if (!e->timing || cudaDeviceSynchronize() != cudaSuccess ||
         cudaMemcpy(&v, e->d_max_cycles, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return static_cast<int64_t>(v);
 }
@@ -818,6 +916,15 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
         const int len = d->bin_start[b + 1] - d->bin_start[b];
         if (len < 0 || d->gather_first[b] < 0 || d->gather_first[b] + len > 3 * d->n_ell)
             return fail(CPB200_E_INVALID, "bin %d gathers outside the three spectra", b);
+        if (d->gather_first[b] % d->n_ell + len > d->n_ell)
+            return fail(CPB200_E_INVALID, "bin %d straddles two spectra (multipoles %d .. %d of a %d-multipole row)", b,
+                        d->gather_first[b] % d->n_ell, d->gather_first[b] % d->n_ell + len - 1, d->n_ell);
+    }
+    if (d->te_binned) {        // the TE band powers arrive as one contiguous run: its bins must be contiguous in the vector
+        int first = -1, last = -1, count = 0;
+        for (int b = 0; b < d->n_bins; ++b)
+            if (d->gather_first[b] / d->n_ell == 1) { if (first < 0) first = b; last = b; ++count; }
+        if (count && last - first + 1 != count) return fail(CPB200_E_INVALID, "te_binned needs the TE bins to be contiguous (bins %d .. %d hold %d)", first, last, count);
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -982,7 +1089,9 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
         if (p->qf) {
             cpb200_engine* q = p->qf;
             q->qf_ext_a0 = p->d_tiles; q->qf_d = p->d_diff; q->qf_pitch = p->pad; q->qf_cols = p->pad; q->qf_partial = p->d_partial;
+            if (int rc = order_before(q, st)) return rc;
             if (int rc = launch_umma(q, nullptr, m, nullptr, 0, 0, st)) return rc;
+            if (int rc = order_after(q, st)) return rc;
             cpb::plik_finish_tensor_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(
                 p->d_partial, p->n_part, p->d_row_scale, q->gemms[0].acc_scale, m, loglike + r0);
         } else {

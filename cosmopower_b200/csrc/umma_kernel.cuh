@@ -115,7 +115,8 @@ struct UmmaParams {
     unsigned jobs[UM_MAX_JOBS];   // job table: g | t << 8 | c << 16 | next << 24 (cpb200_api.cu build_jobs); lives in the
                                   // constant bank with the other parameters, so every role decodes it with uniform loads
     int n_jobs;
-    int* error_flag;           // set to a code by the watchdog before trapping
+    int* error_flag;           // host-mapped status words: [0] set to a role/barrier code by the watchdog before trapping,
+                               // [1] set to 1 when a split operand left the fp16 range (the batch's result is invalid)
     unsigned long long* max_cycles;
     // quadratic-form mode (EPI_QUADFORM, single contraction): the layer-0 operand tiles are prebuilt in global memory
     // (tile i at ext_a0 + i * a0_bytes, the layout the standardiser would write), qf_d holds the same rows in fp32
@@ -319,14 +320,24 @@ __device__ __forceinline__ uint32_t umma_idesc(int nc) {
     return (1u << 4) | (static_cast<uint32_t>(nc >> 3) << 17) | (static_cast<uint32_t>((UM_CLUSTER * UM_TILE_M) >> 4) << 24);
 }
 
-// split two floats into fp16 hi and lo parts (hi = rn(x), lo = rn(x - hi)), packed as half2
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __half2 h = __floats2half2_rn(a, b);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+// split two floats into fp16 hi and lo parts (hi = rn(x), lo = rn(x - hi)), packed as half2.  The conversions
+// saturate (F2FP.SATFINITE, same cost as the plain form): a value beyond the fp16 range becomes +-65504 instead of
+// hi = inf, lo = -inf, which would turn the whole row into NaN one contraction later.  Such a row is still wrong -
+// the producers below flag it (UmmaParams::error_flag[1]) and the host reports CPB200_E_RANGE.
+constexpr float UM_F16_MAX = 65504.f;
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));   // first source -> upper half
+    return h;
 }
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_f16x2_sat(a, b);
+    float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi));
+    lo = pack_f16x2_sat(a - hf.x, b - hf.y);
+}
+#ifndef UM_RANGE_CHECK
+#define UM_RANGE_CHECK 1      // producers of split operands report values beyond the fp16 range (0: saturate silently)
+#endif
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -359,7 +370,7 @@ struct EpiCtx {
 // so the special-function unit always has a queued instruction while the FMA pipe works on the other stages
 template <int KIND>
 __device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const float4 (&pp)[8], float acc_scale,
-                                                 uint8_t* dst, uint64_t pol_keep, int dbg) {
+                                                 uint8_t* dst, uint64_t pol_keep, int dbg, int* status) {
     float hv[16];                                  // hv[8rr + j]
     if (KIND == EPI_ACT) {
         float z[16], e[16];
@@ -374,6 +385,13 @@ __device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const 
     } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) { const int rr = i >> 3, j = i & 7; hv[i] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), pp[j].x, pp[j].y); }
+    }
+    if (UM_RANGE_CHECK) {
+        // one FMNMX per value on the otherwise idle ALU pipe; NaN cannot occur (exp overflow gives sigma = 0)
+        float m = fabsf(hv[0]);
+#pragma unroll
+        for (int i = 1; i < 16; ++i) m = fmaxf(m, fabsf(hv[i]));
+        if (m >= UM_F16_MAX && status) *reinterpret_cast<volatile int*>(status + 1) = 1;   // same value from every writer: no atomic
     }
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
@@ -391,7 +409,7 @@ __device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const 
 // hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
 // contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
 template <int KIND>
-__device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_scale, uint8_t* a_dst) {
+__device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_scale, uint8_t* a_dst, int* status) {
     const uint64_t pol_keep = policy_evict_last();
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
     // accumulator column 8i+2tr+cc of a 32-column piece holds logical column 8tr+2i+cc (packing order),
@@ -412,10 +430,10 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
         uint8_t* dst = a_dst + static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(E.q * 32 + E.tq, E.tr);
         tmem_ld_wait16(va);
         tmem_ld_16x256b_x4(t_addr1 + pc, vb);
-        epi_operand_half<KIND>(va, pp, acc_scale, dst, pol_keep, E.dbg);
+        epi_operand_half<KIND>(va, pp, acc_scale, dst, pol_keep, E.dbg, status);
         tmem_ld_wait16(vb);
         if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
-        epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep, E.dbg);          // rows +16
+        epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep, E.dbg, status);          // rows +16
     }
 }
 
@@ -869,6 +887,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             if (k < np) {
                                 const float raw_v = (grow < P.n_rows) ? P.params[grow * np + k] : P.pmean[k];
                                 v = (raw_v - P.pmean[k]) / P.pstd[k] * UM_INPUT_SCALE;
+                                // beyond +-64 sigma (or non-finite) the split would saturate: flag the batch
+                                if (UM_RANGE_CHECK && !(fabsf(v) < UM_F16_MAX) && P.error_flag) *reinterpret_cast<volatile int*>(P.error_flag + 1) = 1;
                             }
                             x[u] = v;
                         }
@@ -930,8 +950,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     }
                 }
             } else
-            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, out_buf(g, t, pidx));
-            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, out_buf(g, t, pidx));
+            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, out_buf(g, t, pidx), P.error_flag);
+            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, out_buf(g, t, pidx), P.error_flag);
             else if (L.epi_kind == EPI_QUADFORM)
                 epi_chunk_quadform(E, P.qf_d + (row0 + q * 32 + tq) * P.qf_pitch, P.qf_pitch, P.n_rows - row0, P.qf_cols,
                                    P.qf_partial + (row0 + q * 32 + tq) * (2 * L.n_chunks) + 2 * c + cw, 2 * L.n_chunks, lane);

@@ -36,6 +36,9 @@ def predict_sharded(forward, parameters_arr, n_modes, group=None, gather=False, 
     if is_np or forward_into is None:
         local = forward(parameters_arr[lo:hi])
         t = torch.from_numpy(np.ascontiguousarray(local)) if isinstance(local, np.ndarray) else local
+        if not t.is_cuda and dist.get_backend(group) == "nccl":
+            # NCCL moves device memory only: a host shard travels through this rank's GPU
+            t = t.to(torch.device("cuda", torch.cuda.current_device()))
         full = torch.empty((world * rows_max, n_modes), dtype=t.dtype, device=t.device)
         mine = full[rank * rows_max:(rank + 1) * rows_max]
         mine[:hi - lo] = t
@@ -54,4 +57,4 @@ def predict_sharded(forward, parameters_arr, n_modes, group=None, gather=False, 
     else:
         out = torch.cat([full[r * rows_max:r * rows_max + shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0], :n_modes]
                          for r in range(world)], dim=0)
-    return out.numpy() if is_np else out
+    return out.cpu().numpy() if is_np else out

@@ -10,7 +10,10 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * CPB200_E_* code and never throws or aborts; cpb200_last_error() gives the message of the last
  * failure on the calling thread.  One engine per (model, device).  Calls on different engines
- * may run concurrently; calls on one engine must be serialised by the caller.
+ * may run concurrently.  Launches of one engine share its activation scratch: the library orders a
+ * launch on another stream behind the engine's previous launch with an event, so asynchronous calls
+ * on different streams are safe; calls from several host THREADS on one engine must still be
+ * serialised by the caller (the Python binding holds a lock per engine).
  */
 #ifndef CPB200_H
 #define CPB200_H
@@ -21,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CPB200_ABI_VERSION 1
+#define CPB200_ABI_VERSION 2
 
 /* error codes */
 #define CPB200_OK            0
@@ -29,7 +32,8 @@ extern "C" {
 #define CPB200_E_CUDA       -2   /* a CUDA runtime call failed (message has the detail)  */
 #define CPB200_E_NO_DEVICE  -3   /* no sm_100 device visible: there is NO CPU fallback   */
 #define CPB200_E_UNSUPPORTED -4  /* layer shape outside what the kernels were built for  */
-#define CPB200_E_RANGE      -5   /* weights overflow the fp16 split (use CPB200_PREC_FP32) */
+#define CPB200_E_RANGE      -5   /* weights, or a batch's inputs / activations, outside the fp16 split range
+                                    (use CPB200_PREC_FP32_SIMT) */
 
 /* numeric formats of the dense contractions (one kernel family, not back-ends) */
 #define CPB200_PREC_FP32_SIMT  0  /* CUDA-core fp32 FMA: on-GPU fp32 truth, slow               */
@@ -138,11 +142,24 @@ int64_t cpb200_engine_launch_count(const cpb200_engine* e);
  * (CUDA events recorded on the launching stream); < 0 if none. Synchronises on those events. */
 float cpb200_engine_last_kernel_ms(cpb200_engine* e);
 /* SM cycles the slowest CTA of the most recent fused-kernel launch spent between entry and exit (a clock-independent
- * cost figure: wall time also depends on the SM clock the power cap leaves); -1 if none.  Synchronises the device. */
+ * cost figure: wall time also depends on the SM clock the power cap leaves); -1 if none or if timing is off.
+ * Synchronises the device. */
 int64_t cpb200_engine_last_kernel_cycles(cpb200_engine* e);
-/* Turn per-call kernel timing events on/off (off by default: they serialise nothing but cost two
- * event records per call). */
+/* Turn per-call kernel timing on/off (off by default: two event records, a 8-byte memset and one atomic per CTA
+ * per call). */
 int cpb200_engine_set_timing(cpb200_engine* e, int enabled);
+/*
+ * Status words the fused kernel writes into mapped host memory (readable after a device fault):
+ *   watchdog_code : 0, or role*100 + barrier of a pipeline role that was stuck for ~3 s before the kernel trapped
+ *                   (1xx loader, 2xx MMA issuer / relay, 3xx standardiser, 4xx epilogue); returns CPB200_E_CUDA then.
+ *   range_flag    : 1 if, since it was last cleared, a parameter row was beyond +-64 standard deviations of the
+ *                   training mean (or not finite) or an activation left the fp16 split range - that batch's result
+ *                   is finite but wrong (the operands saturate); cpb200_forward_host checks it itself and returns
+ *                   CPB200_E_RANGE, callers of the asynchronous cpb200_forward_device ask here after synchronising.
+ * The reference evaluates such rows in float64 without complaint (cosmopower_NN.py:371-384): the Python binding
+ * re-runs the batch on the CPB200_PREC_FP32_SIMT kernels when it sees CPB200_E_RANGE.
+ */
+int cpb200_engine_status(cpb200_engine* e, int32_t* watchdog_code, int32_t* range_flag, int clear_range);
 
 /* Debug: per-CTA cycle counters of the fused kernel's roles (16 int64 per SM; layout UM_CNT_* in
  * csrc/umma_kernel.cuh).  enable!=0 switches collection on for later launches; when `out` is

@@ -22,6 +22,7 @@ def main():
         pitch = (m.n_modes + 7) // 8 * 8
         out = torch.empty((n, pitch), dtype=torch.float32, device="cuda")[:, :m.n_modes]
         eng = m.engine()
+        eng.set_timing(True)
         for _ in range(5):
             eng.forward_torch(x, out=out, ten_to=True)
         torch.cuda.synchronize()

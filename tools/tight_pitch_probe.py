@@ -11,6 +11,7 @@ for name in ("cmb_TT_NN", "PKLIN_NN"):
     for label, out in (("padded pitch", torch.empty((n, pitch), dtype=torch.float32, device="cuda")[:, :m.n_modes]),
                        ("tight pitch", torch.empty((n, m.n_modes), dtype=torch.float32, device="cuda"))):
         eng = m.engine()
+        eng.set_timing(True)
         for _ in range(2):
             eng.forward_torch(x, out=out, ten_to=True)
         torch.cuda.synchronize()

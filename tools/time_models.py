@@ -18,6 +18,7 @@ def main():
         kind, path = standins.model_path(name)
         m = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
         eng = m.engine()
+        eng.set_timing(True)                 # the cycle figure is collected in timing mode only
         x = torch.from_numpy(priors.sample_prior(m.parameters, rows, seed=1, dtype=np.float32)).cuda()
         pitch = (m.n_modes + 7) // 8 * 8
         out = torch.empty((rows, pitch), dtype=torch.float32, device="cuda")[:, :m.n_modes]
