@@ -13,11 +13,36 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("COSMOPOWER_REFERENCE", "/root/reference")
+# The upstream checkout when it exists (the build container); else the byte copies of the two class files that
+# __graft_entry__.build() stages in the git-ignored oracle/_ref/ so that the executed reference travels to the GPU box.
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _ref_root():
+    env = os.environ.get("COSMOPOWER_REFERENCE")
+    for root in ([env] if env else []) + ["/root/reference", _STAGED]:
+        if os.path.isfile(os.path.join(root, "cosmopower", "cosmopower_NN.py")):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _ref_root()
 
 
 def available():
     return os.path.isfile(os.path.join(REF_ROOT, "cosmopower", "cosmopower_NN.py"))
+
+
+def stage(dst=_STAGED, src="/root/reference"):
+    """Copy the two reference class files (unmodified) into oracle/_ref/ - git-ignored, shipped by gpurun - so that
+    bench.py's CPU arm can execute the reference itself on the GPU box.  Called by __graft_entry__.build()."""
+    import shutil
+    os.makedirs(os.path.join(dst, "cosmopower"), exist_ok=True)
+    for name in ("cosmopower_NN.py", "cosmopower_PCAplusNN.py"):
+        shutil.copyfile(os.path.join(src, "cosmopower", name), os.path.join(dst, "cosmopower", name))
+    for name in ("LICENSE",):
+        if os.path.isfile(os.path.join(src, name)):
+            shutil.copyfile(os.path.join(src, name), os.path.join(dst, name))
 
 
 def _install_stub_tf():

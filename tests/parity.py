@@ -3,7 +3,12 @@
 Log-spectrum models (TT, EE, PP, PKLIN, PKNLBOOST): err = max |y - y_ref| / max(|y_ref|, 1) on the
 log10 output of predictions_np against the float64 oracle; must be <= 1e-5 (north star).
 Linear-spectrum model (TE): err = max |y - y_ref| / (row peak |y_ref|) <= 1e-4 (the reference's own
-float32 path sits at 1.6e-5 by this metric on the stand-in, see tests/golden).
+float32 path sits at 1.2e-5 by this metric on the stand-in).  SURVEY 7.2 proposed the stricter per-mode floor
+`max |y - y_ref| / max(|y_ref|, features_std_) <= 1e-5` (`linear_error_strict`): the reference's OWN float32 pass
+(what its TF twin computes) misses that at 7.7e-5 on the stand-in - the spectrum crosses zero and its
+standard deviation is a tenth of the row peak - so no float32 implementation can be held to it.  The GPU tests
+report it beside the row-peak metric and bound it by a small multiple of the reference's float32 figure
+(tests/test_parity_gpu.py::test_te_tolerance_in_both_metrics).
 ten_to_predictions_np: the same log-space metric applied to log10 of the returned spectrum (a
 relative error of 10**y is ln10 * the log-space error, so it is the log error that is bounded).
 """
@@ -33,6 +38,14 @@ def linear_error(y, y_ref):
     y_ref = np.asarray(y_ref, np.float64)
     peak = np.max(np.abs(y_ref), axis=1, keepdims=True)
     return float(np.max(np.abs(y - y_ref) / peak))
+
+
+def linear_error_strict(y, y_ref, features_std):
+    """SURVEY 7.2's metric for the linear-spectrum model: |dy| / max(|y_ref|, features_std_) per mode."""
+    y = np.asarray(y, np.float64)
+    y_ref = np.asarray(y_ref, np.float64)
+    floor = np.maximum(np.abs(y_ref), np.asarray(features_std, np.float64)[None, :])
+    return float(np.max(np.abs(y - y_ref) / floor))
 
 
 def model_error(name, y, y_ref):

@@ -116,7 +116,7 @@ def test_full_batch_tensor_path_against_cuda_core_path(name):
     assert worst <= parity.TOL_LOG, worst
 
 
-@pytest.mark.parametrize("name", ["cmb_TT_NN", "cmb_PP_PCAplusNN", "PKLIN_NN", "PKNLBOOST_NN"])
+@pytest.mark.parametrize("name", parity.MODELS)
 def test_full_batch_sample_against_oracle(name):
     """SURVEY 8d parity sampling at BASELINE size: one 1 048 576-row launch; a fixed random subset of 4096 rows plus the
     first and last row of every cluster's share (pair-group boundaries: 512 rows) near both ends and in the middle of
@@ -312,3 +312,121 @@ def test_float64_host_path_is_the_widened_float32_result(name, n):
     assert np.array_equal(wide[:, :m.n_modes], y64) and (wide[:, m.n_modes:] == -1.0).all()
     d = {k: x[:, i].astype(np.float64) for i, k in enumerate(m.parameters)}
     assert np.array_equal(m.ten_to_predictions_np(d), y64)
+
+
+def test_te_tolerance_in_both_metrics():
+    """The linear-spectrum model in BOTH metrics: the row-peak metric the suite holds it to (1e-4) and
+    SURVEY 7.2's per-mode floor |dy| / max(|y_ref|, features_std_) <= 1e-5.  The second one is not attainable in
+    float32 at all: the reference's own float32 pass (NumPy on float32 inputs = what its TF twin computes) is
+    measured here beside the two GPU paths, and the tensor path is bounded by a small multiple of it."""
+    name = "cmb_TE_PCAplusNN"
+    m, attrs = get_model(name)
+    ms, _ = get_model(name, "fp32")
+    x = priors.sample_prior(m.parameters, 10000, seed=20260201)
+    y_ref = oracle_np.forward_chunked(attrs, x)
+    y_ref32 = oracle_np.forward_chunked(attrs, x.astype(np.float32)).astype(np.float64)     # the reference in float32
+    fs = attrs["features_std_"]
+    rows = {}
+    for label, y in (("tensor f16x3", m.forward_pass_np(x)), ("cuda-core fp32", ms.forward_pass_np(x)), ("reference float32 (CPU)", y_ref32)):
+        rows[label] = (parity.linear_error(y, y_ref), parity.linear_error_strict(y, y_ref, fs))
+        print("cmb_TE %-24s row-peak metric %.3g (tol 1e-4)   per-mode-floor metric %.3g (SURVEY 7.2 proposal: 1e-5)" % ((label,) + rows[label]))
+    for label, (peak_err, strict_err) in rows.items():
+        assert peak_err <= parity.TOL_LINEAR, (label, peak_err)
+    ref_strict = rows["reference float32 (CPU)"][1]
+    assert ref_strict > 1e-5                      # the stricter proposal fails for the reference's own float32 arithmetic
+    assert rows["tensor f16x3"][1] <= 4 * ref_strict, rows
+    assert rows["cuda-core fp32"][1] <= 4 * ref_strict, rows
+
+
+def test_truncation_bias_calibration():
+    """UM_TRUNC_BIAS_ULPS_PER_STEP (umma_kernel.cuh): the tensor core truncates its fp32 accumulator after every MMA
+    step, and the epilogue scale carries (1 + 0.16 ulp x steps) to undo the mean of that.  This pins the calibration:
+    a single 512-deep contraction (96 MMA steps, identity activation) whose outputs are all positive sums, so the
+    truncation is a pure shrink - the mean signed relative error against float64 must sit near zero, far inside the
+    0.16 x 96 = 15 ulp (9e-7) that an uncompensated accumulator loses (a different stepping or driver that rounds
+    differently would show up here as a mean of that size)."""
+    rng = np.random.default_rng(99)
+    K, N = 512, 256
+    W = [np.abs(rng.standard_normal((K, N))).astype(np.float32) / K]
+    b = [np.zeros(N, np.float32)]
+    kw = dict(parameters=["p%d" % i for i in range(K)], modes=np.arange(N), n_hidden=[],
+              weights=dict(W_=W, b_=b, alphas_=[], betas_=[]))
+    x = rng.random((4096, K)) + 0.5                                    # positive inputs, unit standardisation
+    m = cp.cosmopower_NN(device=0, precision="f16x3", **kw)
+    y = m.forward_pass_np(x.astype(np.float32)).astype(np.float64)
+    y_ref = x.astype(np.float32).astype(np.float64) @ W[0].astype(np.float64)
+    rel = (y - y_ref) / y_ref
+    ulp = 2.0 ** -24
+    mean_ulps, spread_ulps = float(rel.mean() / ulp), float(rel.std() / ulp)
+    print("truncation-bias calibration: mean signed error %.2f ulp, spread %.2f ulp (uncompensated: about -15)" % (mean_ulps, spread_ulps))
+    assert abs(mean_ulps) <= 4.0, mean_ulps
+    m.close()
+    # mixed-sign weights (what trained layers look like; the constant was calibrated on those): magnitude-signed error of
+    # the larger half of the outputs
+    W2 = [(rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)]
+    kw["weights"] = dict(W_=W2, b_=b, alphas_=[], betas_=[])
+    m2 = cp.cosmopower_NN(device=0, precision="f16x3", **kw)
+    xs = rng.standard_normal((4096, K))
+    y2 = m2.forward_pass_np(xs.astype(np.float32)).astype(np.float64)
+    r2 = xs.astype(np.float32).astype(np.float64) @ W2[0].astype(np.float64)
+    big = np.abs(r2) > np.median(np.abs(r2))
+    shrink = float((np.sign(r2[big]) * (y2[big] - r2[big]) / np.abs(r2[big])).mean() / ulp)
+    print("truncation-bias calibration, mixed signs: mean magnitude error %.2f ulp of the result" % shrink)
+    assert abs(shrink) <= 8.0, shrink
+    m2.close()
+
+
+def test_rows_outside_the_fp16_split_range():
+    """the standardised parameters are pre-scaled by 2^10 before the fp16 split, so a row more than 64 sigma
+    from the training mean used to become NaN.  Now the split saturates, the kernel raises the range flag,
+    cpb200_forward_host returns CPB200_E_RANGE and the drop-in class redoes the batch on the fp32 kernels: finite
+    numbers that match the oracle, like the reference."""
+    import torch
+    m, attrs = get_model("PKLIN_NN")
+    x = priors.sample_prior(m.parameters, 300, seed=4)
+    x[7, 0] = attrs["parameters_mean_"][0] + 200.0 * attrs["parameters_std_"][0]      # 200 sigma
+    x[250, 3] = attrs["parameters_mean_"][3] - 90.0 * attrs["parameters_std_"][3]
+    with pytest.raises(_engine.Cpb200Error) as ei:
+        m.engine().forward_host(x.astype(np.float32))
+    assert ei.value.code == _engine.E_RANGE
+    y = m.forward_pass_np(x)                                           # class API: falls back to the fp32 kernels
+    y_ref = oracle_np.forward_pass(attrs, x)
+    assert np.all(np.isfinite(y))
+    assert parity.log_error(y, y_ref) <= parity.TOL_LOG
+    # device path: asynchronous, so the flag is polled; the saturated result is finite (no NaN poisoning)
+    eng = m.engine()
+    assert eng.status(clear_range=True) == (0, 0)
+    yd = eng.forward_torch(torch.from_numpy(x.astype(np.float32)).cuda())
+    torch.cuda.synchronize()
+    assert eng.status(clear_range=True) == (0, 1)
+    assert bool(torch.isfinite(yd).all())
+    good = np.ones(300, bool); good[[7, 250]] = False
+    assert parity.log_error(yd.cpu().numpy()[good], y_ref[good]) <= parity.TOL_LOG      # the other rows are unaffected
+    assert eng.status() == (0, 0)
+    # in-prior batches never raise the flag
+    m.forward_pass_np(priors.sample_prior(m.parameters, 5000, seed=6))
+    assert eng.status() == (0, 0)
+
+
+def test_launches_on_different_streams_are_ordered():
+    """every launch of an engine uses its activation scratch; a launch on another stream than the previous
+    one is ordered behind it by the library.  Back-to-back launches on three streams plus a host call, no
+    synchronisation in between, must give the serial results."""
+    import torch
+    m, _ = get_model("cmb_TT_NN")
+    eng = m.engine()
+    xs = [torch.from_numpy(priors.sample_prior(m.parameters, 40000, seed=50 + i, dtype=np.float32)).cuda() for i in range(3)]
+    want = [eng.forward_torch(x).clone() for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in xs]
+    got = []
+    for rep in range(3):
+        got = []
+        for x, st in zip(xs, streams):
+            with torch.cuda.stream(st):
+                got.append(eng.forward_torch(x))
+        y_host = eng.forward_host(xs[0][:3000].cpu().numpy())           # own streams, straight after the async launches
+        torch.cuda.synchronize()
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)
+        assert np.array_equal(y_host, want[0][:3000].cpu().numpy())
