@@ -71,38 +71,55 @@ class _EmulatorBase:
             return np.stack([input_dict[k] for k in self.parameters], axis=1)
         return np.stack([input_dict[k] for k in input_dict], axis=1)
 
-    def forward_pass_np(self, parameters_arr):
+    def forward_pass_np(self, parameters_arr, devices=None):
         """Forward pass on the B200 (reference cosmopower_NN.py:354-384 / cosmopower_PCAplusNN.py:351-381).
         The contraction runs in split-fp16/fp32 on the device; the returned dtype follows the
-        reference's promotion rule (float32 inputs -> float32, anything else -> float64)."""
-        return self._forward_np(parameters_arr, ten_to=False)
+        reference's promotion rule (float32 inputs -> float32, anything else -> float64).
+        `devices` (extension): a list of CUDA device indices, or "all" - the rows are sharded over those GPUs from this
+        one process (one engine and one host thread per device, no collective); the result is the same array."""
+        return self._forward_np(parameters_arr, ten_to=False, devices=devices)
 
-    def _forward_np(self, parameters_arr, ten_to):
+    def _device_list(self, devices):
+        if devices is None:
+            return None
+        if isinstance(devices, str):
+            if devices != "all":
+                raise ValueError("devices must be a list of device indices or \"all\"")
+            devices = list(range(_engine.load_library().cpb200_device_count()))
+        devices = [int(d) for d in devices]
+        if len(set(devices)) != len(devices) or not devices:
+            raise ValueError("devices must name each GPU once")
+        return devices
+
+    def _forward_np(self, parameters_arr, ten_to, devices=None):
         x = np.asarray(parameters_arr)
         if x.ndim != 2 or x.shape[1] != int(self.n_parameters):
             raise ValueError("parameters array must have shape (N, %d), got %s" % (self.n_parameters, x.shape))
         out_dtype = np.float32 if x.dtype == np.float32 else np.float64
         x32 = np.ascontiguousarray(x, dtype=np.float32)
         # float64 results are widened inside the library while they are copied out (cpb200_forward_host_f64)
+        devices = self._device_list(devices)
         try:
-            return self.engine().forward_host(x32, ten_to=ten_to, dtype=out_dtype)
+            if devices is not None and len(devices) > 1:
+                return _engine.forward_host_multi([self.engine(d) for d in devices], x32, ten_to=ten_to, dtype=out_dtype)
+            return self.engine(devices[0] if devices else None).forward_host(x32, ten_to=ten_to, dtype=out_dtype)
         except _engine.Cpb200Error as err:
             if err.code != _engine.E_RANGE:
                 raise
         # a row beyond the fp16 split range (|z| >= 64 sigma, a huge activation, NaN): the reference evaluates those
         # without complaint (cosmopower_NN.py:371-384), so the batch is redone on the fp32 CUDA-core kernels
-        eng = self.engine()
+        eng = self.engine(devices[0] if devices else None)
         if eng.device not in self._engines_fp32:
             self._engines_fp32[eng.device] = _engine.Engine(self._attrs(), device=eng.device, precision="fp32")
         return self._engines_fp32[eng.device].forward_host(x32, ten_to=ten_to, dtype=out_dtype)
 
-    def predictions_np(self, parameters_dict):
-        """reference cosmopower_NN.py:388-405 / cosmopower_PCAplusNN.py:384-401."""
-        return self._forward_np(self.dict_to_ordered_arr_np(parameters_dict), ten_to=False)
+    def predictions_np(self, parameters_dict, devices=None):
+        """reference cosmopower_NN.py:388-405 / cosmopower_PCAplusNN.py:384-401 (`devices`: see forward_pass_np)."""
+        return self._forward_np(self.dict_to_ordered_arr_np(parameters_dict), ten_to=False, devices=devices)
 
-    def ten_to_predictions_np(self, parameters_dict):
+    def ten_to_predictions_np(self, parameters_dict, devices=None):
         """reference cosmopower_NN.py:409-425 / cosmopower_PCAplusNN.py:405-421 (10**x fused in the kernel)."""
-        return self._forward_np(self.dict_to_ordered_arr_np(parameters_dict), ten_to=True)
+        return self._forward_np(self.dict_to_ordered_arr_np(parameters_dict), ten_to=True, devices=devices)
 
     # -- batched device-resident twins of predictions_tf / ten_to_predictions_tf ---------------------------
     def predictions_tf(self, parameters_tensor):

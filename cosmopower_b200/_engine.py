@@ -50,6 +50,10 @@ SYMBOLS = [
     ("cpb200_forward_host", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     ("cpb200_forward_host_f64", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    ("cpb200_forward_host_multi", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
+                                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    ("cpb200_forward_host_multi_f64", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
+                                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     ("cpb200_host_alloc", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
     ("cpb200_host_free", ctypes.c_int, [ctypes.c_void_p]),
     ("cpb200_engine_info", ctypes.c_int, [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 4),
@@ -297,6 +301,36 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self._lib.cpb200_engine_last_kernel_ms(self._h))
+
+
+def forward_host_multi(engines, params, out=None, ten_to=False, dtype=np.float32):
+    """One batch over several devices from one process (cpb200_forward_host_multi): `engines` holds one Engine of the
+    same model per device; rows are sharded contiguously, one library thread per device.  Same result as
+    engines[0].forward_host(params), bit for bit."""
+    if len(engines) == 1:
+        return engines[0].forward_host(params, out=out, ten_to=ten_to, dtype=dtype)
+    e0 = engines[0]
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    if params.ndim != 2 or params.shape[1] != e0.n_parameters:
+        raise ValueError("expected an array of shape (N, %d), got %s" % (e0.n_parameters, params.shape))
+    n = params.shape[0]
+    if out is None:
+        out = np.empty((n, e0.n_modes), dtype=dtype)
+    if out.dtype not in (np.float32, np.float64) or out.ndim != 2 or out.shape != (n, e0.n_modes) or (n > 0 and out.strides[1] != out.itemsize):
+        raise ValueError("out must be a float32 or float64 (N, %d) array with contiguous rows" % e0.n_modes)
+    lib = e0._lib
+    fn = lib.cpb200_forward_host_multi if out.dtype == np.float32 else lib.cpb200_forward_host_multi_f64
+    handles = (ctypes.c_void_p * len(engines))(*[e._h for e in engines])
+    locks = sorted(engines, key=id)
+    for e in locks:
+        e._call_lock.acquire()
+    try:
+        _check(fn(handles, len(engines), ctypes.c_void_p(params.ctypes.data), n, ctypes.c_void_p(out.ctypes.data),
+                  out.strides[0] // out.itemsize if n > 1 else e0.n_modes, FLAG_TEN_TO if ten_to else 0))
+    finally:
+        for e in reversed(locks):
+            e._call_lock.release()
+    return out
 
 
 class PlikEngine:

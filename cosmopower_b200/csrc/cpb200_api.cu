@@ -5,7 +5,11 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -782,6 +786,91 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
 int cpb200_forward_host_f64(cpb200_engine* e, const float* params_host, int64_t n_rows, double* out_host,
                             int64_t out_pitch, int flags) {
     return forward_host_impl<double>(e, params_host, n_rows, out_host, out_pitch, flags);
+}
+
+}  // extern "C"
+
+namespace {
+// CPUs next to a CUDA device (sysfs local_cpulist of its PCI function); empty when the kernel does not say
+std::vector<int> device_local_cpus(int device) {
+    std::vector<int> cpus;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return cpus; }
+    for (char* c = bus; *c; ++c) *c = static_cast<char>(tolower(*c));
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return cpus;
+    char line[4096] = {0};
+    if (fgets(line, sizeof line, f)) {
+        for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            const int got = sscanf(tok, "%d-%d", &a, &b);
+            if (got == 1) b = a;
+            if (got >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; ++c) cpus.push_back(c);
+        }
+    }
+    fclose(f);
+    return cpus;
+}
+
+// Bind the calling thread to the CPUs next to `device` (those it is allowed to use): the pinned bounce buffers it
+// allocates and the result pages it first touches then sit on the GPU's NUMA node.
+void bind_thread_to_device(int device) {
+    const std::vector<int> cpus = device_local_cpus(device);
+    if (cpus.empty()) return;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&allowed); CPU_ZERO(&want);
+    if (pthread_getaffinity_np(pthread_self(), sizeof allowed, &allowed) != 0) return;
+    int n = 0;
+    for (int c : cpus) if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); ++n; }
+    if (n > 0) pthread_setaffinity_np(pthread_self(), sizeof want, &want);
+}
+
+template <typename T>
+int forward_host_multi_impl(cpb200_engine* const* engines, int n_engines, const float* params_host, int64_t n_rows,
+                            T* out_host, int64_t out_pitch, int flags) {
+    if (!engines || n_engines < 1) return fail(CPB200_E_INVALID, "no engines");
+    for (int i = 0; i < n_engines; ++i) {
+        if (!engines[i]) return fail(CPB200_E_INVALID, "null engine");
+        if (engines[i]->P != engines[0]->P || engines[i]->n_modes != engines[0]->n_modes)
+            return fail(CPB200_E_INVALID, "engines describe different models");
+        for (int j = 0; j < i; ++j) if (engines[j] == engines[i]) return fail(CPB200_E_INVALID, "engine listed twice");
+    }
+    if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
+    if (n_engines == 1 || n_rows < 2 * n_engines) return forward_host_impl<T>(engines[0], params_host, n_rows, out_host, out_pitch, flags);
+    // contiguous row shards, sizes differing by at most one row (cosmopower_b200/sharding.py shard_bounds); one host
+    // thread per device, each running the ordinary pipelined host path of its engine into its slice of the result
+    std::vector<int> rc(n_engines, 0);
+    std::vector<std::string> msg(n_engines);
+    std::vector<std::thread> pool;
+    const int64_t base = n_rows / n_engines, extra = n_rows % n_engines;
+    for (int i = 0; i < n_engines; ++i) {
+        const int64_t lo = i * base + std::min<int64_t>(i, extra), m = base + (i < extra ? 1 : 0);
+        pool.emplace_back([=, &rc, &msg] {
+            bind_thread_to_device(engines[i]->device);
+            rc[i] = forward_host_impl<T>(engines[i], params_host + lo * engines[i]->P, m, out_host + lo * out_pitch, out_pitch, flags);
+            if (rc[i]) msg[i] = g_err;
+        });
+    }
+    for (std::thread& th : pool) th.join();
+    for (int i = 0; i < n_engines; ++i)
+        if (rc[i] && rc[i] != CPB200_E_RANGE) return fail(rc[i], "device %d: %s", engines[i]->device, msg[i].c_str());
+    for (int i = 0; i < n_engines; ++i)
+        if (rc[i]) return fail(rc[i], "device %d: %s", engines[i]->device, msg[i].c_str());
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int cpb200_forward_host_multi(cpb200_engine* const* engines, int32_t n_engines, const float* params_host, int64_t n_rows,
+                              float* out_host, int64_t out_pitch, int flags) {
+    return forward_host_multi_impl<float>(engines, n_engines, params_host, n_rows, out_host, out_pitch, flags);
+}
+
+int cpb200_forward_host_multi_f64(cpb200_engine* const* engines, int32_t n_engines, const float* params_host, int64_t n_rows,
+                                  double* out_host, int64_t out_pitch, int flags) {
+    return forward_host_multi_impl<double>(engines, n_engines, params_host, n_rows, out_host, out_pitch, flags);
 }
 
 int cpb200_host_alloc(void** ptr, uint64_t bytes) {

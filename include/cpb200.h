@@ -129,6 +129,19 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
 int cpb200_forward_host_f64(cpb200_engine* e, const float* params_host, int64_t n_rows,
                             double* out_host, int64_t out_pitch, int flags);
 
+/*
+ * The same two calls on several devices of one node from ONE process (rows are independent, every device
+ * holds a full engine): `engines` lists one engine of the same model per device; rows are split into contiguous
+ * shards (sizes differing by at most one row), one host thread per device - bound to the CPUs next to its GPU - runs the
+ * pipelined host path of its engine and DMAs its rows straight into the caller's array.  No collective is involved.
+ * Replaces: predictions_np / ten_to_predictions_np (cosmopower_NN.py:388-425; cosmopower_PCAplusNN.py:384-421) on a
+ * multi-GPU box; the result is identical, bit for bit, to the single-device call.
+ */
+int cpb200_forward_host_multi(cpb200_engine* const* engines, int32_t n_engines, const float* params_host, int64_t n_rows,
+                              float* out_host, int64_t out_pitch, int flags);
+int cpb200_forward_host_multi_f64(cpb200_engine* const* engines, int32_t n_engines, const float* params_host, int64_t n_rows,
+                                  double* out_host, int64_t out_pitch, int flags);
+
 /* Pinned host memory for zero-bounce cpb200_forward_host calls. */
 int cpb200_host_alloc(void** ptr, uint64_t bytes);
 int cpb200_host_free(void* ptr);

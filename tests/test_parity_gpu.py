@@ -430,3 +430,20 @@ def test_launches_on_different_streams_are_ordered():
         for w, g in zip(want, got):
             assert torch.equal(w, g)
         assert np.array_equal(y_host, want[0][:3000].cpu().numpy())
+
+
+def test_single_process_multi_device_equals_one_device():
+    """one process, one engine + host thread per device, contiguous row
+    shards DMA'd into one result array - bit for bit the one-device result.  Needs two GPUs (skipped on a 1-GPU box)."""
+    lib = _engine.load_library()
+    if lib.cpb200_device_count() < 2:
+        pytest.skip("needs two B200s")
+    for name, n in (("PKLIN_NN", 100003), ("cmb_PP_PCAplusNN", 70001)):
+        m, _ = get_model(name)
+        x = priors.sample_prior(m.parameters, n, seed=8)
+        d = {k: x[:, i] for i, k in enumerate(m.parameters)}
+        y1 = m.ten_to_predictions_np(d)
+        y2 = m.ten_to_predictions_np(d, devices=[0, 1])
+        assert y2.dtype == y1.dtype and np.array_equal(y1, y2)
+        y_all = m.predictions_np({k: v.astype(np.float32) for k, v in d.items()}, devices="all")
+        assert y_all.dtype == np.float32 and np.array_equal(y_all, m.predictions_np({k: v.astype(np.float32) for k, v in d.items()}))
