@@ -347,7 +347,7 @@ def test_truncation_bias_calibration():
     differently would show up here as a mean of that size)."""
     rng = np.random.default_rng(99)
     K, N = 512, 256
-    W = [np.abs(rng.standard_normal((K, N))).astype(np.float32) / K]
+    W = [(0.05 * np.abs(rng.standard_normal((K, N)))).astype(np.float32)]
     b = [np.zeros(N, np.float32)]
     kw = dict(parameters=["p%d" % i for i in range(K)], modes=np.arange(N), n_hidden=[],
               weights=dict(W_=W, b_=b, alphas_=[], betas_=[]))
