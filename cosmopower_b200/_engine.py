@@ -64,6 +64,9 @@ SYMBOLS = [
     ("cpb200_engine_status", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_int]),
     ("cpb200_engine_debug_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
+    ("cpb200_debug_job_table", ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                              ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.POINTER(ctypes.c_uint32),
+                                              ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     ("cpb200_plik_create", ctypes.c_int, [ctypes.POINTER(PlikDesc), ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     ("cpb200_plik_destroy", ctypes.c_int, [ctypes.c_void_p]),
     ("cpb200_plik_loglike_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -118,6 +121,29 @@ def _f32(a):
 
 def _ptr(a):
     return a.ctypes.data_as(_fp)
+
+
+def job_table(dims_k, dims_n, kinds, tri=False):
+    """The fused kernel's static schedule for a network (cpb200_debug_job_table; no device needed).
+    Returns (entries, info): entries = list of dicts (g, t, c, nxt, s0, ns, first, last, slot, two, in_code, out_code),
+    info = dict(schedule, rot_mul, par_stages, gemms=[(k_stages, nc, n_chunks)])."""
+    lib = load_library()
+    n = len(dims_k)
+    arr = lambda v: (ctypes.c_int32 * len(v))(*[int(x) for x in v])
+    cap = 512
+    w0, w1 = (ctypes.c_uint32 * cap)(), (ctypes.c_uint32 * cap)()
+    info = (ctypes.c_int32 * (3 + 3 * n))()
+    cnt = lib.cpb200_debug_job_table(n, arr(dims_k), arr(dims_n), arr(kinds), 1 if tri else 0, w0, w1, cap, info)
+    if cnt < 0:
+        _check(cnt)
+    entries = []
+    for i in range(cnt):
+        a, b = int(w0[i]), int(w1[i])
+        entries.append(dict(g=a & 15, t=(a >> 4) & 1, c=(a >> 5) & 127, nxt=(a >> 12) & 1, s0=(a >> 13) & 63, ns=(a >> 19) & 63,
+                            first=(a >> 25) & 1, last=(a >> 26) & 1, slot=(a >> 27) & 3, two=(a >> 29) & 1,
+                            in_code=b & 0xff, out_code=(b >> 8) & 0xff))
+    return entries, dict(schedule=int(info[0]), rot_mul=int(info[1]), par_stages=int(info[2]),
+                         gemms=[(int(info[3 + 3 * i]), int(info[4 + 3 * i]), int(info[5 + 3 * i])) for i in range(n)])
 
 
 class PinnedArray:

@@ -63,6 +63,7 @@ struct Gemm {
     float *dW = nullptr, *dp0 = nullptr, *dp1 = nullptr, *dp2 = nullptr;
     // device, UMMA path
     int k_pad = 0, k_stages = 0, nc = 0, n_chunks = 0;
+    int max_nc = cpb::UM_MAX_NC;   // widest chunk the schedule wants for this contraction (256 = two TMEM slots, 128 = one)
     float acc_scale = 1.f;         // 1 / (weight scale * input-activation scale), a power of two
     bool tri = false;              // upper-triangular weights (quadratic form): chunk c skips the K stages past its columns
     __half* dwpack = nullptr;
@@ -102,7 +103,11 @@ struct cpb200_engine {
     int qf_cols = 0;
     float* qf_partial = nullptr;
     std::vector<unsigned> jobs;         // job table of the fused kernel (build_jobs), passed in the kernel parameters
+    std::vector<unsigned short> jobs_x;
     int n_jobs = 0;
+    int um_rot_mul = 0;                 // see UmmaParams::rot_mul
+    unsigned um_pbuf_bytes = 0;         // see UmmaParams::pbuf_bytes
+    int schedule = 0;                   // SCHED_* chosen by plan_schedule
     long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
     // host pipeline
     cudaStream_t hstream[2] = {nullptr, nullptr};
@@ -182,6 +187,14 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // 2^-11 of the value, so operands are pre-scaled by powers of two (exact) to sit high in the fp16
 // range: weights by s_w (largest |w| lands in [16384, 32768)), the incoming activations by s_in,
 // the produced activations by s_out.  The epilogue undoes s_w*s_in on the fp32 accumulator.
+// chunking of one contraction: K padded to whole stages, N cut into equal chunks of at most max_nc columns (multiples of 32)
+void plan_chunks(Gemm& g, int k_pad) {
+    g.k_pad = k_pad;
+    g.k_stages = k_pad / cpb::UM_KS;
+    g.n_chunks = (g.N + g.max_nc - 1) / g.max_nc;
+    g.nc = round_up((g.N + g.n_chunks - 1) / g.n_chunks, 32);
+}
+
 int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
     float wmax = 0.f;
     for (float w : g.W) {
@@ -204,10 +217,7 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
 #endif
     const float inv = (1.f / (s_w * s_in)) * (1.f + bias_ulps * 5.9604645e-8f);
     g.acc_scale = inv;
-    g.k_pad = k_pad;
-    g.k_stages = k_pad / cpb::UM_KS;
-    g.n_chunks = (g.N + cpb::UM_MAX_NC - 1) / cpb::UM_MAX_NC;
-    g.nc = round_up((g.N + g.n_chunks - 1) / g.n_chunks, 32);
+    plan_chunks(g, k_pad);
     // per (chunk, stage): [CTA0: hi half | lo half][CTA1: hi half | lo half], a half = nc/2 columns
     const size_t tile = static_cast<size_t>(g.nc / 2) * cpb::UM_KS;        // elements per hi or lo half tile
     std::vector<__half> pack(static_cast<size_t>(g.n_chunks) * g.k_stages * 4 * tile, __float2half(0.f));
@@ -270,27 +280,233 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
     return 0;
 }
 
-// Job sequence of one iteration of the fused kernel: all chunks of contractions 1..G-1 for the
-// current pair of tiles, with the NEXT pair's layer-0 chunks merged into the last contraction's
-// (output) phase, so that their epilogues overlap MMAs that do not depend on them.
-std::vector<unsigned> build_jobs(const std::vector<Gemm>& gemms) {
+// ---------------------------------------------------------------------------------------------
+// Job table of the fused kernel (UmmaParams::jobs): the static schedule of one iteration.
+//
+// A job = (contraction g, tile t of the CTA's pair, N-chunk c) = one accumulator in TMEM (one 128-column slot, or two
+// for chunks wider than 128) drained by one epilogue.  The MMA issuer and the loader walk the table's entries in order;
+// an entry is a PART of a job (K stages [s0, s0 + ns)), so a short job can be issued between two parts of a long one.
+// The epilogue warps take the jobs in the order of their last parts.  Why: with two full-width accumulators a job whose
+// MMA is short (layer 0: K = 32; cmb_PP's output chunks: K = 64) makes the next job wait for the previous epilogue -
+// issued in the middle of a long job, into a slot the previous long job's epilogue has already handed back, it costs
+// the tensor pipe nothing.
+//
+// Two schedules (plan_schedule):
+//  SCHED_MERGE_L0   cur = contractions 1 .. G-1 of pair it-1, next = layer 0 of pair it as 128-column jobs, each placed in
+//                   the middle of an output-phase job of the same tile (big-K output phase: cmb_TT/EE/TE, P(k)).
+//  SCHED_OVERLAP    the last contraction has a short K (cmb_PP: 64): its chunks (128 columns) are store-bound, almost
+//                   MMA-free.  cur = the output chunks of pair it-1, next = the WHOLE trunk of pair it; two output jobs
+//                   are issued inside every two-slot trunk job, the rest around the single-slot trunk jobs.  The output
+//                   phase's operand (written by pair p's trunk, read during pair p+1's) lives in per-parity buffers.
+// ---------------------------------------------------------------------------------------------
+enum { SCHED_SIMPLE = 0, SCHED_MERGE_L0 = 1, SCHED_OVERLAP = 2 };
+
+struct JobEntry {
+    int g = 0, t = 0, c = 0, nxt = 0, s0 = 0, ns = 0, first = 1, last = 1, slot = 0, two = 0, in_code = 0, out_code = 0;
+    int job = -1;                   // index of the job this entry is a part of (build-time only)
+};
+
+// which schedule fits the model; also fixes the chunk width of every contraction (before pack_umma)
+int plan_schedule(std::vector<Gemm>& gemms, int k_pad0) {
     const int G = static_cast<int>(gemms.size());
-    std::vector<unsigned> cur_head, cur_out, next0, jobs;
-    auto enc = [](int g, int t, int c, int next) { return static_cast<unsigned>(g | (t << 8) | (c << 16) | (next << 24)); };
-    for (int t = 0; t < 2; ++t)
-        for (int c = 0; c < gemms[0].n_chunks; ++c) next0.push_back(enc(0, t, c, 1));
-    if (G == 1) return next0;       // a single contraction: nothing to overlap (its chunks are both layer 0 and output)
-    for (int g = 1; g < G; ++g)
-        for (int t = 0; t < 2; ++t)
-            for (int c = 0; c < gemms[g].n_chunks; ++c) (g == G - 1 ? cur_out : cur_head).push_back(enc(g, t, c, 0));
-    jobs = cur_head;
-    size_t k = 0;
-    for (size_t i = 0; i < cur_out.size(); ++i) {
-        jobs.push_back(cur_out[i]);
-        while (k < next0.size() && (k + 1) * cur_out.size() <= (i + 1) * (next0.size() + 1)) jobs.push_back(next0[k++]);
+    int sched = SCHED_SIMPLE;
+#ifdef CPB200_PROFILING_BUILD
+    const char* force = getenv("CPB200_SCHEDULE");      // profiling build only: "simple", "merge", "overlap"
+#else
+    const char* force = nullptr;
+#endif
+    if (G >= 2 && gemms[0].epi != cpb::EPI_QUADFORM) {
+        sched = SCHED_MERGE_L0;
+        const int k_last = G >= 2 ? round_up(gemms[G - 2].N, 32) : k_pad0;        // (a lower bound of) the last contraction's padded K
+        if (G >= 3 && k_last <= 128 && gemms[G - 1].epi == cpb::EPI_OUT) sched = SCHED_OVERLAP;
     }
-    while (k < next0.size()) jobs.push_back(next0[k++]);
-    return jobs;
+    if (force) {
+        if (!strcmp(force, "simple")) sched = SCHED_SIMPLE;
+        else if (!strcmp(force, "merge") && G >= 2) sched = SCHED_MERGE_L0;
+        else if (!strcmp(force, "overlap") && G >= 3) sched = SCHED_OVERLAP;
+    }
+    for (Gemm& g : gemms) g.max_nc = cpb::UM_MAX_NC;
+    if (sched != SCHED_SIMPLE) gemms[0].max_nc = cpb::UM_SLOT_COLS;
+    if (sched == SCHED_OVERLAP) gemms[G - 1].max_nc = cpb::UM_SLOT_COLS;
+    return sched;
+}
+
+// cut a job (entry with all its stages) into parts at the given stage indices
+std::vector<JobEntry> split_job(const JobEntry& e, const std::vector<int>& cuts) {
+    std::vector<int> bounds;
+    for (int c : cuts) if (c > 0 && c < e.ns && (bounds.empty() || c > bounds.back())) bounds.push_back(c);
+    bounds.push_back(e.ns);
+    std::vector<JobEntry> parts;
+    int s = 0;
+    for (size_t i = 0; i < bounds.size(); ++i) {
+        JobEntry p = e;
+        p.s0 = e.s0 + s; p.ns = bounds[i] - s; p.first = i == 0; p.last = i + 1 == bounds.size();
+        parts.push_back(p);
+        s = bounds[i];
+    }
+    return parts;
+}
+
+// TMEM slots for every job of an ordered entry list.  A job owns its slot(s) from its first part to the end of its
+// epilogue; the kernel's barriers make ANY static assignment correct as long as a job never waits for a slot whose
+// owner has not been issued completely (deadlock), i.e. the previous owner's last part must precede the new job's first
+// part.  Among the candidates the allocator takes the slot whose previous owner completes earliest in the epilogue order
+// (ties: the lower slot, which a two-slot job's epilogue hands back first).
+int assign_slots(std::vector<JobEntry>& entries) {
+    const int n = static_cast<int>(entries.size());
+    int owner_last[cpb::UM_TMEM_SLOTS];          // table position of the last part of the slot's current owner (-1 = never used)
+    bool open[cpb::UM_TMEM_SLOTS];               // the owner's last part has not been seen yet
+    // the table repeats every iteration: run the allocator twice and keep the second pass (steady state), with the
+    // ownership at the end of pass one as the initial condition
+    std::vector<int> job_slot;
+    for (int sl = 0; sl < cpb::UM_TMEM_SLOTS; ++sl) { owner_last[sl] = -1 - (cpb::UM_TMEM_SLOTS - sl); open[sl] = false; }
+    for (int pass = 0; pass < 2; ++pass) {
+        job_slot.assign(n, -1);
+        for (int i = 0; i < n; ++i) {
+            JobEntry& e = entries[i];
+            if (e.first) {
+                // position of this job's last part
+                int last_pos = i;
+                while (!(entries[last_pos].last && entries[last_pos].job == e.job)) ++last_pos;
+                int best = -1, best_key = 0;
+                if (e.two) {
+                    for (int sl = 0; sl < cpb::UM_TMEM_SLOTS; sl += 2) {
+                        if (open[sl] || open[sl + 1]) continue;
+                        const int key = std::max(owner_last[sl], owner_last[sl + 1]);
+                        if (best < 0 || key < best_key) { best = sl; best_key = key; }
+                    }
+                } else {
+                    for (int sl = 0; sl < cpb::UM_TMEM_SLOTS; ++sl) {
+                        if (open[sl]) continue;
+                        if (best < 0 || owner_last[sl] < best_key) { best = sl; best_key = owner_last[sl]; }
+                    }
+                }
+                if (best < 0) return fail(CPB200_E_UNSUPPORTED, "job table needs more than %d TMEM slots at entry %d", cpb::UM_TMEM_SLOTS, i);
+                job_slot[e.job] = best;
+                for (int k = 0; k <= e.two; ++k) { open[best + k] = true; owner_last[best + k] = last_pos + (pass ? 0 : -n); }
+            }
+            e.slot = job_slot[e.job];
+            if (e.slot < 0) return fail(CPB200_E_UNSUPPORTED, "job table: part before its job's first part at entry %d", i);
+            if (e.last) for (int k = 0; k <= e.two; ++k) open[e.slot + k] = false;
+        }
+        for (int sl = 0; sl < cpb::UM_TMEM_SLOTS; ++sl) if (pass == 0) owner_last[sl] -= 0;   // positions of pass one are already shifted by -n
+    }
+    return 0;
+}
+
+int build_jobs(const std::vector<Gemm>& gemms, int sched, std::vector<JobEntry>& out, int* rot_mul, int* par_stages) {
+    const int G = static_cast<int>(gemms.size());
+    out.clear();
+    *rot_mul = 0; *par_stages = 0;
+    int n_jobs = 0;
+    auto make = [&](int g, int t, int c, int nxt) {
+        JobEntry e;
+        const Gemm& L = gemms[g];
+        e.g = g; e.t = t; e.c = c; e.nxt = nxt; e.s0 = 0;
+        e.ns = L.tri ? std::min(L.k_stages, ((c + 1) * L.nc) / cpb::UM_KS) : L.k_stages;      // upper-triangular weights: stages up to the chunk's last column
+        e.two = L.nc > cpb::UM_SLOT_COLS;
+        e.job = n_jobs++;
+        // operand buffers: layer 0 reads the standardiser's tile; step n = 2(g-1) + t reads rotating buffer 2n and writes 2n + 1
+        const int n = 2 * (g - 1) + t;
+        e.in_code = g == 0 ? cpb::UM_BUF_A0 + t : cpb::UM_BUF_ROT + ((2 * n) % 3 + 3) % 3;
+        e.out_code = g == G - 1 ? cpb::UM_BUF_NONE : cpb::UM_BUF_ROT + ((2 * n + 1) % 3 + 3) % 3;
+        if (sched == SCHED_OVERLAP) {
+            if (g == G - 1) e.in_code = cpb::UM_BUF_PAR + t;
+            if (g == G - 2) e.out_code = cpb::UM_BUF_PAR + t;
+        }
+        return e;
+    };
+    std::vector<JobEntry> l0, head, tail;
+    for (int g = 0; g < G; ++g)
+        for (int t = 0; t < 2; ++t)
+            for (int c = 0; c < gemms[g].n_chunks; ++c) {
+                if (sched == SCHED_OVERLAP) (g == G - 1 ? tail : head).push_back(make(g, t, c, g != G - 1));
+                else if (G == 1 || g == 0) l0.push_back(make(g, t, c, 1));
+                else (g == G - 1 ? tail : head).push_back(make(g, t, c, 0));
+            }
+    if (sched == SCHED_OVERLAP) {
+        *par_stages = gemms[G - 1].k_stages;
+        size_t oi = 0;
+        size_t n_two = 0;
+        for (const JobEntry& e : head) n_two += e.two;
+        const size_t n_small = head.size() - n_two;
+        const size_t per_two = 2;
+        size_t in_two = std::min(tail.size(), per_two * n_two);
+        size_t rest = tail.size() - in_two;
+        const size_t rest_per_small = n_small ? (rest + n_small - 1) / n_small : 0;
+        for (const JobEntry& e : head) {
+            if (!e.two) {
+                out.push_back(e);
+                for (size_t k = 0; k < rest_per_small && rest > 0 && oi < tail.size(); ++k, --rest) out.push_back(tail[oi++]);
+                continue;
+            }
+            const size_t k = std::min(per_two, std::min(in_two, tail.size() - oi));
+            if (k == 0) { out.push_back(e); continue; }
+            // the slots of the previous two-slot job come back after half and after the whole of its epilogue (8.5 k
+            // cycles for a 128 x 256 activation chunk against 0.77 k per K stage): cut after 6/16 and 12/16 of the stages
+            std::vector<int> cuts;
+            for (size_t j = 0; j < k; ++j) cuts.push_back(static_cast<int>((e.ns * (k == 2 ? (j == 0 ? 6 : 12) : 8) + 8) / 16));
+            std::vector<JobEntry> parts = split_job(e, cuts);
+            for (size_t j = 0; j < parts.size(); ++j) {
+                out.push_back(parts[j]);
+                if (j < k && j + 1 < parts.size()) { out.push_back(tail[oi++]); --in_two; }
+            }
+        }
+        while (oi < tail.size()) out.push_back(tail[oi++]);
+    } else if (sched == SCHED_MERGE_L0) {
+        *rot_mul = (G - 1) % 3;
+        out = head;
+        // layer-0 jobs of tile t go into the output jobs of tile t (tile 1's must follow tile 0's last output chunk: the
+        // buffer they write is tile 0's output operand)
+        for (int t = 0; t < 2; ++t) {
+            std::vector<JobEntry> outs, l0s;
+            for (const JobEntry& e : tail) if (e.t == t) outs.push_back(e);
+            for (const JobEntry& e : l0) if (e.t == t) l0s.push_back(e);
+            const size_t n_o = outs.size(), n_l = l0s.size();
+            std::vector<std::vector<JobEntry>> where(n_o);
+            for (size_t k = 0; k < n_l; ++k) where[std::min(n_o - 1, static_cast<size_t>((k + 0.5) * n_o / n_l))].push_back(l0s[k]);
+            for (size_t i = 0; i < n_o; ++i) {
+                const std::vector<JobEntry>& ins = where[i];
+                if (ins.empty() || outs[i].ns < 2) {
+                    out.push_back(outs[i]);
+                    for (const JobEntry& e : ins) out.push_back(e);
+                    continue;
+                }
+                std::vector<int> cuts;
+                for (size_t j = 0; j < ins.size(); ++j) cuts.push_back(static_cast<int>((j + 1) * outs[i].ns / (ins.size() + 1)));
+                std::vector<JobEntry> parts = split_job(outs[i], cuts);
+                size_t used = 0;
+                for (size_t j = 0; j < parts.size(); ++j) {
+                    out.push_back(parts[j]);
+                    if (j + 1 < parts.size() && used < ins.size()) out.push_back(ins[used++]);
+                }
+                while (used < ins.size()) out.push_back(ins[used++]);
+            }
+        }
+    } else {
+        // round-1 order: whole jobs; layer 0 of the next pair spread over the output phase
+        *rot_mul = G > 1 ? (G - 1) % 3 : 0;
+        out = head;
+        size_t k = 0;
+        for (size_t i = 0; i < tail.size(); ++i) {
+            out.push_back(tail[i]);
+            while (k < l0.size() && (k + 1) * tail.size() <= (i + 1) * (l0.size() + 1)) out.push_back(l0[k++]);
+        }
+        while (k < l0.size()) out.push_back(l0[k++]);
+    }
+    if (out.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
+        return fail(CPB200_E_UNSUPPORTED, "%zu job-table entries per tile pair exceed %d", out.size(), cpb::UM_MAX_JOBS);
+    for (const JobEntry& e : out)
+        if (e.c > 127 || e.s0 > 63 || e.ns > 63 || e.g > 15) return fail(CPB200_E_UNSUPPORTED, "layer too wide or too deep for the job-table encoding");
+    return assign_slots(out);
+}
+
+void encode_jobs(const std::vector<JobEntry>& entries, std::vector<unsigned>& w0, std::vector<unsigned short>& w1) {
+    w0.clear(); w1.clear();
+    for (const JobEntry& e : entries) {
+        w0.push_back(cpb::um_job_w0(e.g, e.t, e.c, e.nxt, e.s0, e.ns, e.first, e.last, e.slot, e.two));
+        w1.push_back(cpb::um_job_w1(e.in_code, e.out_code));
+    }
 }
 
 // Every launch of an engine uses the engine's activation scratch, and the entry points are asynchronous on the
@@ -418,8 +634,10 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     p.scratch_cta_bytes = e->um_scratch_cta;
     p.a0_bytes = e->um_a0_bytes;
     p.abuf_bytes = e->um_abuf_bytes;
-    for (int i = 0; i < e->n_jobs; ++i) p.jobs[i] = e->jobs[i];
+    for (int i = 0; i < e->n_jobs; ++i) { p.jobs[i] = e->jobs[i]; p.jobs_x[i] = e->jobs_x[i]; }
     p.n_jobs = e->n_jobs;
+    p.rot_mul = e->um_rot_mul;
+    p.pbuf_bytes = e->um_pbuf_bytes;
     p.error_flag = e->d_status;
     p.max_cycles = e->timing ? e->d_max_cycles : nullptr;       // the cycle figure costs a memset + one atomic per CTA: timing mode only
     p.ext_a0 = e->qf_ext_a0; p.qf_d = e->qf_d; p.qf_pitch = e->qf_pitch; p.qf_cols = e->qf_cols; p.qf_partial = e->qf_partial;
@@ -470,6 +688,7 @@ int setup_umma(cpb200_engine* e) {
     int rc;
     int k_pad = round_up(e->P, cpb::UM_KS);
     unsigned max_stages = 1;
+    e->schedule = plan_schedule(e->gemms, k_pad);
     for (size_t i = 0; i < e->gemms.size(); ++i) {
         Gemm& g = e->gemms[i];
         const float s_in = i == 0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
@@ -479,15 +698,22 @@ int setup_umma(cpb200_engine* e) {
     }
     e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
     e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
-    e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes;
-    if (e->gemms.size() == 1 && e->gemms[0].epi == cpb::EPI_QUADFORM) e->um_scratch_cta = 1024;   // operand tiles are prebuilt elsewhere
     {
-        std::vector<unsigned> jobs = build_jobs(e->gemms);
-        if (jobs.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
-            return (fail(CPB200_E_UNSUPPORTED, "%zu jobs per tile pair exceed %d", jobs.size(), cpb::UM_MAX_JOBS));
-        e->n_jobs = static_cast<int>(jobs.size());
-        e->jobs = jobs;
+        std::vector<JobEntry> entries;
+        int par_stages = 0;
+        if ((rc = build_jobs(e->gemms, e->schedule, entries, &e->um_rot_mul, &par_stages))) return rc;
+        encode_jobs(entries, e->jobs, e->jobs_x);
+        e->n_jobs = static_cast<int>(entries.size());
+        e->um_pbuf_bytes = static_cast<unsigned>(par_stages) * cpb::UM_A_STAGE_BYTES;
+        if (e->schedule == SCHED_OVERLAP) {
+            // the last contraction's operand lives in the parity buffers: the rotating buffers only hold the trunk's tiles
+            max_stages = 1;
+            for (size_t i = 1; i + 1 < e->gemms.size(); ++i) max_stages = std::max<unsigned>(max_stages, e->gemms[i].k_stages);
+            e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
+        }
     }
+    e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes + 4ull * e->um_pbuf_bytes;
+    if (e->gemms.size() == 1 && e->gemms[0].epi == cpb::EPI_QUADFORM) e->um_scratch_cta = 1024;   // operand tiles are prebuilt elsewhere
     const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
     if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
         return (fail(CPB200_E_CUDA, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -914,6 +1140,27 @@ int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int
         e->d_counters = nullptr;
     }
     return static_cast<int>(n);
+}
+
+int cpb200_debug_job_table(int32_t n_gemms, const int32_t* k, const int32_t* n, const int32_t* epi_kind, int32_t tri,
+                           uint32_t* w0, uint32_t* w1, int32_t capacity, int32_t* info) {
+    if (n_gemms < 1 || n_gemms > cpb::UM_MAX_GEMMS || !k || !n || !epi_kind) return fail(CPB200_E_INVALID, "bad job-table request");
+    std::vector<Gemm> gemms(n_gemms);
+    for (int i = 0; i < n_gemms; ++i) { gemms[i].K = k[i]; gemms[i].N = n[i]; gemms[i].epi = epi_kind[i]; gemms[i].tri = tri != 0; }
+    int k_pad = round_up(k[0], cpb::UM_KS);
+    const int sched = plan_schedule(gemms, k_pad);
+    for (int i = 0; i < n_gemms; ++i) { plan_chunks(gemms[i], k_pad); k_pad = gemms[i].n_chunks * gemms[i].nc; }
+    std::vector<JobEntry> entries;
+    int rot_mul = 0, par_stages = 0;
+    if (int rc = build_jobs(gemms, sched, entries, &rot_mul, &par_stages)) return rc;
+    std::vector<unsigned> a; std::vector<unsigned short> b;
+    encode_jobs(entries, a, b);
+    for (size_t i = 0; i < a.size() && static_cast<int>(i) < capacity; ++i) { if (w0) w0[i] = a[i]; if (w1) w1[i] = b[i]; }
+    if (info) {
+        info[0] = sched; info[1] = rot_mul; info[2] = par_stages;
+        for (int i = 0; i < n_gemms; ++i) { info[3 + 3 * i] = gemms[i].k_stages; info[4 + 3 * i] = gemms[i].nc; info[5 + 3 * i] = gemms[i].n_chunks; }
+    }
+    return static_cast<int>(a.size());
 }
 
 int64_t cpb200_engine_launch_count(const cpb200_engine* e) { return e ? e->launches : 0; }

@@ -47,7 +47,9 @@ namespace cpb {
 
 constexpr int UM_TILE_M = 128;
 constexpr int UM_KS = 32;                                    // k elements per pipeline stage
-constexpr int UM_MAX_NC = 256;                               // widest N chunk (one accumulator)
+constexpr int UM_MAX_NC = 256;                               // widest N chunk (one accumulator = two TMEM slots)
+constexpr int UM_SLOT_COLS = 128;                            // TMEM is handed out in four slots of 128 columns
+constexpr int UM_TMEM_SLOTS = 4;
 constexpr int UM_STAGES = 6;
 constexpr int UM_ACT_BUFS = 3;                               // activation buffers per CTA (rotated between its two tiles)
 constexpr int UM_CLUSTER = 2;                                // CTA pair: one tcgen05.mma.cta_group::2 (M = 256) drives both SMs
@@ -68,12 +70,12 @@ constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre
 
 // shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int UM_SMEM_STAGES = 0;
-constexpr int UM_PAR_SLOTS = 4;          // ring of per-chunk epilogue constants: deep enough that the loader never waits for an epilogue
+constexpr int UM_PAR_SLOTS = 6;          // ring of per-chunk epilogue constants: deep enough that the loader never waits for an epilogue
 constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // UM_PAR_SLOTS x 256 float4
 constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + UM_PAR_SLOTS * UM_MAX_NC * 16;
-constexpr int UM_NUM_BARS = 2 * UM_STAGES + 4 + 2 + 2 + 2 + 2 * UM_PAR_SLOTS;
+constexpr int UM_NUM_BARS = 2 * UM_STAGES + 2 * UM_TMEM_SLOTS + 4 + 2 + 2 + 2 * UM_PAR_SLOTS;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
-constexpr int UM_MAX_JOBS = 96;
+constexpr int UM_MAX_JOBS = 320;         // entries of the job table (parts of jobs) per iteration
 constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // + alignment slack
 
 struct UmmaGemm {
@@ -112,9 +114,15 @@ struct UmmaParams {
     unsigned long long scratch_cta_bytes;
     unsigned a0_bytes;         // per tile: k_stages(gemm 0) * 16384
     unsigned abuf_bytes;       // per activation buffer: max k_stages(gemm >= 1) * 16384; a CTA owns UM_ACT_BUFS of them
-    unsigned jobs[UM_MAX_JOBS];   // job table: g | t << 8 | c << 16 | next << 24 (cpb200_api.cu build_jobs); lives in the
-                                  // constant bank with the other parameters, so every role decodes it with uniform loads
+    // Job table (cpb200_api.cu build_jobs): one entry per PART of a job.  A job = (contraction g, tile t, N-chunk c)
+    // = one accumulator; its K loop may be cut into parts so that another job's MMAs are issued in between (the static
+    // schedule interleaves short jobs into long ones).  Lives in the constant bank with the
+    // other parameters, so every role decodes it with uniform loads.  Encoding: um_job_w0 / um_job_w1 below.
+    unsigned jobs[UM_MAX_JOBS];
+    unsigned short jobs_x[UM_MAX_JOBS];
     int n_jobs;
+    int rot_mul;               // rotating activation buffers: buffer = (static index + pair number * rot_mul) mod UM_ACT_BUFS
+    unsigned pbuf_bytes;       // per-pair-parity operand buffers of the last contraction (overlapped output phase); 0 = none
     int* error_flag;           // host-mapped status words: [0] set to a role/barrier code by the watchdog before trapping,
                                // [1] set to 1 when a split operand left the fp16 range (the batch's result is invalid)
     unsigned long long* max_cycles;
@@ -128,6 +136,18 @@ struct UmmaParams {
     float* qf_partial;   // every launch: max over CTAs of the SM cycles between kernel entry and exit
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
 };
+
+// job-table entry, word 0: which part of which job, and where its accumulator lives
+//   g (4 bits) | t << 4 | c << 5 (7 bits) | nxt << 12 | s0 << 13 (6) | ns << 19 (6) | first << 25 | last << 26 | slot << 27 (2) | two << 29
+// nxt: the entry belongs to the pair of iteration `it` (else to pair it-1); stages [s0, s0 + ns) of the job's K loop;
+// first / last part of the job; TMEM slot (128 columns) of the accumulator, `two` = it spans slot and slot + 1.
+__host__ __device__ inline unsigned um_job_w0(int g, int t, int c, int nxt, int s0, int ns, int first, int last, int slot, int two) {
+    return static_cast<unsigned>(g | (t << 4) | (c << 5) | (nxt << 12) | (s0 << 13) | (ns << 19) | (first << 25) | (last << 26) | (slot << 27) | (two << 29));
+}
+// word 1: operand buffer the job reads | buffer its epilogue writes << 8.  Codes: UM_BUF_A0 + t = layer-0 operand of tile t;
+// UM_BUF_ROT + i = rotating activation buffer (i + pair * rot_mul) mod 3; UM_BUF_PAR + t = buffer t of the pair's parity set
+enum { UM_BUF_NONE = 0, UM_BUF_A0 = 0x10, UM_BUF_ROT = 0x20, UM_BUF_PAR = 0x40 };
+__host__ __device__ inline unsigned short um_job_w1(int in_code, int out_code) { return static_cast<unsigned short>(in_code | (out_code << 8)); }
 
 // debug counter slots (cycles), per CTA
 enum { UM_CNT_LOAD_WAIT_EMPTY = 0, UM_CNT_LOAD_WAIT_AREADY = 1, UM_CNT_LOAD_TOTAL = 2,
@@ -360,7 +380,26 @@ struct EpiCtx {
     int q, tq, tr;
     const float4* par;       // the chunk's per-column constants in shared memory (logical column order)
     int dbg;                 // profiling ablations (always 0 in the production instantiation): 4 = no global stores, 8 = no constant loads
+    // TMEM hand-back: the accumulator sits in slot `slot` (and slot + 1 when `two`); the leader CTA's MMA issuer owns
+    // the "slot empty" barriers, the peer arrives on them remotely
+    int lane;
+    uint32_t rel_bar;        // two-slot accumulator: the leader's "slot empty" barrier of its FIRST slot (local address in the
+                             // leader, cluster-mapped in the peer), handed back as soon as its columns are drained; 0 = none
+    bool leader;
 };
+
+// all lanes of the warp have finished reading TMEM slot `sl` (tcgen05.wait::ld precedes this): give it back
+__device__ __forceinline__ void epi_release_first_slot(const EpiCtx& E) {
+    tc_fence_before();
+    __syncwarp();
+    if (E.lane == 0) {
+        if (E.leader) mbar_arrive(E.rel_bar);
+        else mbar_arrive_remote_relaxed(E.rel_bar);        // pure event: the TMEM reads are complete
+    }
+}
+// A two-slot accumulator's first slot is drained once a warp's next piece lies in the second slot: the piece loops below
+// run in two legs (columns below / from UM_SLOT_COLS) and hand the first slot back in between, so that a short job can
+// be issued into it while this epilogue continues.
 
 // hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
 // contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
@@ -419,7 +458,10 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
     int pc = E.cw * UM_PIECE;
     uint32_t va[16], vb[16];
     if (pc < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);            // TMEM reads run one half piece ahead of the math
-    for (; pc < E.nc; pc += kStep) {
+#pragma unroll 1
+    for (int leg = 0; leg < 2; ++leg) {
+    const int leg_end = (leg == 0 && E.rel_bar) ? min(E.nc, UM_SLOT_COLS) : E.nc;
+    for (; pc < leg_end; pc += kStep) {
         // the constants of a 32-column block are stored lane-interleaved (value j of lane group tr at 4j + tr):
         // the four lane groups read 64 contiguous bytes - no shared-memory bank conflicts
         float4 pp[8];
@@ -434,6 +476,8 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
         tmem_ld_wait16(vb);
         if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
         epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep, E.dbg, status);          // rows +16
+    }
+    if (leg == 0 && E.rel_bar) epi_release_first_slot(E);
     }
 }
 
@@ -543,7 +587,10 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     const int nc_valid = min(E.nc, n_modes - E.chunk_col0);
     uint32_t va[16], vb[16];
     if (pc < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);        // TMEM reads run one half piece ahead of the math
-    for (; pc < nc_valid; pc += kStep) {
+#pragma unroll 1
+    for (int leg = 0; leg < 2; ++leg) {
+    const int leg_end = (leg == 0 && E.rel_bar) ? min(nc_valid, UM_SLOT_COLS) : nc_valid;
+    for (; pc < leg_end; pc += kStep) {
         float2 pp[8];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
@@ -569,6 +616,8 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
         tmem_ld_wait16(vb);
         if (pc + kStep < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
         epi_output_half<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, pitch, mode, E.q * 32 + E.tq + 16, rows_left, gc, n_modes, E.dbg);
+    }
+    if (leg == 0 && E.rel_bar) epi_release_first_slot(E);
     }
 }
 
@@ -638,15 +687,16 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const int lane = threadIdx.x & 31;
 
     const uint32_t bars = base + UM_SMEM_BARS;
+    constexpr int B_ACC = 2 * UM_STAGES, B_AREADY = B_ACC + 2 * UM_TMEM_SLOTS, B_A0 = B_AREADY + 4, B_PAR = B_A0 + 4;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (UM_STAGES + s); };
-    auto bar_accfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + b); };
-    auto bar_accempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 2 + b); }; // leader only: both CTAs' epilogues arrive
-    auto bar_aready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 4 + t); };
-    auto bar_a0ready = [&](int t) { return bars + 8u * (2 * UM_STAGES + 6 + t); };
-    auto bar_a0free = [&](int t) { return bars + 8u * (2 * UM_STAGES + 8 + t); };
-    auto bar_parfull = [&](int b) { return bars + 8u * (2 * UM_STAGES + 10 + b); };
-    auto bar_parempty = [&](int b) { return bars + 8u * (2 * UM_STAGES + 10 + UM_PAR_SLOTS + b); };
+    auto bar_accfull = [&](int sl) { return bars + 8u * (B_ACC + sl); };                    // per TMEM slot (a job signals its first slot)
+    auto bar_accempty = [&](int sl) { return bars + 8u * (B_ACC + UM_TMEM_SLOTS + sl); };   // leader only: both CTAs' epilogues arrive
+    auto bar_aready = [&](int ts) { return bars + 8u * (B_AREADY + ts); };                  // ts = 2 * (pair number & 1) + tile
+    auto bar_a0ready = [&](int t) { return bars + 8u * (B_A0 + t); };
+    auto bar_a0free = [&](int t) { return bars + 8u * (B_A0 + 2 + t); };
+    auto bar_parfull = [&](int b) { return bars + 8u * (B_PAR + b); };
+    auto bar_parempty = [&](int b) { return bars + 8u * (B_PAR + UM_PAR_SLOTS + b); };
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbase + UM_SMEM_TMEMPTR);
 
     if (threadIdx.x == 0) {
@@ -654,13 +704,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         // its loader) AND the peer's relay has reported the peer's copies (one remote arrive): one wait per stage
         const uint32_t full_count = (UM_CLUSTER > 1 && cluster_ctarank() == 0) ? 2 : 1;
         for (int s = 0; s < UM_STAGES; ++s) { mbar_init(bar_full(s), full_count); mbar_init(bar_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS); }
+        for (int b = 0; b < UM_TMEM_SLOTS; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS); }
         for (int b = 0; b < UM_PAR_SLOTS; ++b) { mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS); }
-        for (int t = 0; t < 2; ++t) {
-            mbar_init(bar_aready(t), UM_EPI_WARPS);
-            mbar_init(bar_a0ready(t), 1);
-            mbar_init(bar_a0free(t), 1);
-        }
+        for (int ts = 0; ts < 4; ++ts) mbar_init(bar_aready(ts), UM_EPI_WARPS);
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_a0ready(t), 1); mbar_init(bar_a0free(t), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -678,45 +725,46 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const int out_split = SPLIT ? P.out_split : 1, split_id = SPLIT ? static_cast<int>(blockIdx.x / UM_CLUSTER) % out_split : 0;
     const int out_gemm = SPLIT ? P.n_gemms - 1 : -1;       // the contraction whose chunks are dealt out
     const long long pg_first = (blockIdx.x / UM_CLUSTER) / out_split, pg_step = (gridDim.x / UM_CLUSTER) / out_split;
-    // pair-groups this cluster walks; iteration `it` runs the table's "cur" jobs (contractions >= 1) for
-    // pair-group it-1 and its "next" jobs (layer 0) for pair-group it, so a pair's layer-0 epilogues hide
-    // behind the previous pair's output phase instead of stalling the tensor pipe at every pair start
+    // pair-groups this cluster walks; iteration `it` runs the table's "cur" entries for pair-group it-1 and its "next"
+    // entries for pair-group it (layer 0 only, or the whole trunk when the output phase is overlapped): work of the next
+    // pair fills the phases of the current one in which the tensor pipe would wait for epilogues
     const long long n_my_pg = P.n_pairgroups > pg_first ? (P.n_pairgroups - pg_first + pg_step - 1) / pg_step : 0;
     const int n_jobs = P.n_jobs;
-    // K stages job (g, c) runs: all of them, or - for upper-triangular weights - those up to the chunk's last column
-    auto job_stages = [&](const UmmaGemm& L, int c) { return L.tri ? min(L.k_stages, ((c + 1) * L.nc) / UM_KS) : L.k_stages; };
 
     uint8_t* cta_scratch = P.scratch + static_cast<unsigned long long>(blockIdx.x) * P.scratch_cta_bytes;
-    auto a0_buf = [&](int t) { return cta_scratch + static_cast<size_t>(t) * P.a0_bytes; };
-    const int G = P.n_gemms;
-    // Activation buffers: THREE per CTA, rotated between its two tiles.  With the job order X.g, Y.g, X.g+1, ...
-    // at most three 128 x K tiles are live at any time (X.in, X.out, Y.in - or Y.in, Y.out, X.out), so step
-    // n = 2(g-1) + t of pair number `pidx` reads slot (2n + pidx(G-1)) mod 3 and writes slot (2n + 1 + ...) mod 3
-    // (= the slot step n+2, the same tile's next contraction, reads).  The per-pair offset makes the next
-    // pair's layer 0, which runs inside this pair's output phase, land in the slot that is free then.
-    // 3 x 256 KB per CTA instead of 4-6 keeps the whole scratch (111 MB) under the L2 capacity.
-    auto act_slot = [&](int slot) { return cta_scratch + 2ull * P.a0_bytes + static_cast<size_t>(slot) * P.abuf_bytes; };
-    auto in_buf = [&](int g, int t, long long pidx) {      // operand of contraction g >= 1
-        return act_slot(static_cast<int>((2 * (2 * (g - 1) + t) + pidx * (G - 1)) % 3));
-    };
-    auto out_buf = [&](int g, int t, long long pidx) {     // written by contraction g (any g that is not the last)
-        return act_slot(static_cast<int>((2 * (2 * (g - 1) + t) + 3 + 1 + pidx * (G - 1)) % 3));
+    // CTA-private scratch: [2 layer-0 operand tiles][UM_ACT_BUFS rotating activation buffers][4 parity buffers].
+    // Rotating buffers: with the job order X.g, Y.g, X.g+1, ... at most three 128 x K tiles are live at any time
+    // (X.in, X.out, Y.in - or Y.in, Y.out, X.out); the host numbers them so that step n = 2(g-1) + t reads buffer 2n and
+    // writes buffer 2n + 1 (mod 3), plus a per-pair offset (rot_mul) that lets the next pair's layer 0, which runs inside
+    // this pair's output phase, land in the buffer that is free then.  3 x 256 KB per CTA keeps the scratch at 111 MB.
+    // Parity buffers hold the operand of an overlapped output phase: written by pair p's trunk, read during pair p+1's.
+    auto buf_addr = [&](uint32_t code, long long pidx) -> uint8_t* {
+        if (code & UM_BUF_ROT)
+            return cta_scratch + 2ull * P.a0_bytes + static_cast<size_t>(((code & 0xf) + pidx * P.rot_mul) % UM_ACT_BUFS) * P.abuf_bytes;
+        if (code & UM_BUF_PAR)
+            return cta_scratch + 2ull * P.a0_bytes + static_cast<size_t>(UM_ACT_BUFS) * P.abuf_bytes
+                   + static_cast<size_t>(2 * (pidx & 1) + (code & 1)) * P.pbuf_bytes;
+        return cta_scratch + static_cast<size_t>(code & 1) * P.a0_bytes;
     };
 
-// every role walks the same job sequence
-#define UM_FOR_EACH_JOB(...)                                                                           \
+// every role walks the same entry sequence
+#define UM_FOR_EACH_ENTRY(...)                                                                         \
     for (long long it = 0; it <= n_my_pg; ++it) {                                                      \
         const bool has_cur = it >= 1, has_next = it < n_my_pg;                                         \
         for (int ji = 0; ji < n_jobs; ++ji) {                                                          \
-            const uint32_t jw = P.jobs[ji];                                                              \
-            const int g = jw & 0xff, t = (jw >> 8) & 0xff, c = (jw >> 16) & 0xff;                      \
-            const bool is_next = (jw >> 24) != 0;                                                      \
+            const uint32_t jw = P.jobs[ji];                                                            \
+            const int g = jw & 15, t = (jw >> 4) & 1, c = (jw >> 5) & 127;                             \
+            const bool is_next = (jw >> 12) & 1;                                                       \
             if (is_next ? !has_next : !has_cur) continue;                                              \
             if (SPLIT && g == out_gemm && c % out_split != split_id) continue;   /* another cluster's columns */ \
+            const int s0 = (jw >> 13) & 63, ns = (jw >> 19) & 63;                                      \
+            const bool first = (jw >> 25) & 1, last = (jw >> 26) & 1;                                  \
+            const int slot = (jw >> 27) & 3, two = (jw >> 29) & 1;                                     \
             /* rows beyond n_rows are padding (computed, never stored) */                              \
             const long long pidx = is_next ? it : it - 1;      /* this cluster's running pair number */  \
             const long long pair = (pg_first + pidx * pg_step) * UM_CLUSTER + cta_rank;                \
-            (void)pair; (void)c; (void)pidx;                                                           \
+            const int ts = 2 * static_cast<int>(pidx & 1) + t;                                         \
+            (void)pair; (void)c; (void)pidx; (void)s0; (void)ns; (void)first; (void)last; (void)slot; (void)two; (void)ts; \
             __VA_ARGS__                                                                                \
         }                                                                                              \
     }
@@ -727,23 +775,22 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         {
             long long w_empty = 0, w_aready = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_empty = 1;                 // fresh "empty" barriers pass at parity 1
-            uint32_t ph_aready = 0, ph_a0ready = 0;               // one phase bit per tile
+            uint32_t ph_aready = 0, ph_a0ready = 0;               // one phase bit per barrier
             uint32_t ph_parempty = (1u << UM_PAR_SLOTS) - 1;      // one phase bit per slot
             const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-            int job = 0;
-            UM_FOR_EACH_JOB({
+            int pb = 0;
+            UM_FOR_EACH_ENTRY({
                 const UmmaGemm& L = P.g[g];
-                const int k_stages = job_stages(L, c);
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
                 const long long j_t0 = now(), j_we0 = w_empty, j_wa0 = w_aready;
-                if (c == (g == out_gemm ? split_id : 0) && !(g == 0 && P.ext_a0)) {   // first chunk this cluster runs of (g, t): the whole K extent of the tile's operand must be written
+                if (first && c == (g == out_gemm ? split_id : 0) && !(g == 0 && P.ext_a0)) {   // first chunk this cluster runs of (g, t): the whole K extent of the tile's operand must be written
                     if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), (ph_a0ready >> t) & 1, P.error_flag, 101); ph_a0ready ^= 1u << t; }
-                    else { w_aready += mbar_wait(bar_aready(t), (ph_aready >> t) & 1, P.error_flag, 102); ph_aready ^= 1u << t; }
+                    else { w_aready += mbar_wait(bar_aready(ts), (ph_aready >> ts) & 1, P.error_flag, 102); ph_aready ^= 1u << ts; }
                 }
-                const uint8_t* a_src = g != 0 ? in_buf(g, t, pidx)
-                                     : P.ext_a0 ? P.ext_a0 + static_cast<size_t>(pair * 2 + t) * P.a0_bytes : a0_buf(t);
-                {   // this chunk's per-column epilogue constants -> shared memory (ring indexed by the job count)
-                    const int pb = job & (UM_PAR_SLOTS - 1);
+                const uint8_t* a_src = (g == 0 && P.ext_a0) ? P.ext_a0 + static_cast<size_t>(pair * 2 + t) * P.a0_bytes
+                                                            : buf_addr(P.jobs_x[ji] & 0xff, pidx);
+                a_src += static_cast<size_t>(s0) * UM_A_STAGE_BYTES;
+                if (last) {   // this chunk's per-column epilogue constants -> shared memory (ring in the order the jobs COMPLETE)
                     w_empty += mbar_wait(bar_parempty(pb), (ph_parempty >> pb) & 1, P.error_flag, 104); ph_parempty ^= 1u << pb;
                     // operand layers: one float4 per column; output layers: {scale, shift} pairs, two columns per
                     // float4, in two variants (plain, then pre-multiplied by log2(10) for ten_to)
@@ -754,14 +801,15 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                         mbar_arrive_expect_tx(bar_parfull(pb), par_bytes);
                         bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), par_src, par_bytes, bar_parfull(pb));
                     }
+                    if (++pb == UM_PAR_SLOTS) pb = 0;
                 }
                 // this CTA's half of each weight stage ([hi | lo] of its nc/2 columns)
-                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack) + static_cast<size_t>(c) * L.k_stages * b_bytes
+                const uint8_t* b_src = reinterpret_cast<const uint8_t*>(L.wpack) + (static_cast<size_t>(c) * L.k_stages + s0) * b_bytes
                                      + cta_rank * (b_bytes / 2);
                 // an activation tile is dead after its last chunk has streamed it
                 const uint64_t pol_a = c == L.n_chunks - 1 ? pol_stream : pol_keep;
                 const uint32_t tx_bytes = UM_A_STAGE_BYTES + b_bytes / 2;
-                for (int s = 0; s < k_stages; ++s) {
+                for (int s = 0; s < ns; ++s) {
                     w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
                     if (PROF && P.counters && blockIdx.x == 0 && it == UM_JOB_TRACE_ITERATION && s < UM_TRACE_STAGES && lane == 0)
                         P.counters[(gridDim.x + UM_MAX_JOBS) * UM_CNT_SLOTS + (ji * UM_TRACE_STAGES + s) * 2] = now();
@@ -780,7 +828,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     jc[UM_JOB_LOAD_WAIT_AREADY] += w_aready - j_wa0; jc[UM_JOB_LOAD_WAIT_EMPTY] += w_empty - j_we0;
                     if (it == UM_JOB_TRACE_ITERATION) { jc[UM_JOB_T_LOAD0] = j_t0; jc[UM_JOB_T_LOAD1] = now(); }
                 }
-                ++job;
             })
             if (PROF && P.counters && lane == 0) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
@@ -795,10 +842,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             // the peer's operands live in its own shared memory: tell the leader when each stage has landed
             int stage = 0; uint32_t ph_full = 0;
             const uint32_t leader_full0 = map_to_cta(bar_full(0), 0);     // the leader's full barriers
-            UM_FOR_EACH_JOB({
-                (void)t;
-                const int ks = job_stages(P.g[g], c);
-                for (int i = 0; i < ks; ++i) {
+            UM_FOR_EACH_ENTRY({
+                for (int i = 0; i < ns; ++i) {
                     mbar_wait(bar_full(stage), ph_full, P.error_flag, 203);
                     if (elect_one()) mbar_arrive_remote_relaxed(leader_full0 + 8u * stage);
                     if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
@@ -807,25 +852,25 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         } else {
             long long w_full = 0, w_accempty = 0; const long long t_begin = now();
             int stage = 0; uint32_t ph_full = 0;
-            uint32_t ph_accempty = 3;                             // one phase bit per accumulator buffer
-            int job = 0;
+            uint32_t ph_accempty = (1u << UM_TMEM_SLOTS) - 1;     // one phase bit per TMEM slot
             // shared-memory descriptors of ring stage 0; a stage advances the 14-bit address field by its size >> 4
             const uint64_t a_hi0 = umma_desc_a(base + UM_SMEM_STAGES);
             const uint64_t a_lo0 = umma_desc_a(base + UM_SMEM_STAGES + UM_A_HALF_BYTES);
             const uint64_t b_hi0 = umma_desc(base + UM_SMEM_STAGES + UM_A_STAGE_BYTES);
-            UM_FOR_EACH_JOB({
+            UM_FOR_EACH_ENTRY({
                 const UmmaGemm& L = P.g[g];
-                const int k_stages = job_stages(L, c);
                 const uint32_t idesc = umma_idesc(L.nc);
                 const uint64_t b_lo_off = static_cast<uint64_t>((static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u) >> 4);   // (hi -> lo half tile) >> 4
-                const int buf = job & 1;
                 const long long j_t0 = now(), j_wf0 = w_full, j_wa0 = w_accempty;
-                // (a cluster-scope acquire would cost an L1 invalidate per wait on the issue path; the peer
-                // only hands back TMEM it has finished reading - tcgen05.wait::ld precedes its arrive)
-                w_accempty += mbar_wait(bar_accempty(buf), (ph_accempty >> buf) & 1, P.error_flag, 201); ph_accempty ^= 1u << buf;
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * UM_MAX_NC;
-                for (int s = 0; s < k_stages; ++s) {
+                if (first) {
+                    // (a cluster-scope acquire would cost an L1 invalidate per wait on the issue path; the peer
+                    // only hands back TMEM it has finished reading - tcgen05.wait::ld precedes its arrive)
+                    w_accempty += mbar_wait(bar_accempty(slot), (ph_accempty >> slot) & 1, P.error_flag, 201); ph_accempty ^= 1u << slot;
+                    if (two) { w_accempty += mbar_wait(bar_accempty(slot + 1), (ph_accempty >> (slot + 1)) & 1, P.error_flag, 201); ph_accempty ^= 1u << (slot + 1); }
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(slot) * UM_SLOT_COLS;
+                for (int s = 0; s < ns; ++s) {
                     w_full += mbar_wait(bar_full(stage), ph_full, P.error_flag, 202);
                     if (PROF && P.counters && blockIdx.x == 0 && it == UM_JOB_TRACE_ITERATION && s < UM_TRACE_STAGES && lane == 0)
                         P.counters[(gridDim.x + UM_MAX_JOBS) * UM_CNT_SLOTS + (ji * UM_TRACE_STAGES + s) * 2 + 1] = now();
@@ -837,7 +882,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                         for (int kk = 0; kk < UM_KS / 16; ++kk) {
                             const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
                             const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
-                            umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, (s | kk) != 0);
+                            umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, ((s0 + s) | kk) != 0);
                             umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
                             umma_f16_2cta(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                         }
@@ -845,8 +890,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     }
                     if (++stage == UM_STAGES) { stage = 0; ph_full ^= 1; }
                 }
-                if (elect_one()) {
-                    umma_commit_2cta(bar_accfull(buf));           // both CTAs' epilogues may drain their 128 rows
+                if (last && elect_one()) {
+                    umma_commit_2cta(bar_accfull(slot));          // both CTAs' epilogues may drain their 128 rows
                     if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
                 }
                 if (PROF && P.counters && blockIdx.x == 0 && lane == 0) {
@@ -856,7 +901,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     jc[UM_JOB_MMA_BUSY] += j_t1 - j_t0; jc[UM_CNT_SLOTS - 1] = jw;
                     if (it == UM_JOB_TRACE_ITERATION) { jc[UM_JOB_T_MMA0] = j_t0; jc[UM_JOB_T_MMA1] = j_t1; }
                 }
-                ++job;
             })
             if (PROF && P.counters && lane == 0) {
                 long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
@@ -874,7 +918,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             for (int t = 0; t < 2; ++t) {
                 w_in += mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
                 const long long row0 = (pair * 2 + t) * UM_TILE_M;
-                uint8_t* dst = a0_buf(t);
+                uint8_t* dst = cta_scratch + static_cast<size_t>(t) * P.a0_bytes;
                 for (int rr = 0; rr < UM_TILE_M / 32; ++rr) {
                     const int r = rr * 32 + lane;
                     const long long grow = row0 + r;
@@ -912,6 +956,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
     } else if (warp >= UM_EPI_WARP0) {
         // ===================== epilogue warps =====================
+        // They take the jobs in the order in which the table COMPLETES them (the entries flagged `last`).
         const int ew = warp - UM_EPI_WARP0;          // 0..7
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int cw = ew >> 2;                      // which of the lane quarter's warps: takes every (UM_EPI_WARPS/4)-th 32-column piece
@@ -920,27 +965,30 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         // 32-byte (16-byte) output stores need a 32-byte (16-byte) aligned base and a row pitch that is a multiple of 8 (4) floats
         const int vec_mode = ((reinterpret_cast<uintptr_t>(P.out) & 31) | (static_cast<uintptr_t>(P.out_pitch) & 7)) == 0 ? OUT_VEC32
                            : ((reinterpret_cast<uintptr_t>(P.out) & 15) | (static_cast<uintptr_t>(P.out_pitch) & 3)) == 0 ? OUT_VEC16 : OUT_SCALAR;
-        uint32_t ph_accfull[2] = {0, 0}, ph_parfull = 0;
+        uint32_t ph_accfull = 0, ph_parfull = 0;     // one phase bit per TMEM slot / constant slot
         long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = now();
-        int job = 0;
+        int pb = 0;
         EpiCtx E;
-        E.q = q; E.tq = tq; E.tr = tr; E.cw = cw;
+        E.q = q; E.tq = tq; E.tr = tr; E.cw = cw; E.lane = lane;
         E.dbg = PROF ? P.debug_flags : 0;
-        const uint32_t accempty_leader0 = map_to_cta(bar_accempty(0), 0);
-        UM_FOR_EACH_JOB({
+        E.leader = cta_rank == 0;
+        const uint32_t accempty0 = E.leader ? bar_accempty(0) : map_to_cta(bar_accempty(0), 0);     // the leader's MMA issuer owns the TMEM hand-back
+        UM_FOR_EACH_ENTRY({
+            if (!last) continue;
             const UmmaGemm& L = P.g[g];
             E.nc = L.nc;
+            // quadratic-form chunks hand both slots back at the end
+            E.rel_bar = (two && L.epi_kind != EPI_QUADFORM && !(PROF && (P.debug_flags & 3))) ? accempty0 + 8u * slot : 0u;
             const long long row0 = (pair * 2 + t) * UM_TILE_M;
-            const int buf = job & 1;
-            const int pb = job & (UM_PAR_SLOTS - 1);
             E.par = epipar + pb * UM_MAX_NC;                  // filled by the loader's bulk copy
             const long long j_w0 = w_accfull;
             w_accfull += mbar_wait(bar_parfull(pb), (ph_parfull >> pb) & 1, P.error_flag, 402); ph_parfull ^= 1u << pb;
-            w_accfull += mbar_wait(bar_accfull(buf), ph_accfull[buf], P.error_flag, 401); ph_accfull[buf] ^= 1;
+            w_accfull += mbar_wait(bar_accfull(slot), (ph_accfull >> slot) & 1, P.error_flag, 401); ph_accfull ^= 1u << slot;
             tc_fence_after();
             const long long t_job = now();
-            E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * UM_MAX_NC);
+            E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * UM_SLOT_COLS);
             E.chunk_col0 = c * L.nc;
+            uint8_t* const o_buf = buf_addr(P.jobs_x[ji] >> 8, pidx);
             if (PROF && (P.debug_flags & 3)) {
                 if (P.debug_flags & 2) {           // TMEM reads only
                     uint32_t va[16];
@@ -950,8 +998,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     }
                 }
             } else
-            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, out_buf(g, t, pidx), P.error_flag);
-            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, out_buf(g, t, pidx), P.error_flag);
+            if (L.epi_kind == EPI_ACT) epi_chunk_operand<EPI_ACT>(E, L.acc_scale, o_buf, P.error_flag);
+            else if (L.epi_kind == EPI_AFFINE) epi_chunk_operand<EPI_AFFINE>(E, 1.f, o_buf, P.error_flag);
             else if (L.epi_kind == EPI_QUADFORM)
                 epi_chunk_quadform(E, P.qf_d + (row0 + q * 32 + tq) * P.qf_pitch, P.qf_pitch, P.n_rows - row0, P.qf_cols,
                                    P.qf_partial + (row0 + q * 32 + tq) * (2 * L.n_chunks) + 2 * c + cw, 2 * L.n_chunks, lane);
@@ -967,30 +1015,36 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     else epi_chunk_output<false, false>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
                 }
             }
-            // accumulator drained (every lane has passed tcgen05.wait::ld): hand the TMEM buffer back to the MMA
-            // issuer first - the rest of this job's tail does not touch TMEM
+            // accumulator drained (every lane has passed tcgen05.wait::ld): hand the rest of its TMEM back to the MMA
+            // issuer first - the remainder of this job's tail does not touch TMEM
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (cta_rank == 0) mbar_arrive(bar_accempty(buf));          // the leader's MMA issuer owns the TMEM hand-back
-                else mbar_arrive_remote_relaxed(accempty_leader0 + 8u * buf);   // TMEM reads are complete (wait::ld)
+                if (E.leader) {
+                    if (!E.rel_bar) mbar_arrive(accempty0 + 8u * slot);
+                    if (two) mbar_arrive(accempty0 + 8u * (slot + 1));
+                } else {                                                          // TMEM reads are complete (wait::ld)
+                    if (!E.rel_bar) mbar_arrive_remote_relaxed(accempty0 + 8u * slot);
+                    if (two) mbar_arrive_remote_relaxed(accempty0 + 8u * (slot + 1));
+                }
                 mbar_arrive(bar_parempty(pb));
             }
+            if (++pb == UM_PAR_SLOTS) pb = 0;
             if (L.epi_kind <= EPI_AFFINE && c == L.n_chunks - 1) {     // operand-producing kinds
                 // the next layer's loader may only read the scratch once every chunk of this layer is
                 // written: one fence per thread before the last chunk's arrive covers all its stores
                 UM_SCRATCH_FENCE(); fence_proxy_async_global();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_aready(t));
+                if (lane == 0) mbar_arrive(bar_aready(ts));
             }
             if (UM_DISCARD_DEAD_TILES && P.discard_ok && g >= 1 && c == L.n_chunks - 1) {
                 // This was the last chunk to stream the tile's operand: every copy of it has landed and been consumed
                 // (its MMAs are complete), so its L2 lines are dead - drop them instead of letting them be written
-                // back to HBM on eviction.  The slot is rewritten by the very next step, possibly while slower warps
+                // back to HBM on eviction.  The buffer is rewritten soon, possibly while slower warps
                 // are still in this job, so a warp only drops the lines it will itself rewrite (program order then
                 // keeps discard before store): with chunk widths that are multiples of 64 (discard_ok) warp (q, cw)
                 // writes exactly the rows of lane quarter q in the K stages of parity cw - 32 lines per stage.
-                const uint8_t* dead = in_buf(g, t, pidx) + (lane >> 4) * UM_A_HALF_BYTES + q * 2048 + (lane & 15) * 128;
+                const uint8_t* dead = buf_addr(P.jobs_x[ji] & 0xff, pidx) + (lane >> 4) * UM_A_HALF_BYTES + q * 2048 + (lane & 15) * 128;
                 for (int sd = cw; sd < L.k_stages; sd += UM_EPI_WARPS / 4) l2_discard_line(dead + static_cast<size_t>(sd) * UM_A_STAGE_BYTES);
             }
             if (L.epi_kind >= EPI_OUT) c_out += now() - t_job; else c_act += now() - t_job;
@@ -1000,7 +1054,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 jc[UM_JOB_EPI_WAIT] += w_accfull - j_w0; jc[UM_JOB_EPI_BUSY] += j_t1 - t_job;
                 if (it == UM_JOB_TRACE_ITERATION) { jc[UM_JOB_T_EPI0] = t_job; jc[UM_JOB_T_EPI1] = j_t1; }
             }
-            ++job;
         })
         if (PROF && P.counters && ew == 0 && lane == 0) {
             long long* cnt = P.counters + blockIdx.x * UM_CNT_SLOTS;
@@ -1008,7 +1061,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             cnt[UM_CNT_EPI_TOTAL] = now() - t_begin;
         }
     }
-#undef UM_FOR_EACH_JOB
+#undef UM_FOR_EACH_ENTRY
 
     tc_fence_before();
     __syncthreads();

@@ -180,6 +180,14 @@ int cpb200_engine_status(cpb200_engine* e, int32_t* watchdog_code, int32_t* rang
  * Returns the number of int64 values available, or a negative error. */
 int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int32_t capacity);
 
+/* Debug, needs no device: the fused kernel's job table (the static schedule of one tile pair, see csrc/cpb200_api.cu
+ * build_jobs) for a network given by its contractions' logical K, N and epilogue kinds (0 activation, 1 affine, 2 output,
+ * 3 quadratic form).  Writes up to `capacity` encoded entries (csrc/umma_kernel.cuh um_job_w0 / um_job_w1) and, in `info`
+ * (3 + 3 * n_gemms ints): schedule, rot_mul, parity-buffer stages, then k_stages / chunk width / chunks per contraction.
+ * Returns the number of entries or a negative error.  Used by tests/test_job_table.py and tools/schedule_sim.py. */
+int cpb200_debug_job_table(int32_t n_gemms, const int32_t* k, const int32_t* n, const int32_t* epi_kind, int32_t tri,
+                           uint32_t* w0, uint32_t* w1, int32_t capacity, int32_t* info);
+
 /* -------------------------------------------------------------------------------------------------
  * Planck 2018 plik-lite likelihood tail behind the TT / TE / EE emulators.
  *
