@@ -287,17 +287,19 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
 // for chunks wider than 128) drained by one epilogue.  The MMA issuer and the loader walk the table's entries in order;
 // an entry is a PART of a job (K stages [s0, s0 + ns)), so a short job can be issued between two parts of a long one.
 // The epilogue warps take the jobs in the order of their last parts.  Why: with two full-width accumulators a job whose
-// MMA is short (layer 0: K = 32; cmb_PP's output chunks: K = 64) makes the next job wait for the previous epilogue -
-// issued in the middle of a long job, into a slot the previous long job's epilogue has already handed back, it costs
-// the tensor pipe nothing.
+// MMA is short (layer 0: K = 32; cmb_PP's output chunks: K = 64) makes the job after it wait for the previous epilogue.
+// Issued in the MIDDLE of a long job - as soon as the other accumulator has been drained - its own epilogue starts
+// that much earlier and the job after the host finds its accumulator free.
 //
-// Two schedules (plan_schedule):
-//  SCHED_MERGE_L0   cur = contractions 1 .. G-1 of pair it-1, next = layer 0 of pair it as 128-column jobs, each placed in
-//                   the middle of an output-phase job of the same tile (big-K output phase: cmb_TT/EE/TE, P(k)).
-//  SCHED_OVERLAP    the last contraction has a short K (cmb_PP: 64): its chunks (128 columns) are store-bound, almost
-//                   MMA-free.  cur = the output chunks of pair it-1, next = the WHOLE trunk of pair it; two output jobs
-//                   are issued inside every two-slot trunk job, the rest around the single-slot trunk jobs.  The output
-//                   phase's operand (written by pair p's trunk, read during pair p+1's) lives in per-parity buffers.
+// Schedules (plan_schedule):
+//  SCHED_SIMPLE     round 1's order: whole jobs; cur = contractions 1 .. G-1 of pair it-1, next = layer 0 of pair it, spread
+//                   over the output phase.
+//  SCHED_MERGE_L0   same split, but each layer-0 job is issued inside an output-phase job of its tile (big-K output phase:
+//                   cmb_TT/EE/TE, P(k)).
+//  SCHED_OVERLAP    the last contraction has a short K (cmb_PP: 64): its chunks are store-bound, almost MMA-free.
+//                   cur = the output chunks of pair it-1, next = the WHOLE trunk of pair it; one output job is issued inside
+//                   every two-slot trunk job, the rest surround the layer-0 and coefficient jobs.  The output phase's
+//                   operand (written by pair p's trunk, read during pair p+1's) lives in per-parity buffers.
 // ---------------------------------------------------------------------------------------------
 enum { SCHED_SIMPLE = 0, SCHED_MERGE_L0 = 1, SCHED_OVERLAP = 2 };
 
@@ -315,21 +317,28 @@ int plan_schedule(std::vector<Gemm>& gemms, int k_pad0) {
 #else
     const char* force = nullptr;
 #endif
-    if (G >= 2 && gemms[0].epi != cpb::EPI_QUADFORM) {
-        sched = SCHED_MERGE_L0;
-        const int k_last = G >= 2 ? round_up(gemms[G - 2].N, 32) : k_pad0;        // (a lower bound of) the last contraction's padded K
-        if (G >= 3 && k_last <= 128 && gemms[G - 1].epi == cpb::EPI_OUT) sched = SCHED_OVERLAP;
-    }
+    (void)k_pad0;
+    // Measured on B200 (profiles/r2c_schedule_ab.txt, SM cycles of a 1 048 576-row launch, SIMPLE / MERGE_L0 / OVERLAP):
+    // cmb_TT 11.81 / 11.66 / -, cmb_TE 13.27 / 13.06 / -, PKLIN 4.885 / 4.817 / -, cmb_PP 9.12 / 9.06 / 9.03-9.11 M.
+    // MERGE_L0 is the default wherever there is an output phase to host layer 0; OVERLAP buys cmb_PP nothing measurable
+    // (the job after a hosted output job still waits for that job's epilogue: two accumulators) and stays a
+    // profiling-build option.
+    if (G >= 2 && gemms[0].epi != cpb::EPI_QUADFORM) sched = SCHED_MERGE_L0;
     if (force) {
         if (!strcmp(force, "simple")) sched = SCHED_SIMPLE;
         else if (!strcmp(force, "merge") && G >= 2) sched = SCHED_MERGE_L0;
         else if (!strcmp(force, "overlap") && G >= 3) sched = SCHED_OVERLAP;
     }
     for (Gemm& g : gemms) g.max_nc = cpb::UM_MAX_NC;
-    if (sched != SCHED_SIMPLE) gemms[0].max_nc = cpb::UM_SLOT_COLS;
-    if (sched == SCHED_OVERLAP) gemms[G - 1].max_nc = cpb::UM_SLOT_COLS;
     return sched;
 }
+
+// measured costs (SM cycles) the placement of inserted jobs is derived from
+double est_epilogue_cycles(const Gemm& L) {
+    const double per256 = L.epi == cpb::EPI_ACT ? 8500.0 : L.epi == cpb::EPI_AFFINE ? 3000.0 : 5300.0;
+    return 1000.0 + per256 * L.nc / 256.0;
+}
+double est_stage_cycles(const Gemm& L) { return 6.0 * std::max(L.nc / 2.0, 32.0); }       // 6 MMAs of nc/2 cycles; A-operand read floor below N = 64
 
 // cut a job (entry with all its stages) into parts at the given stage indices
 std::vector<JobEntry> split_job(const JobEntry& e, const std::vector<int>& cuts) {
@@ -347,25 +356,37 @@ std::vector<JobEntry> split_job(const JobEntry& e, const std::vector<int>& cuts)
     return parts;
 }
 
+// `host` with `guest` issued inside it: after the K stage at which the epilogue of `prev` (the job before the host, whose
+// accumulator the guest takes over) has finished.  When that is beyond the host's last stage the guest simply follows.
+void push_hosted(std::vector<JobEntry>& out, const std::vector<Gemm>& gemms, const JobEntry& host, const JobEntry& guest,
+                 const JobEntry* prev) {
+    const double wait = prev ? est_epilogue_cycles(gemms[prev->g]) : 0.0;
+    const int cut = static_cast<int>(wait / est_stage_cycles(gemms[host.g])) + 1;
+    if (cut >= host.ns) { out.push_back(host); out.push_back(guest); return; }
+    std::vector<JobEntry> parts = split_job(host, {cut});
+    out.push_back(parts[0]);
+    out.push_back(guest);
+    out.push_back(parts[1]);
+}
+
 // TMEM slots for every job of an ordered entry list.  A job owns its slot(s) from its first part to the end of its
 // epilogue; the kernel's barriers make ANY static assignment correct as long as a job never waits for a slot whose
 // owner has not been issued completely (deadlock), i.e. the previous owner's last part must precede the new job's first
 // part.  Among the candidates the allocator takes the slot whose previous owner completes earliest in the epilogue order
-// (ties: the lower slot, which a two-slot job's epilogue hands back first).
+// (ties: the lower slot).
 int assign_slots(std::vector<JobEntry>& entries) {
     const int n = static_cast<int>(entries.size());
-    int owner_last[cpb::UM_TMEM_SLOTS];          // table position of the last part of the slot's current owner (-1 = never used)
+    int owner_last[cpb::UM_TMEM_SLOTS];          // table position of the last part of the slot's current owner
     bool open[cpb::UM_TMEM_SLOTS];               // the owner's last part has not been seen yet
     // the table repeats every iteration: run the allocator twice and keep the second pass (steady state), with the
-    // ownership at the end of pass one as the initial condition
+    // ownership at the end of pass one (positions shifted by -n) as the initial condition
     std::vector<int> job_slot;
-    for (int sl = 0; sl < cpb::UM_TMEM_SLOTS; ++sl) { owner_last[sl] = -1 - (cpb::UM_TMEM_SLOTS - sl); open[sl] = false; }
+    for (int sl = 0; sl < cpb::UM_TMEM_SLOTS; ++sl) { owner_last[sl] = -2 * n - (cpb::UM_TMEM_SLOTS - sl); open[sl] = false; }
     for (int pass = 0; pass < 2; ++pass) {
         job_slot.assign(n, -1);
         for (int i = 0; i < n; ++i) {
             JobEntry& e = entries[i];
             if (e.first) {
-                // position of this job's last part
                 int last_pos = i;
                 while (!(entries[last_pos].last && entries[last_pos].job == e.job)) ++last_pos;
                 int best = -1, best_key = 0;
@@ -389,7 +410,6 @@ int assign_slots(std::vector<JobEntry>& entries) {
             if (e.slot < 0) return fail(CPB200_E_UNSUPPORTED, "job table: part before its job's first part at entry %d", i);
             if (e.last) for (int k = 0; k <= e.two; ++k) open[e.slot + k] = false;
         }
-        for (int sl = 0; sl < cpb::UM_TMEM_SLOTS; ++sl) if (pass == 0) owner_last[sl] -= 0;   // positions of pass one are already shifted by -n
     }
     return 0;
 }
@@ -426,31 +446,35 @@ int build_jobs(const std::vector<Gemm>& gemms, int sched, std::vector<JobEntry>&
             }
     if (sched == SCHED_OVERLAP) {
         *par_stages = gemms[G - 1].k_stages;
-        size_t oi = 0;
-        size_t n_two = 0;
-        for (const JobEntry& e : head) n_two += e.two;
-        const size_t n_small = head.size() - n_two;
-        const size_t per_two = 2;
-        size_t in_two = std::min(tail.size(), per_two * n_two);
-        size_t rest = tail.size() - in_two;
-        const size_t rest_per_small = n_small ? (rest + n_small - 1) / n_small : 0;
-        for (const JobEntry& e : head) {
-            if (!e.two) {
-                out.push_back(e);
-                for (size_t k = 0; k < rest_per_small && rest > 0 && oi < tail.size(); ++k, --rest) out.push_back(tail[oi++]);
+        // hosts: the trunk jobs with a long MMA (at least 8 stages); every host takes one output job of the previous pair
+        size_t n_host = 0;
+        for (const JobEntry& e : head) n_host += e.ns >= 8;
+        const size_t hosted = std::min(tail.size(), n_host);
+        // what is left surrounds the other trunk jobs: two thirds before the first host (the layer-0 jobs: long epilogues,
+        // no MMA to speak of), one third after the last (the dependent coefficient jobs)
+        const size_t rest = tail.size() - hosted;
+        size_t n_pre = 0, n_post = 0;
+        { bool seen_host = false; for (const JobEntry& e : head) { if (e.ns >= 8) seen_host = true; else (seen_host ? n_post : n_pre)++; } }
+        size_t rest_post = n_post ? std::min(rest, std::max<size_t>(rest / 3, n_post)) : 0, rest_pre = n_pre ? rest - rest_post : 0;
+        if (!n_pre) rest_post = n_post ? rest : 0;
+        size_t oi = 0, pre_seen = 0, post_seen = 0, pre_used = 0, post_used = 0;
+        const JobEntry* prev = nullptr;
+        std::vector<JobEntry> pending;
+        for (size_t i = 0; i < head.size(); ++i) {
+            const JobEntry& e = head[i];
+            if (e.ns >= 8 && oi < tail.size() && hosted > 0 && (oi - pre_used - post_used) < hosted) {
+                push_hosted(out, gemms, e, tail[oi++], prev);
+                prev = &head[i];
                 continue;
             }
-            const size_t k = std::min(per_two, std::min(in_two, tail.size() - oi));
-            if (k == 0) { out.push_back(e); continue; }
-            // the slots of the previous two-slot job come back after half and after the whole of its epilogue (8.5 k
-            // cycles for a 128 x 256 activation chunk against 0.77 k per K stage): cut after 6/16 and 12/16 of the stages
-            std::vector<int> cuts;
-            for (size_t j = 0; j < k; ++j) cuts.push_back(static_cast<int>((e.ns * (k == 2 ? (j == 0 ? 6 : 12) : 8) + 8) / 16));
-            std::vector<JobEntry> parts = split_job(e, cuts);
-            for (size_t j = 0; j < parts.size(); ++j) {
-                out.push_back(parts[j]);
-                if (j < k && j + 1 < parts.size()) { out.push_back(tail[oi++]); --in_two; }
-            }
+            out.push_back(e);
+            prev = &head[i];
+            if (e.ns >= 8) continue;
+            const bool is_pre = post_seen == 0 && pre_seen < n_pre;
+            size_t want;
+            if (is_pre) { ++pre_seen; want = rest_pre * pre_seen / n_pre - pre_used; }
+            else { ++post_seen; want = rest_post * post_seen / std::max<size_t>(1, n_post) - post_used; }
+            for (size_t k = 0; k < want && oi < tail.size(); ++k) { prev = &tail[oi]; out.push_back(tail[oi++]); (is_pre ? pre_used : post_used)++; }
         }
         while (oi < tail.size()) out.push_back(tail[oi++]);
     } else if (sched == SCHED_MERGE_L0) {
@@ -458,29 +482,22 @@ int build_jobs(const std::vector<Gemm>& gemms, int sched, std::vector<JobEntry>&
         out = head;
         // layer-0 jobs of tile t go into the output jobs of tile t (tile 1's must follow tile 0's last output chunk: the
         // buffer they write is tile 0's output operand)
+        const JobEntry* prev = head.empty() ? nullptr : &head.back();
+        std::vector<JobEntry> outs[2], l0s[2];
+        for (const JobEntry& e : tail) outs[e.t].push_back(e);
+        for (const JobEntry& e : l0) l0s[e.t].push_back(e);
         for (int t = 0; t < 2; ++t) {
-            std::vector<JobEntry> outs, l0s;
-            for (const JobEntry& e : tail) if (e.t == t) outs.push_back(e);
-            for (const JobEntry& e : l0) if (e.t == t) l0s.push_back(e);
-            const size_t n_o = outs.size(), n_l = l0s.size();
+            const size_t n_o = outs[t].size(), n_l = l0s[t].size();
             std::vector<std::vector<JobEntry>> where(n_o);
-            for (size_t k = 0; k < n_l; ++k) where[std::min(n_o - 1, static_cast<size_t>((k + 0.5) * n_o / n_l))].push_back(l0s[k]);
+            // spread over the tile's output jobs, leaving out the first one when there is room (it follows a long epilogue)
+            const size_t lo = (n_o > n_l) ? 1 : 0;
+            for (size_t k = 0; k < n_l; ++k) where[std::min(n_o - 1, lo + static_cast<size_t>((k + 0.5) * (n_o - lo) / n_l))].push_back(l0s[t][k]);
             for (size_t i = 0; i < n_o; ++i) {
-                const std::vector<JobEntry>& ins = where[i];
-                if (ins.empty() || outs[i].ns < 2) {
-                    out.push_back(outs[i]);
-                    for (const JobEntry& e : ins) out.push_back(e);
-                    continue;
-                }
-                std::vector<int> cuts;
-                for (size_t j = 0; j < ins.size(); ++j) cuts.push_back(static_cast<int>((j + 1) * outs[i].ns / (ins.size() + 1)));
-                std::vector<JobEntry> parts = split_job(outs[i], cuts);
-                size_t used = 0;
-                for (size_t j = 0; j < parts.size(); ++j) {
-                    out.push_back(parts[j]);
-                    if (j + 1 < parts.size() && used < ins.size()) out.push_back(ins[used++]);
-                }
-                while (used < ins.size()) out.push_back(ins[used++]);
+                const JobEntry& host = outs[t][i];
+                if (where[i].empty()) { out.push_back(host); prev = &outs[t][i]; continue; }
+                push_hosted(out, gemms, host, where[i][0], prev);
+                for (size_t k = 1; k < where[i].size(); ++k) out.push_back(where[i][k]);
+                prev = &outs[t][i];
             }
         }
     } else {

@@ -70,7 +70,10 @@ constexpr float UM_ACT_SCALE = 64.f;                         // power-of-two pre
 
 // shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int UM_SMEM_STAGES = 0;
-constexpr int UM_PAR_SLOTS = 6;          // ring of per-chunk epilogue constants: deep enough that the loader never waits for an epilogue
+#ifndef UM_PAR_SLOTS_N
+#define UM_PAR_SLOTS_N 6
+#endif
+constexpr int UM_PAR_SLOTS = UM_PAR_SLOTS_N;          // ring of per-chunk epilogue constants: deep enough that the loader never waits for an epilogue
 constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // UM_PAR_SLOTS x 256 float4
 constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + UM_PAR_SLOTS * UM_MAX_NC * 16;
 constexpr int UM_NUM_BARS = 2 * UM_STAGES + 2 * UM_TMEM_SLOTS + 4 + 2 + 2 + 2 * UM_PAR_SLOTS;
@@ -355,6 +358,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi));
     lo = pack_f16x2_sat(a - hf.x, b - hf.y);
 }
+#ifndef UM_EARLY_RELEASE
+#define UM_EARLY_RELEASE 0    // 1: a two-slot accumulator's first slot is handed back as soon as its columns are drained (measured
+                              // on B200: the mid-job fence costs cmb_PP 3.5 % and no schedule in use needs the half accumulator)
+#endif
 #ifndef UM_RANGE_CHECK
 #define UM_RANGE_CHECK 1      // producers of split operands report values beyond the fp16 range (0: saturate silently)
 #endif
@@ -459,8 +466,8 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
     uint32_t va[16], vb[16];
     if (pc < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);            // TMEM reads run one half piece ahead of the math
 #pragma unroll 1
-    for (int leg = 0; leg < 2; ++leg) {
-    const int leg_end = (leg == 0 && E.rel_bar) ? min(E.nc, UM_SLOT_COLS) : E.nc;
+    for (int leg = 0; leg < (UM_EARLY_RELEASE ? 2 : 1); ++leg) {
+    const int leg_end = (UM_EARLY_RELEASE && leg == 0 && E.rel_bar) ? min(E.nc, UM_SLOT_COLS) : E.nc;
     for (; pc < leg_end; pc += kStep) {
         // the constants of a 32-column block are stored lane-interleaved (value j of lane group tr at 4j + tr):
         // the four lane groups read 64 contiguous bytes - no shared-memory bank conflicts
@@ -477,7 +484,7 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
         if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
         epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep, E.dbg, status);          // rows +16
     }
-    if (leg == 0 && E.rel_bar) epi_release_first_slot(E);
+    if (UM_EARLY_RELEASE && leg == 0 && E.rel_bar) epi_release_first_slot(E);
     }
 }
 
@@ -588,8 +595,8 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     uint32_t va[16], vb[16];
     if (pc < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);        // TMEM reads run one half piece ahead of the math
 #pragma unroll 1
-    for (int leg = 0; leg < 2; ++leg) {
-    const int leg_end = (leg == 0 && E.rel_bar) ? min(nc_valid, UM_SLOT_COLS) : nc_valid;
+    for (int leg = 0; leg < (UM_EARLY_RELEASE ? 2 : 1); ++leg) {
+    const int leg_end = (UM_EARLY_RELEASE && leg == 0 && E.rel_bar) ? min(nc_valid, UM_SLOT_COLS) : nc_valid;
     for (; pc < leg_end; pc += kStep) {
         float2 pp[8];
 #pragma unroll
@@ -617,7 +624,7 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
         if (pc + kStep < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
         epi_output_half<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, pitch, mode, E.q * 32 + E.tq + 16, rows_left, gc, n_modes, E.dbg);
     }
-    if (leg == 0 && E.rel_bar) epi_release_first_slot(E);
+    if (UM_EARLY_RELEASE && leg == 0 && E.rel_bar) epi_release_first_slot(E);
     }
 }
 
@@ -738,19 +745,20 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     // writes buffer 2n + 1 (mod 3), plus a per-pair offset (rot_mul) that lets the next pair's layer 0, which runs inside
     // this pair's output phase, land in the buffer that is free then.  3 x 256 KB per CTA keeps the scratch at 111 MB.
     // Parity buffers hold the operand of an overlapped output phase: written by pair p's trunk, read during pair p+1's.
-    auto buf_addr = [&](uint32_t code, long long pidx) -> uint8_t* {
-        if (code & UM_BUF_ROT)
-            return cta_scratch + 2ull * P.a0_bytes + static_cast<size_t>(((code & 0xf) + pidx * P.rot_mul) % UM_ACT_BUFS) * P.abuf_bytes;
-        if (code & UM_BUF_PAR)
-            return cta_scratch + 2ull * P.a0_bytes + static_cast<size_t>(UM_ACT_BUFS) * P.abuf_bytes
-                   + static_cast<size_t>(2 * (pidx & 1) + (code & 1)) * P.pbuf_bytes;
-        return cta_scratch + static_cast<size_t>(code & 1) * P.a0_bytes;
+    // (pm3 = pair number mod 3, ppar = its parity: kept as small ints so that no 64-bit division sits on any role's path)
+    auto buf_addr = [&](uint32_t code, int pm3, int ppar) -> uint8_t* {
+        uint32_t off;
+        if (code & UM_BUF_ROT) off = 2u * P.a0_bytes + (((code & 0xf) + pm3 * P.rot_mul) % UM_ACT_BUFS) * P.abuf_bytes;
+        else if (code & UM_BUF_PAR) off = 2u * P.a0_bytes + UM_ACT_BUFS * P.abuf_bytes + (2 * ppar + (code & 1)) * P.pbuf_bytes;
+        else off = (code & 1) * P.a0_bytes;
+        return cta_scratch + off;
     };
 
 // every role walks the same entry sequence
 #define UM_FOR_EACH_ENTRY(...)                                                                         \
     for (long long it = 0; it <= n_my_pg; ++it) {                                                      \
         const bool has_cur = it >= 1, has_next = it < n_my_pg;                                         \
+        const int it_m3 = static_cast<int>(it % 3), it_par = static_cast<int>(it & 1);                 \
         for (int ji = 0; ji < n_jobs; ++ji) {                                                          \
             const uint32_t jw = P.jobs[ji];                                                            \
             const int g = jw & 15, t = (jw >> 4) & 1, c = (jw >> 5) & 127;                             \
@@ -763,8 +771,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             /* rows beyond n_rows are padding (computed, never stored) */                              \
             const long long pidx = is_next ? it : it - 1;      /* this cluster's running pair number */  \
             const long long pair = (pg_first + pidx * pg_step) * UM_CLUSTER + cta_rank;                \
-            const int ts = 2 * static_cast<int>(pidx & 1) + t;                                         \
-            (void)pair; (void)c; (void)pidx; (void)s0; (void)ns; (void)first; (void)last; (void)slot; (void)two; (void)ts; \
+            const int ppar = is_next ? it_par : it_par ^ 1;            /* parity and residue mod 3 of the pair number */ \
+            const int pm3 = is_next ? it_m3 : (it_m3 + 2) % 3;                                         \
+            const int ts = 2 * ppar + t;                                                               \
+            (void)pair; (void)c; (void)pidx; (void)s0; (void)ns; (void)first; (void)last; (void)slot; (void)two; (void)ts; (void)pm3; \
             __VA_ARGS__                                                                                \
         }                                                                                              \
     }
@@ -788,7 +798,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     else { w_aready += mbar_wait(bar_aready(ts), (ph_aready >> ts) & 1, P.error_flag, 102); ph_aready ^= 1u << ts; }
                 }
                 const uint8_t* a_src = (g == 0 && P.ext_a0) ? P.ext_a0 + static_cast<size_t>(pair * 2 + t) * P.a0_bytes
-                                                            : buf_addr(P.jobs_x[ji] & 0xff, pidx);
+                                                            : buf_addr(P.jobs_x[ji] & 0xff, pm3, ppar);
                 a_src += static_cast<size_t>(s0) * UM_A_STAGE_BYTES;
                 if (last) {   // this chunk's per-column epilogue constants -> shared memory (ring in the order the jobs COMPLETE)
                     w_empty += mbar_wait(bar_parempty(pb), (ph_parempty >> pb) & 1, P.error_flag, 104); ph_parempty ^= 1u << pb;
@@ -978,7 +988,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const UmmaGemm& L = P.g[g];
             E.nc = L.nc;
             // quadratic-form chunks hand both slots back at the end
-            E.rel_bar = (two && L.epi_kind != EPI_QUADFORM && !(PROF && (P.debug_flags & 3))) ? accempty0 + 8u * slot : 0u;
+            E.rel_bar = (UM_EARLY_RELEASE && two && L.epi_kind != EPI_QUADFORM && !(PROF && (P.debug_flags & 3))) ? accempty0 + 8u * slot : 0u;
             const long long row0 = (pair * 2 + t) * UM_TILE_M;
             E.par = epipar + pb * UM_MAX_NC;                  // filled by the loader's bulk copy
             const long long j_w0 = w_accfull;
@@ -988,7 +998,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const long long t_job = now();
             E.t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * UM_SLOT_COLS);
             E.chunk_col0 = c * L.nc;
-            uint8_t* const o_buf = buf_addr(P.jobs_x[ji] >> 8, pidx);
+            uint8_t* const o_buf = buf_addr(P.jobs_x[ji] >> 8, pm3, ppar);
             if (PROF && (P.debug_flags & 3)) {
                 if (P.debug_flags & 2) {           // TMEM reads only
                     uint32_t va[16];
@@ -1044,7 +1054,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 // are still in this job, so a warp only drops the lines it will itself rewrite (program order then
                 // keeps discard before store): with chunk widths that are multiples of 64 (discard_ok) warp (q, cw)
                 // writes exactly the rows of lane quarter q in the K stages of parity cw - 32 lines per stage.
-                const uint8_t* dead = buf_addr(P.jobs_x[ji] & 0xff, pidx) + (lane >> 4) * UM_A_HALF_BYTES + q * 2048 + (lane & 15) * 128;
+                const uint8_t* dead = buf_addr(P.jobs_x[ji] & 0xff, pm3, ppar) + (lane >> 4) * UM_A_HALF_BYTES + q * 2048 + (lane & 15) * 128;
                 for (int sd = cw; sd < L.k_stages; sd += UM_EPI_WARPS / 4) l2_discard_line(dead + static_cast<size_t>(sd) * UM_A_STAGE_BYTES);
             }
             if (L.epi_kind >= EPI_OUT) c_out += now() - t_job; else c_act += now() - t_job;

@@ -147,5 +147,5 @@ def test_job_table_invariants(built_library, name):
 def test_schedules_chosen_for_the_shipped_models(built_library):
     sched = {name: _engine.job_table(*NETWORKS[name])[1]["schedule"] for name in NETWORKS}
     assert sched["cmb_TT_NN"] == 1 and sched["PKLIN_NN"] == 1 and sched["cmb_TE_PCAplusNN"] == 1      # layer 0 merged into the output jobs
-    assert sched["cmb_PP_PCAplusNN"] == 2                                                                 # overlapped output phase
+    assert sched["cmb_PP_PCAplusNN"] == 1                  # (the overlapped output phase measured no faster: profiling builds only)
     assert sched["single"] == 0

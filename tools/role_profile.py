@@ -11,6 +11,8 @@ import torch  # noqa: E402
 import cosmopower_b200 as cp  # noqa: E402
 from cosmopower_b200 import priors, standins  # noqa: E402
 
+NJ = 320          # UM_MAX_JOBS
+
 NAMES = ["load_wait_empty", "load_wait_aready", "load_total", "mma_wait_full", "mma_wait_accempty", "mma_total",
          "epi_wait_accfull", "epi_act", "epi_out", "epi_total", "in_wait", "in_total"]
 
@@ -37,10 +39,10 @@ def main():
     ms = e0.elapsed_time(e1)
     print("%s rows=%d: %.3f ms, %.3g spectra/s" % (name, rows, ms, rows / ms * 1e3))
     flat = c.reshape(-1)
-    ntrace = 96 * 16 * 2
-    trace = flat[flat.size - ntrace:].reshape(96, 16, 2)     # [job][stage][loader issue, MMA saw it landed]
+    ntrace = NJ * 16 * 2
+    trace = flat[flat.size - ntrace:].reshape(NJ, 16, 2)     # [job][stage][loader issue, MMA saw it landed]
     c = flat[:flat.size - ntrace].reshape(-1, 16)
-    ncta = c.shape[0] - 96                     # per-CTA rows, then 96 per-job rows written by CTA 0
+    ncta = c.shape[0] - NJ                     # per-CTA rows, then NJ per-entry rows written by CTA 0
     jobs = c[ncta:]
     c = c[:ncta]
     tot = c[:, 5].max()
@@ -51,16 +53,18 @@ def main():
     for i, n in enumerate(NAMES):
         print("  %-18s mean %12.0f  (%5.1f%% of mma_total)  min %12.0f max %12.0f" % (n, c[:, i].mean(), 100 * c[:, i].mean() / tot, c[:, i].min(), c[:, i].max()))
     print("per job-table entry of CTA 0 (cycles summed over its iterations; time stamps of iteration 3 relative to the first):")
-    print("  ji  g t  c nxt | mma: wait_full wait_accempty     busy | epi:     wait     busy | load: wait_aready wait_empty | t_mma0  t_mma1  t_epi0  t_epi1 t_load0 t_load1")
+    print("  ji  g t  c nxt s0 ns FL slot | mma: wait_full wait_accempty     busy | epi:     wait     busy | load: wait_aready wait_empty | t_mma0  t_mma1  t_epi0  t_epi1 t_load0 t_load1")
     t0 = min(x for x in jobs[:, 8] if x > 0) if (jobs[:, 8] > 0).any() else 0
-    for ji in range(96):
+    for ji in range(NJ):
         r = jobs[ji]
         if r[2] == 0:
             continue
         jw = int(r[15])
         ts = ["%7d" % (x - t0) if x > 0 else "      -" for x in r[8:14]]
-        print("  %2d %2d %d %2d  %d  | %14.0f %13.0f %8.0f | %13.0f %8.0f | %17.0f %10.0f | %s" % (
-            ji, jw & 255, (jw >> 8) & 255, (jw >> 16) & 255, jw >> 24, r[0], r[1], r[2], r[3], r[4], r[5], r[6], " ".join(ts)))
+        print("  %3d %2d %d %2d  %d  %2d %2d %s%s %d%s | %14.0f %13.0f %8.0f | %13.0f %8.0f | %17.0f %10.0f | %s" % (
+            ji, jw & 15, (jw >> 4) & 1, (jw >> 5) & 127, (jw >> 12) & 1, (jw >> 13) & 63, (jw >> 19) & 63,
+            "F" if (jw >> 25) & 1 else "-", "L" if (jw >> 26) & 1 else "-", (jw >> 27) & 3, "+" if (jw >> 29) & 1 else " ",
+            r[0], r[1], r[2], r[3], r[4], r[5], r[6], " ".join(ts)))
     print_trace(trace, jobs, t0)
 
 
@@ -68,7 +72,7 @@ def main():
 
 def print_trace(trace, jobs, t0):
     print("stage trace of the traced iteration (cycles relative to its first MMA job): per job, loader issue times then MMA landed times")
-    for ji in range(96):
+    for ji in range(NJ):
         if jobs[ji][2] == 0 or trace[ji, 0, 1] == 0:
             continue
         ld = " ".join("%6d" % (x - t0) if x > 0 else "     -" for x in trace[ji, :, 0])
