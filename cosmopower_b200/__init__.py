@@ -5,7 +5,8 @@ Drop-in for `cosmopower.cosmopower_NN` / `cosmopower.cosmopower_PCAplusNN` on th
 from .cosmopower_NN import cosmopower_NN
 from .cosmopower_PCAplusNN import cosmopower_PCAplusNN
 from . import priors
-from .fused import ten_to_sum_predictions_np, ten_to_sum_predictions_tf
+from .fused import predictions_multi_tf, ten_to_sum_predictions_np, ten_to_sum_predictions_tf
 
-__all__ = ["cosmopower_NN", "cosmopower_PCAplusNN", "priors", "ten_to_sum_predictions_np", "ten_to_sum_predictions_tf"]
+__all__ = ["cosmopower_NN", "cosmopower_PCAplusNN", "priors", "predictions_multi_tf", "ten_to_sum_predictions_np",
+           "ten_to_sum_predictions_tf"]
 __version__ = "0.1.0"

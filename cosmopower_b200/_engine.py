@@ -65,8 +65,14 @@ SYMBOLS = [
     ("cpb200_engine_debug_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
     ("cpb200_debug_job_table", ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
-                                              ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.POINTER(ctypes.c_uint32),
-                                              ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+                                              ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32,
+                                              ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32,
+                                              ctypes.POINTER(ctypes.c_int32)]),
+    ("cpb200_create_multi", ctypes.c_int, [ctypes.POINTER(ctypes.POINTER(ModelDesc)), ctypes.c_int32, ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_void_p)]),
+    ("cpb200_forward_multi_device", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64,
+                                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                                   ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p]),
     ("cpb200_plik_create", ctypes.c_int, [ctypes.POINTER(PlikDesc), ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     ("cpb200_plik_destroy", ctypes.c_int, [ctypes.c_void_p]),
     ("cpb200_plik_loglike_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -123,7 +129,7 @@ def _ptr(a):
     return a.ctypes.data_as(_fp)
 
 
-def job_table(dims_k, dims_n, kinds, tri=False):
+def job_table(dims_k, dims_n, kinds, tri=False, models=None):
     """The fused kernel's static schedule for a network (cpb200_debug_job_table; no device needed).
     Returns (entries, info): entries = list of dicts (g, t, c, nxt, s0, ns, first, last, slot, two, in_code, out_code),
     info = dict(schedule, rot_mul, par_stages, gemms=[(k_stages, nc, n_chunks)])."""
@@ -133,7 +139,8 @@ def job_table(dims_k, dims_n, kinds, tri=False):
     cap = 512
     w0, w1 = (ctypes.c_uint32 * cap)(), (ctypes.c_uint32 * cap)()
     info = (ctypes.c_int32 * (3 + 3 * n))()
-    cnt = lib.cpb200_debug_job_table(n, arr(dims_k), arr(dims_n), arr(kinds), 1 if tri else 0, w0, w1, cap, info)
+    cnt = lib.cpb200_debug_job_table(n, arr(dims_k), arr(dims_n), arr(kinds), arr(models) if models is not None else None,
+                                     1 if tri else 0, w0, w1, cap, info)
     if cnt < 0:
         _check(cnt)
     entries = []
@@ -172,6 +179,49 @@ class PinnedArray:
             pass
 
 
+def _model_desc(attrs, keep):
+    """cpb200_model_desc of one restored emulator; the arrays it points to are appended to `keep`."""
+    n_dense = len(attrs["W_"])
+    dims = [int(attrs["W_"][0].shape[0])] + [int(w.shape[1]) for w in attrs["W_"]]
+
+    def arr_list(items):
+        arrs = [_f32(a) for a in items]
+        keep.extend(arrs)
+        c = (_fp * max(len(arrs), 1))(*[_ptr(a) for a in arrs])
+        keep.append(c)
+        return c
+
+    def arr(a):
+        a = _f32(a)
+        keep.append(a)
+        return _ptr(a)
+
+    d = ModelDesc()
+    d.n_parameters = int(attrs["n_parameters"])
+    d.n_modes = int(attrs["n_modes"])
+    d.n_dense = n_dense
+    d.n_pcas = int(attrs.get("n_pcas", 0) or 0)
+    cdims = (ctypes.c_int32 * len(dims))(*dims)
+    keep.append(cdims)
+    d.dims = cdims
+    for i, w in enumerate(attrs["W_"]):
+        if tuple(w.shape) != (dims[i], dims[i + 1]):
+            raise ValueError("W_[%d] has shape %s, expected %s" % (i, w.shape, (dims[i], dims[i + 1])))
+    d.W = arr_list(attrs["W_"])
+    d.b = arr_list(attrs["b_"])
+    d.alphas = arr_list(attrs["alphas_"])
+    d.betas = arr_list(attrs["betas_"])
+    d.parameters_mean = arr(attrs["parameters_mean_"])
+    d.parameters_std = arr(attrs["parameters_std_"])
+    d.features_mean = arr(attrs["features_mean_"])
+    d.features_std = arr(attrs["features_std_"])
+    if d.n_pcas:
+        d.pca_mean = arr(attrs["pca_mean_"])
+        d.pca_std = arr(attrs["pca_std_"])
+        d.pca_transform_matrix = arr(attrs["pca_transform_matrix_"])
+    return d
+
+
 class Engine:
     """One restored emulator resident on one B200 (opaque cpb200_engine handle)."""
 
@@ -179,45 +229,8 @@ class Engine:
         lib = load_library()
         self._lib = lib
         self._h = None
-        n_dense = len(attrs["W_"])
-        dims = [int(attrs["W_"][0].shape[0])] + [int(w.shape[1]) for w in attrs["W_"]]
         keep = []
-
-        def arr_list(items):
-            arrs = [_f32(a) for a in items]
-            keep.extend(arrs)
-            c = (_fp * max(len(arrs), 1))(*[_ptr(a) for a in arrs])
-            keep.append(c)
-            return c
-
-        def arr(a):
-            a = _f32(a)
-            keep.append(a)
-            return _ptr(a)
-
-        d = ModelDesc()
-        d.n_parameters = int(attrs["n_parameters"])
-        d.n_modes = int(attrs["n_modes"])
-        d.n_dense = n_dense
-        d.n_pcas = int(attrs.get("n_pcas", 0) or 0)
-        cdims = (ctypes.c_int32 * len(dims))(*dims)
-        keep.append(cdims)
-        d.dims = cdims
-        for i, w in enumerate(attrs["W_"]):
-            if tuple(w.shape) != (dims[i], dims[i + 1]):
-                raise ValueError("W_[%d] has shape %s, expected %s" % (i, w.shape, (dims[i], dims[i + 1])))
-        d.W = arr_list(attrs["W_"])
-        d.b = arr_list(attrs["b_"])
-        d.alphas = arr_list(attrs["alphas_"])
-        d.betas = arr_list(attrs["betas_"])
-        d.parameters_mean = arr(attrs["parameters_mean_"])
-        d.parameters_std = arr(attrs["parameters_std_"])
-        d.features_mean = arr(attrs["features_mean_"])
-        d.features_std = arr(attrs["features_std_"])
-        if d.n_pcas:
-            d.pca_mean = arr(attrs["pca_mean_"])
-            d.pca_std = arr(attrs["pca_std_"])
-            d.pca_transform_matrix = arr(attrs["pca_transform_matrix_"])
+        d = _model_desc(attrs, keep)
         prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
         h = ctypes.c_void_p()
         _check(lib.cpb200_create(ctypes.byref(d), int(device), prec, ctypes.byref(h)))
@@ -327,6 +340,84 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self._lib.cpb200_engine_last_kernel_ms(self._h))
+
+
+class MultiEngine:
+    """Several emulators evaluated on the same rows by ONE launch (cpb200_create_multi / cpb200_forward_multi_device):
+    TT + TE + EE behind the likelihood, or the linear P(k) and its nonlinear boost with the log-sum fused."""
+
+    def __init__(self, attrs_list, device=0):
+        lib = load_library()
+        self._lib = lib
+        self._h = None
+        keep = []
+        descs = [_model_desc(a, keep) for a in attrs_list]
+        ptrs = (ctypes.POINTER(ModelDesc) * len(descs))(*[ctypes.pointer(d) for d in descs])
+        h = ctypes.c_void_p()
+        _check(lib.cpb200_create_multi(ptrs, len(descs), int(device), ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.n_models = len(descs)
+        self.n_parameters = [int(d.n_parameters) for d in descs]
+        self.n_modes = [int(d.n_modes) for d in descs]
+        self._call_lock = threading.RLock()
+
+    def close(self):
+        if self._h is not None:
+            with self._call_lock:
+                self._lib.cpb200_destroy(self._h)
+                self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward_torch(self, params, outs=None, ten_to=False, accumulate=False):
+        """params: one CUDA float32 (N, P_m) tensor per emulator (the same tensor may be passed several times);
+        ten_to / accumulate: one bool per emulator (or one for all).  With accumulate[m] emulator m adds its log10
+        spectrum to emulator m-1's and writes into the same tensor.  Returns the list of output tensors."""
+        import torch
+        M = self.n_models
+        if len(params) != M:
+            raise ValueError("need one parameter tensor per emulator")
+        ten_to = [bool(ten_to)] * M if isinstance(ten_to, (bool, int)) else [bool(v) for v in ten_to]
+        accumulate = [bool(accumulate and m > 0) for m in range(M)] if isinstance(accumulate, (bool, int)) else [bool(v) for v in accumulate]
+        n = int(params[0].shape[0])
+        xs = []
+        for m, x in enumerate(params):
+            if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape == (n, self.n_parameters[m]) and x.device.index == self.device):
+                raise ValueError("emulator %d expects a CUDA float32 tensor of shape (%d, %d) on device %d" % (m, n, self.n_parameters[m], self.device))
+            xs.append(x.contiguous())
+        if outs is None:
+            outs = []
+            for m in range(M):
+                if accumulate[m]:
+                    outs.append(outs[m - 1])
+                else:
+                    pitch = (self.n_modes[m] + 7) // 8 * 8
+                    outs.append(torch.empty((n, pitch), dtype=torch.float32, device=xs[0].device)[:, :self.n_modes[m]])
+        for m, o in enumerate(outs):
+            if not (o.is_cuda and o.dtype == torch.float32 and o.dim() == 2 and o.shape == (n, self.n_modes[m]) and o.stride(1) == 1):
+                raise ValueError("bad output tensor for emulator %d" % m)
+        pp = (ctypes.c_void_p * M)(*[x.data_ptr() for x in xs])
+        po = (ctypes.c_void_p * M)(*[o.data_ptr() for o in outs])
+        pitch = (ctypes.c_int64 * M)(*[int(o.stride(0)) if n > 1 else self.n_modes[m] for m, o in enumerate(outs)])
+        fl = (ctypes.c_int32 * M)(*[(FLAG_TEN_TO if ten_to[m] else 0) | (FLAG_ACCUMULATE if accumulate[m] else 0) for m in range(M)])
+        stream = torch.cuda.current_stream(xs[0].device).cuda_stream
+        with self._call_lock:
+            _check(self._lib.cpb200_forward_multi_device(self._h, pp, n, po, pitch, fl, ctypes.c_void_p(stream)))
+        return outs
+
+    def launch_count(self):
+        return int(self._lib.cpb200_engine_launch_count(self._h))
+
+    def set_timing(self, enabled):
+        _check(self._lib.cpb200_engine_set_timing(self._h, 1 if enabled else 0))
+
+    def last_kernel_cycles(self):
+        return int(self._lib.cpb200_engine_last_kernel_cycles(self._h))
 
 
 def forward_host_multi(engines, params, out=None, ten_to=False, dtype=np.float32):

@@ -64,6 +64,9 @@ struct Gemm {
     // device, UMMA path
     int k_pad = 0, k_stages = 0, nc = 0, n_chunks = 0;
     int max_nc = cpb::UM_MAX_NC;   // widest chunk the schedule wants for this contraction (256 = two TMEM slots, 128 = one)
+    int model = 0;                 // emulator of a multi-emulator engine this contraction belongs to
+    bool layer0 = true;            // first contraction of its emulator (operand = standardised parameters)
+    bool last = true;              // last contraction of its emulator (writes the spectrum)
     float acc_scale = 1.f;         // 1 / (weight scale * input-activation scale), a power of two
     bool tri = false;              // upper-triangular weights (quadratic form): chunk c skips the K stages past its columns
     __half* dwpack = nullptr;
@@ -76,9 +79,14 @@ constexpr int64_t HOST_CHUNK_BYTES = 128ll << 20;  // output bytes per pipelined
 
 struct cpb200_engine {
     int device = 0, precision = 0;
-    int P = 0, n_modes = 0, n_pcas = 0, num_sms = 0;
+    int P = 0, n_modes = 0, n_pcas = 0, num_sms = 0;      // of emulator 0 (the only one of an ordinary engine)
     std::vector<Gemm> gemms;
     float *d_pmean = nullptr, *d_pstd = nullptr;
+    // multi-emulator engines (cpb200_create_multi): several emulators evaluated on the same rows by one launch
+    int n_models = 1;
+    int mP[cpb::UM_MAX_MODELS] = {0, 0, 0}, mModes[cpb::UM_MAX_MODELS] = {0, 0, 0};
+    float* md_pmean[cpb::UM_MAX_MODELS] = {nullptr, nullptr, nullptr};
+    float* md_pstd[cpb::UM_MAX_MODELS] = {nullptr, nullptr, nullptr};
     // SIMT scratch (two ping-pong activation buffers)
     float* simt_buf[2] = {nullptr, nullptr};
     int64_t simt_rows = 0;
@@ -135,9 +143,10 @@ int upload(T** dptr, const T* h, size_t n) {
 }
 
 // Turn the reference attributes into the list of contractions + folded epilogue constants.
-int build_gemms(const cpb200_model_desc* d, std::vector<Gemm>& out) {
+int build_gemms(const cpb200_model_desc* d, std::vector<Gemm>& out, int model = 0) {
     const int nd = d->n_dense;
     const bool pca = d->n_pcas > 0;
+    const size_t first_gemm = out.size();
     for (int i = 0; i < nd; ++i) {
         Gemm g;
         g.K = d->dims[i];
@@ -174,6 +183,7 @@ int build_gemms(const cpb200_model_desc* d, std::vector<Gemm>& out) {
         g.p2.assign(g.N, 0.f);
         out.push_back(std::move(g));
     }
+    for (size_t i = first_gemm; i < out.size(); ++i) { out[i].model = model; out[i].layer0 = i == first_gemm; out[i].last = i + 1 == out.size(); }
     return 0;
 }
 
@@ -324,6 +334,7 @@ int plan_schedule(std::vector<Gemm>& gemms, int k_pad0) {
     // (the job after a hosted output job still waits for that job's epilogue: two accumulators) and stays a
     // profiling-build option.
     if (G >= 2 && gemms[0].epi != cpb::EPI_QUADFORM) sched = SCHED_MERGE_L0;
+    if (gemms.back().model > 0) force = nullptr;          // several emulators in one launch: MERGE_L0 is the only order built for it
     if (force) {
         if (!strcmp(force, "simple")) sched = SCHED_SIMPLE;
         else if (!strcmp(force, "merge") && G >= 2) sched = SCHED_MERGE_L0;
@@ -416,9 +427,15 @@ int assign_slots(std::vector<JobEntry>& entries) {
 
 int build_jobs(const std::vector<Gemm>& gemms, int sched, std::vector<JobEntry>& out, int* rot_mul, int* par_stages) {
     const int G = static_cast<int>(gemms.size());
+    const int n_models = gemms.back().model + 1;
     out.clear();
     *rot_mul = 0; *par_stages = 0;
     int n_jobs = 0;
+    // per emulator: its range of contractions and the offset of its walk through the rotating buffers (an emulator with
+    // G contractions advances the rotation by G - 1, see below)
+    std::vector<int> g0(n_models + 1, G), base(n_models + 1, 0);
+    for (int g = G - 1; g >= 0; --g) g0[gemms[g].model] = g;
+    for (int m = 0; m < n_models; ++m) base[m + 1] = base[m] + (g0[m + 1] - g0[m] - 1);
     auto make = [&](int g, int t, int c, int nxt) {
         JobEntry e;
         const Gemm& L = gemms[g];
@@ -426,90 +443,108 @@ int build_jobs(const std::vector<Gemm>& gemms, int sched, std::vector<JobEntry>&
         e.ns = L.tri ? std::min(L.k_stages, ((c + 1) * L.nc) / cpb::UM_KS) : L.k_stages;      // upper-triangular weights: stages up to the chunk's last column
         e.two = L.nc > cpb::UM_SLOT_COLS;
         e.job = n_jobs++;
-        // operand buffers: layer 0 reads the standardiser's tile; step n = 2(g-1) + t reads rotating buffer 2n and writes 2n + 1
-        const int n = 2 * (g - 1) + t;
-        e.in_code = g == 0 ? cpb::UM_BUF_A0 + t : cpb::UM_BUF_ROT + ((2 * n) % 3 + 3) % 3;
-        e.out_code = g == G - 1 ? cpb::UM_BUF_NONE : cpb::UM_BUF_ROT + ((2 * n + 1) % 3 + 3) % 3;
+        // operand buffers: layer 0 reads the standardiser's tile of (emulator, tile); step n = 2(layer-1) + t of an emulator
+        // reads rotating buffer 2n and writes 2n + 1, shifted by what the emulators before it (this pair) have advanced
+        const int gl = g - g0[L.model], n = 2 * (gl - 1) + t, sh = base[L.model];
+        e.in_code = L.layer0 ? cpb::UM_BUF_A0 + 2 * L.model + t : cpb::UM_BUF_ROT + (((2 * n + sh) % 3) + 3) % 3;
+        e.out_code = L.last ? cpb::UM_BUF_NONE : cpb::UM_BUF_ROT + (((2 * n + 1 + sh) % 3) + 3) % 3;
         if (sched == SCHED_OVERLAP) {
             if (g == G - 1) e.in_code = cpb::UM_BUF_PAR + t;
             if (g == G - 2) e.out_code = cpb::UM_BUF_PAR + t;
         }
         return e;
     };
-    std::vector<JobEntry> l0, head, tail;
-    for (int g = 0; g < G; ++g)
-        for (int t = 0; t < 2; ++t)
-            for (int c = 0; c < gemms[g].n_chunks; ++c) {
-                if (sched == SCHED_OVERLAP) (g == G - 1 ? tail : head).push_back(make(g, t, c, g != G - 1));
-                else if (G == 1 || g == 0) l0.push_back(make(g, t, c, 1));
-                else (g == G - 1 ? tail : head).push_back(make(g, t, c, 0));
-            }
-    if (sched == SCHED_OVERLAP) {
-        *par_stages = gemms[G - 1].k_stages;
-        // hosts: the trunk jobs with a long MMA (at least 8 stages); every host takes one output job of the previous pair
-        size_t n_host = 0;
-        for (const JobEntry& e : head) n_host += e.ns >= 8;
-        const size_t hosted = std::min(tail.size(), n_host);
-        // what is left surrounds the other trunk jobs: two thirds before the first host (the layer-0 jobs: long epilogues,
-        // no MMA to speak of), one third after the last (the dependent coefficient jobs)
-        const size_t rest = tail.size() - hosted;
-        size_t n_pre = 0, n_post = 0;
-        { bool seen_host = false; for (const JobEntry& e : head) { if (e.ns >= 8) seen_host = true; else (seen_host ? n_post : n_pre)++; } }
-        size_t rest_post = n_post ? std::min(rest, std::max<size_t>(rest / 3, n_post)) : 0, rest_pre = n_pre ? rest - rest_post : 0;
-        if (!n_pre) rest_post = n_post ? rest : 0;
-        size_t oi = 0, pre_seen = 0, post_seen = 0, pre_used = 0, post_used = 0;
+    if (n_models > 1) {
+        if (sched != SCHED_MERGE_L0) return fail(CPB200_E_UNSUPPORTED, "several emulators in one launch need the merged-layer-0 order");
+        for (int m = 0; m < n_models; ++m)
+            if (g0[m + 1] - g0[m] < 2) return fail(CPB200_E_UNSUPPORTED, "an emulator without a hidden layer cannot share a launch");
+    }
+    if (sched == SCHED_MERGE_L0) {
+        // Per pair of tiles the emulators run one after the other: trunk and output phase of emulator m, and inside its
+        // output jobs the layer-0 jobs of the emulator that follows - emulator m + 1 on the same pair, or emulator 0 on the
+        // NEXT pair.  Every layer 0 thus runs just before its own trunk, in an output phase whose long MMAs hide its long
+        // epilogue, and lands in the rotating buffer that is free then (tile 1's only after tile 0's last output chunk:
+        // the buffer it writes is tile 0's output operand).
+        *rot_mul = base[n_models] % 3;
         const JobEntry* prev = nullptr;
-        std::vector<JobEntry> pending;
-        for (size_t i = 0; i < head.size(); ++i) {
-            const JobEntry& e = head[i];
-            if (e.ns >= 8 && oi < tail.size() && hosted > 0 && (oi - pre_used - post_used) < hosted) {
-                push_hosted(out, gemms, e, tail[oi++], prev);
-                prev = &head[i];
-                continue;
-            }
-            out.push_back(e);
-            prev = &head[i];
-            if (e.ns >= 8) continue;
-            const bool is_pre = post_seen == 0 && pre_seen < n_pre;
-            size_t want;
-            if (is_pre) { ++pre_seen; want = rest_pre * pre_seen / n_pre - pre_used; }
-            else { ++post_seen; want = rest_post * post_seen / std::max<size_t>(1, n_post) - post_used; }
-            for (size_t k = 0; k < want && oi < tail.size(); ++k) { prev = &tail[oi]; out.push_back(tail[oi++]); (is_pre ? pre_used : post_used)++; }
-        }
-        while (oi < tail.size()) out.push_back(tail[oi++]);
-    } else if (sched == SCHED_MERGE_L0) {
-        *rot_mul = (G - 1) % 3;
-        out = head;
-        // layer-0 jobs of tile t go into the output jobs of tile t (tile 1's must follow tile 0's last output chunk: the
-        // buffer they write is tile 0's output operand)
-        const JobEntry* prev = head.empty() ? nullptr : &head.back();
-        std::vector<JobEntry> outs[2], l0s[2];
-        for (const JobEntry& e : tail) outs[e.t].push_back(e);
-        for (const JobEntry& e : l0) l0s[e.t].push_back(e);
-        for (int t = 0; t < 2; ++t) {
-            const size_t n_o = outs[t].size(), n_l = l0s[t].size();
-            std::vector<std::vector<JobEntry>> where(n_o);
-            // spread over the tile's output jobs, leaving out the first one when there is room (it follows a long epilogue)
-            const size_t lo = (n_o > n_l) ? 1 : 0;
-            for (size_t k = 0; k < n_l; ++k) where[std::min(n_o - 1, lo + static_cast<size_t>((k + 0.5) * (n_o - lo) / n_l))].push_back(l0s[t][k]);
-            for (size_t i = 0; i < n_o; ++i) {
-                const JobEntry& host = outs[t][i];
-                if (where[i].empty()) { out.push_back(host); prev = &outs[t][i]; continue; }
-                push_hosted(out, gemms, host, where[i][0], prev);
-                for (size_t k = 1; k < where[i].size(); ++k) out.push_back(where[i][k]);
-                prev = &outs[t][i];
+        std::vector<JobEntry> keep;                      // stable storage for `prev`
+        keep.reserve(4096);
+        for (int m = 0; m < n_models; ++m) {
+            const int nm = (m + 1) % n_models, gl0 = g0[nm], glast = g0[m + 1] - 1;
+            for (int g = g0[m] + 1; g < glast; ++g)
+                for (int t = 0; t < 2; ++t)
+                    for (int c = 0; c < gemms[g].n_chunks; ++c) { keep.push_back(make(g, t, c, 0)); out.push_back(keep.back()); prev = &keep.back(); }
+            for (int t = 0; t < 2; ++t) {
+                std::vector<JobEntry> outs, l0s;
+                for (int c = 0; c < gemms[glast].n_chunks; ++c) outs.push_back(make(glast, t, c, 0));
+                for (int c = 0; c < gemms[gl0].n_chunks; ++c) l0s.push_back(make(gl0, t, c, nm == 0 ? 1 : 0));
+                const size_t n_o = outs.size(), n_l = l0s.size();
+                std::vector<std::vector<JobEntry>> where(n_o);
+                // spread over the tile's output jobs, leaving out the first one when there is room (it follows a long epilogue)
+                const size_t lo = (n_o > n_l) ? 1 : 0;
+                for (size_t k = 0; k < n_l; ++k) where[std::min(n_o - 1, lo + static_cast<size_t>((k + 0.5) * (n_o - lo) / n_l))].push_back(l0s[k]);
+                for (size_t i = 0; i < n_o; ++i) {
+                    keep.push_back(outs[i]);
+                    const JobEntry& host = keep.back();
+                    if (where[i].empty()) { out.push_back(host); prev = &host; continue; }
+                    push_hosted(out, gemms, host, where[i][0], prev);
+                    for (size_t k = 1; k < where[i].size(); ++k) out.push_back(where[i][k]);
+                    prev = &host;
+                }
             }
         }
     } else {
-        // round-1 order: whole jobs; layer 0 of the next pair spread over the output phase
-        *rot_mul = G > 1 ? (G - 1) % 3 : 0;
-        out = head;
-        size_t k = 0;
-        for (size_t i = 0; i < tail.size(); ++i) {
-            out.push_back(tail[i]);
-            while (k < l0.size() && (k + 1) * tail.size() <= (i + 1) * (l0.size() + 1)) out.push_back(l0[k++]);
+        std::vector<JobEntry> l0, head, tail;
+        for (int g = 0; g < G; ++g)
+            for (int t = 0; t < 2; ++t)
+                for (int c = 0; c < gemms[g].n_chunks; ++c) {
+                    if (sched == SCHED_OVERLAP) (g == G - 1 ? tail : head).push_back(make(g, t, c, g != G - 1));
+                    else if (G == 1 || g == 0) l0.push_back(make(g, t, c, 1));
+                    else (g == G - 1 ? tail : head).push_back(make(g, t, c, 0));
+                }
+        if (sched == SCHED_OVERLAP) {
+            *par_stages = gemms[G - 1].k_stages;
+            // hosts: the trunk jobs with a long MMA (at least 8 stages); every host takes one output job of the previous pair
+            size_t n_host = 0;
+            for (const JobEntry& e : head) n_host += e.ns >= 8;
+            const size_t hosted = std::min(tail.size(), n_host);
+            // what is left surrounds the other trunk jobs: before the first host (the layer-0 jobs: long epilogues, no MMA to
+            // speak of) and after the last (the dependent coefficient jobs)
+            const size_t rest = tail.size() - hosted;
+            size_t n_pre = 0, n_post = 0;
+            { bool seen_host = false; for (const JobEntry& e : head) { if (e.ns >= 8) seen_host = true; else (seen_host ? n_post : n_pre)++; } }
+            size_t rest_post = n_post ? std::min(rest, std::max<size_t>(rest / 3, n_post)) : 0, rest_pre = n_pre ? rest - rest_post : 0;
+            if (!n_pre) rest_post = n_post ? rest : 0;
+            size_t oi = 0, pre_seen = 0, post_seen = 0, pre_used = 0, post_used = 0;
+            const JobEntry* prev = nullptr;
+            for (size_t i = 0; i < head.size(); ++i) {
+                const JobEntry& e = head[i];
+                if (e.ns >= 8 && oi < tail.size() && hosted > 0 && (oi - pre_used - post_used) < hosted) {
+                    push_hosted(out, gemms, e, tail[oi++], prev);
+                    prev = &head[i];
+                    continue;
+                }
+                out.push_back(e);
+                prev = &head[i];
+                if (e.ns >= 8) continue;
+                const bool is_pre = post_seen == 0 && pre_seen < n_pre;
+                size_t want;
+                if (is_pre) { ++pre_seen; want = rest_pre * pre_seen / n_pre - pre_used; }
+                else { ++post_seen; want = rest_post * post_seen / std::max<size_t>(1, n_post) - post_used; }
+                for (size_t k = 0; k < want && oi < tail.size(); ++k) { prev = &tail[oi]; out.push_back(tail[oi++]); (is_pre ? pre_used : post_used)++; }
+            }
+            while (oi < tail.size()) out.push_back(tail[oi++]);
+        } else {
+            // round-1 order: whole jobs; layer 0 of the next pair spread over the output phase
+            *rot_mul = G > 1 ? (G - 1) % 3 : 0;
+            out = head;
+            size_t k = 0;
+            for (size_t i = 0; i < tail.size(); ++i) {
+                out.push_back(tail[i]);
+                while (k < l0.size() && (k + 1) * tail.size() <= (i + 1) * (l0.size() + 1)) out.push_back(l0[k++]);
+            }
+            while (k < l0.size()) out.push_back(l0[k++]);
         }
-        while (k < l0.size()) out.push_back(l0[k++]);
     }
     if (out.size() > static_cast<size_t>(cpb::UM_MAX_JOBS))
         return fail(CPB200_E_UNSUPPORTED, "%zu job-table entries per tile pair exceed %d", out.size(), cpb::UM_MAX_JOBS);
@@ -614,11 +649,24 @@ int launch_simt(cpb200_engine* e, const float* params, int64_t n, float* out, in
     return 0;
 }
 
-int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
+int launch_umma(cpb200_engine* e, const float* const* params, int64_t n, float* const* out, const int64_t* pitch, const int* flags,
                 cudaStream_t st) {
     cpb::UmmaParams p;
     memset(&p, 0, sizeof p);
     p.n_gemms = static_cast<int>(e->gemms.size());
+    p.n_models = e->n_models;
+    for (int m = 0; m < e->n_models; ++m) {
+        cpb::UmmaModel& M = p.m[m];
+        M.params = params ? params[m] : nullptr;
+        M.pmean = e->md_pmean[m];
+        M.pstd = e->md_pstd[m];
+        M.out = out ? out[m] : nullptr;
+        M.out_pitch = pitch ? pitch[m] : 0;
+        M.n_parameters = e->mP[m];
+        M.n_modes = e->mModes[m];
+        M.ten_to = (flags && (flags[m] & CPB200_FLAG_TEN_TO)) ? 1 : 0;
+        M.accumulate = (flags && (flags[m] & CPB200_FLAG_ACCUMULATE)) ? 1 : 0;
+    }
     for (int i = 0; i < p.n_gemms; ++i) {
         const Gemm& g = e->gemms[i];
         p.g[i].wpack = g.dwpack;
@@ -629,20 +677,13 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
         p.g[i].epi_kind = g.epi;
         p.g[i].acc_scale = g.acc_scale;
         p.g[i].tri = g.tri ? 1 : 0;
+        p.g[i].model = static_cast<short>(g.model);
+        p.g[i].layer0 = g.layer0 ? 1 : 0;
     }
-    p.n_parameters = e->P;
-    p.n_modes = e->n_modes;
-    p.ten_to = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
-    p.accumulate = (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0;
     p.debug_flags = 0;
     p.discard_ok = 1;
-    for (size_t i = 0; i + 1 < e->gemms.size(); ++i) if (e->gemms[i].nc % 64) p.discard_ok = 0;
+    for (size_t i = 0; i < e->gemms.size(); ++i) if (!e->gemms[i].last && e->gemms[i].nc % 64) p.discard_ok = 0;
     if (e->d_counters) if (const char* dbg = getenv("CPB200_DEBUG_EPILOGUE")) p.debug_flags = atoi(dbg);   // profiling ablations
-    p.params = params;
-    p.pmean = e->d_pmean;
-    p.pstd = e->d_pstd;
-    p.out = out;
-    p.out_pitch = pitch;
     p.n_rows = n;
     const int64_t n_tiles = (n + cpb::UM_TILE_M - 1) / cpb::UM_TILE_M;
     p.n_pairs = (n_tiles + 1) / 2;
@@ -668,7 +709,7 @@ int launch_umma(cpb200_engine* e, const float* params, int64_t n, float* out, in
     {
         const Gemm& last = e->gemms.back();
         const int64_t room = max_clusters / std::max<int64_t>(1, p.n_pairgroups);
-        if (e->gemms.size() > 1 && last.epi == cpb::EPI_OUT && last.n_chunks > 1 && room >= 2 && !getenv("CPB200_NO_OUT_SPLIT")) {
+        if (e->n_models == 1 && e->gemms.size() > 1 && last.epi == cpb::EPI_OUT && last.n_chunks > 1 && room >= 2 && !getenv("CPB200_NO_OUT_SPLIT")) {
             const int smax = static_cast<int>(std::min<int64_t>(room, last.n_chunks));
             const int per = (last.n_chunks + smax - 1) / smax;            // chunks per cluster at the widest split
             p.out_split = (last.n_chunks + per - 1) / per;                // the narrowest split that reaches it
@@ -691,8 +732,9 @@ int forward_async(cpb200_engine* e, const float* params, int64_t n, float* out, 
                   cudaStream_t st) {
     if (n == 0) return 0;
     if (int rc = order_before(e, st)) return rc;
+    const int64_t pitch64 = pitch;
     if (int rc = e->precision == CPB200_PREC_FP32_SIMT ? launch_simt(e, params, n, out, pitch, flags, st)
-                                                       : launch_umma(e, params, n, out, pitch, flags, st)) return rc;
+                                                       : launch_umma(e, &params, n, &out, &pitch64, &flags, st)) return rc;
     return order_after(e, st);
 }
 
@@ -704,16 +746,18 @@ namespace {
 int setup_umma(cpb200_engine* e) {
     int rc;
     int k_pad = round_up(e->P, cpb::UM_KS);
-    unsigned max_stages = 1;
+    unsigned max_stages = 1, a0_stages = 1;
     e->schedule = plan_schedule(e->gemms, k_pad);
     for (size_t i = 0; i < e->gemms.size(); ++i) {
         Gemm& g = e->gemms[i];
-        const float s_in = i == 0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
+        if (g.layer0) k_pad = round_up(g.K, cpb::UM_KS);       // an emulator's first contraction: K = its parameter count
+        const float s_in = g.layer0 ? cpb::UM_INPUT_SCALE : cpb::UM_ACT_SCALE;
         if ((rc = pack_umma(g, k_pad, s_in, cpb::UM_ACT_SCALE))) return rc;
-        if (i > 0) max_stages = std::max<unsigned>(max_stages, g.k_stages);
+        if (g.layer0) a0_stages = std::max<unsigned>(a0_stages, g.k_stages);
+        else max_stages = std::max<unsigned>(max_stages, g.k_stages);
         k_pad = g.n_chunks * g.nc;          // the next contraction's (padded) K
     }
-    e->um_a0_bytes = static_cast<unsigned>(e->gemms[0].k_stages) * cpb::UM_A_STAGE_BYTES;
+    e->um_a0_bytes = a0_stages * cpb::UM_A_STAGE_BYTES;
     e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
     {
         std::vector<JobEntry> entries;
@@ -729,7 +773,7 @@ int setup_umma(cpb200_engine* e) {
             e->um_abuf_bytes = max_stages * cpb::UM_A_STAGE_BYTES;
         }
     }
-    e->um_scratch_cta = 2ull * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes + 4ull * e->um_pbuf_bytes;
+    e->um_scratch_cta = 2ull * e->n_models * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes + 4ull * e->um_pbuf_bytes;
     if (e->gemms.size() == 1 && e->gemms[0].epi == cpb::EPI_QUADFORM) e->um_scratch_cta = 1024;   // operand tiles are prebuilt elsewhere
     const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
     if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)
@@ -768,11 +812,8 @@ int cpb200_device_count(void) {
     return ok;
 }
 
-int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_engine** out) {
-    if (!d || !out) return fail(CPB200_E_INVALID, "null argument");
-    *out = nullptr;
-    if (precision != CPB200_PREC_FP32_SIMT && precision != CPB200_PREC_F16X3)
-        return fail(CPB200_E_INVALID, "unknown precision %d", precision);
+static int check_desc(const cpb200_model_desc* d) {
+    if (!d) return fail(CPB200_E_INVALID, "null model description");
     if (d->n_dense < 1 || d->n_parameters < 1 || d->n_modes < 1 || !d->dims || !d->W || !d->b ||
         !d->parameters_mean || !d->parameters_std || !d->features_mean || !d->features_std)
         return fail(CPB200_E_INVALID, "incomplete model description");
@@ -786,8 +827,22 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
     }
     for (int i = 0; i <= d->n_dense; ++i)
         if (d->dims[i] < 1) return fail(CPB200_E_INVALID, "non-positive layer width");
-    if (d->n_dense + (d->n_pcas > 0 ? 1 : 0) > cpb::UM_MAX_GEMMS)
-        return fail(CPB200_E_UNSUPPORTED, "more than %d dense contractions", cpb::UM_MAX_GEMMS);
+    return 0;
+}
+
+static int create_impl(const cpb200_model_desc* const* descs, int n_models, int device, int precision, cpb200_engine** out) {
+    if (!descs || !out) return fail(CPB200_E_INVALID, "null argument");
+    *out = nullptr;
+    if (precision != CPB200_PREC_FP32_SIMT && precision != CPB200_PREC_F16X3)
+        return fail(CPB200_E_INVALID, "unknown precision %d", precision);
+    if (n_models < 1 || n_models > cpb::UM_MAX_MODELS) return fail(CPB200_E_INVALID, "1 .. %d emulators per engine", cpb::UM_MAX_MODELS);
+    if (n_models > 1 && precision != CPB200_PREC_F16X3) return fail(CPB200_E_UNSUPPORTED, "multi-emulator engines exist for CPB200_PREC_F16X3 only");
+    int n_gemms = 0;
+    for (int m = 0; m < n_models; ++m) {
+        if (int rc = check_desc(descs[m])) return rc;
+        n_gemms += descs[m]->n_dense + (descs[m]->n_pcas > 0 ? 1 : 0);
+    }
+    if (n_gemms > cpb::UM_MAX_GEMMS) return fail(CPB200_E_UNSUPPORTED, "more than %d dense contractions", cpb::UM_MAX_GEMMS);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -804,15 +859,22 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
     cpb200_engine* e = new cpb200_engine();
     e->device = device;
     e->precision = precision;
-    e->P = d->n_parameters;
-    e->n_modes = d->n_modes;
-    e->n_pcas = d->n_pcas;
+    e->n_models = n_models;
+    e->P = descs[0]->n_parameters;
+    e->n_modes = descs[0]->n_modes;
+    e->n_pcas = descs[0]->n_pcas;
     e->num_sms = prop.multiProcessorCount;
-    int rc = build_gemms(d, e->gemms);
     auto bail = [&](int code) { cpb200_destroy(e); return code; };
-    if (rc) return bail(rc);
-    if ((rc = upload(&e->d_pmean, d->parameters_mean, e->P))) return bail(rc);
-    if ((rc = upload(&e->d_pstd, d->parameters_std, e->P))) return bail(rc);
+    int rc = 0;
+    for (int m = 0; m < n_models; ++m) {
+        e->mP[m] = descs[m]->n_parameters;
+        e->mModes[m] = descs[m]->n_modes;
+        if ((rc = build_gemms(descs[m], e->gemms, m))) return bail(rc);
+        if ((rc = upload(&e->md_pmean[m], descs[m]->parameters_mean, e->mP[m]))) return bail(rc);
+        if ((rc = upload(&e->md_pstd[m], descs[m]->parameters_std, e->mP[m]))) return bail(rc);
+    }
+    e->d_pmean = e->md_pmean[0];
+    e->d_pstd = e->md_pstd[0];
 
     if (precision == CPB200_PREC_FP32_SIMT) {
         int width = 1;
@@ -840,6 +902,44 @@ int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_
     return 0;
 }
 
+int cpb200_create(const cpb200_model_desc* d, int device, int precision, cpb200_engine** out) {
+    if (!d || !out) return fail(CPB200_E_INVALID, "null argument");
+    return create_impl(&d, 1, device, precision, out);
+}
+
+int cpb200_create_multi(const cpb200_model_desc* const* descs, int32_t n_models, int device, cpb200_engine** out) {
+    return create_impl(descs, n_models, device, CPB200_PREC_F16X3, out);
+}
+
+int cpb200_forward_multi_device(cpb200_engine* e, const float* const* params_dev, int64_t n_rows, float* const* out_dev,
+                                const int64_t* out_pitch, const int32_t* flags, void* stream) {
+    if (!e) return fail(CPB200_E_INVALID, "null engine");
+    if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
+    if (n_rows == 0) return 0;
+    if (!params_dev || !out_dev || !out_pitch || !flags) return fail(CPB200_E_INVALID, "null argument");
+    int fl[cpb::UM_MAX_MODELS];
+    for (int m = 0; m < e->n_models; ++m) {
+        if (!params_dev[m] || !out_dev[m]) return fail(CPB200_E_INVALID, "null buffer for emulator %d", m);
+        if (out_pitch[m] < e->mModes[m]) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d (emulator %d)", static_cast<long long>(out_pitch[m]), e->mModes[m], m);
+        fl[m] = flags[m];
+        if (flags[m] & CPB200_FLAG_ACCUMULATE) {
+            // the sum is read back by the very lane that wrote it (same chunking): emulator m adds to what emulator m-1 left in
+            // the same buffer, a few microseconds earlier and still in L2
+            if (m == 0 || out_dev[m] != out_dev[m - 1] || out_pitch[m] != out_pitch[m - 1] || e->mModes[m] != e->mModes[m - 1])
+                return fail(CPB200_E_INVALID, "CPB200_FLAG_ACCUMULATE on emulator %d needs the previous emulator's output buffer, pitch and n_modes", m);
+            if (flags[m - 1] & CPB200_FLAG_TEN_TO) return fail(CPB200_E_INVALID, "the emulator before an accumulating one must leave log10 values (no CPB200_FLAG_TEN_TO)");
+        }
+    }
+    DeviceGuard guard(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->timing) CU(cudaEventRecord(e->ev0, st));
+    if (int rc = order_before(e, st)) return rc;
+    if (int rc = launch_umma(e, params_dev, n_rows, out_dev, out_pitch, fl, st)) return rc;
+    if (int rc = order_after(e, st)) return rc;
+    if (e->timing) { CU(cudaEventRecord(e->ev1, st)); e->ev_valid = true; }
+    return 0;
+}
+
 int cpb200_destroy(cpb200_engine* e) {
     if (!e) return 0;
     DeviceGuard guard(e->device);
@@ -848,7 +948,7 @@ int cpb200_destroy(cpb200_engine* e) {
         cudaFree(g.dW); cudaFree(g.dp0); cudaFree(g.dp1); cudaFree(g.dp2);
         cudaFree(g.dwpack); cudaFree(g.depi);
     }
-    cudaFree(e->d_pmean); cudaFree(e->d_pstd);
+    for (int m = 0; m < cpb::UM_MAX_MODELS; ++m) { cudaFree(e->md_pmean[m]); cudaFree(e->md_pstd[m]); }
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
     cudaFree(e->um_scratch); cudaFree(e->d_max_cycles); cudaFree(e->d_counters);
     if (e->h_status) cudaFreeHost(e->h_status);
@@ -872,6 +972,7 @@ int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_r
     if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
     if (n_rows == 0) return 0;
     if (!params_dev || !out_dev) return fail(CPB200_E_INVALID, "null buffer");
+    if (e->n_models != 1) return fail(CPB200_E_INVALID, "a multi-emulator engine is driven through cpb200_forward_multi_device");
     if (out_pitch < e->n_modes) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d", static_cast<long long>(out_pitch), e->n_modes);
     DeviceGuard guard(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -953,6 +1054,7 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
     if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
     if (n_rows == 0) return 0;
     if (!params_host || !out_host) return fail(CPB200_E_INVALID, "null buffer");
+    if (e->n_models != 1) return fail(CPB200_E_INVALID, "a multi-emulator engine is driven through cpb200_forward_multi_device");
     if (out_pitch < e->n_modes) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d", static_cast<long long>(out_pitch), e->n_modes);
     if (flags & CPB200_FLAG_ACCUMULATE)
         return fail(CPB200_E_INVALID, "CPB200_FLAG_ACCUMULATE needs the first emulator's result on the device: device path only");
@@ -1159,14 +1261,23 @@ int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int
     return static_cast<int>(n);
 }
 
-int cpb200_debug_job_table(int32_t n_gemms, const int32_t* k, const int32_t* n, const int32_t* epi_kind, int32_t tri,
+int cpb200_debug_job_table(int32_t n_gemms, const int32_t* k, const int32_t* n, const int32_t* epi_kind, const int32_t* model, int32_t tri,
                            uint32_t* w0, uint32_t* w1, int32_t capacity, int32_t* info) {
     if (n_gemms < 1 || n_gemms > cpb::UM_MAX_GEMMS || !k || !n || !epi_kind) return fail(CPB200_E_INVALID, "bad job-table request");
     std::vector<Gemm> gemms(n_gemms);
-    for (int i = 0; i < n_gemms; ++i) { gemms[i].K = k[i]; gemms[i].N = n[i]; gemms[i].epi = epi_kind[i]; gemms[i].tri = tri != 0; }
+    for (int i = 0; i < n_gemms; ++i) {
+        gemms[i].K = k[i]; gemms[i].N = n[i]; gemms[i].epi = epi_kind[i]; gemms[i].tri = tri != 0;
+        gemms[i].model = model ? model[i] : 0;
+        gemms[i].layer0 = i == 0 || gemms[i].model != gemms[i - 1].model;
+    }
+    for (int i = 0; i < n_gemms; ++i) gemms[i].last = i + 1 == n_gemms || gemms[i + 1].model != gemms[i].model;
     int k_pad = round_up(k[0], cpb::UM_KS);
     const int sched = plan_schedule(gemms, k_pad);
-    for (int i = 0; i < n_gemms; ++i) { plan_chunks(gemms[i], k_pad); k_pad = gemms[i].n_chunks * gemms[i].nc; }
+    for (int i = 0; i < n_gemms; ++i) {
+        if (gemms[i].layer0) k_pad = round_up(k[i], cpb::UM_KS);
+        plan_chunks(gemms[i], k_pad);
+        k_pad = gemms[i].n_chunks * gemms[i].nc;
+    }
     std::vector<JobEntry> entries;
     int rot_mul = 0, par_stages = 0;
     if (int rc = build_jobs(gemms, sched, entries, &rot_mul, &par_stages)) return rc;
@@ -1369,6 +1480,7 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
         cpb200_engine* q = new cpb200_engine();
         p->qf = q;
         q->device = device; q->precision = CPB200_PREC_F16X3; q->P = p->pad; q->n_modes = p->pad; q->num_sms = p->num_sms;
+        q->mP[0] = p->pad; q->mModes[0] = p->pad;
         Gemm g;
         g.K = p->pad; g.N = p->pad; g.epi = cpb::EPI_QUADFORM; g.tri = true;
         g.W.assign(static_cast<size_t>(p->pad) * p->pad, 0.f);
@@ -1443,7 +1555,7 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
             cpb200_engine* q = p->qf;
             q->qf_ext_a0 = p->d_tiles; q->qf_d = p->d_diff; q->qf_pitch = p->pad; q->qf_cols = p->pad; q->qf_partial = p->d_partial;
             if (int rc = order_before(q, st)) return rc;
-            if (int rc = launch_umma(q, nullptr, m, nullptr, 0, 0, st)) return rc;
+            if (int rc = launch_umma(q, nullptr, m, nullptr, nullptr, nullptr, st)) return rc;
             if (int rc = order_after(q, st)) return rc;
             cpb::plik_finish_tensor_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(
                 p->d_partial, p->n_part, p->d_row_scale, q->gemms[0].acc_scale, m, loglike + r0);

@@ -57,7 +57,8 @@ constexpr int UM_A_HALF_BYTES = UM_TILE_M * UM_KS * 2;       // 8192: one of (hi
 constexpr int UM_A_STAGE_BYTES = 2 * UM_A_HALF_BYTES;        // 16384
 constexpr int UM_B_STAGE_BYTES_MAX = 2 * (UM_MAX_NC / 2) * UM_KS * 2;   // 16384: each CTA of the pair holds half of the chunk's columns
 constexpr int UM_STAGE_BYTES = UM_A_STAGE_BYTES + UM_B_STAGE_BYTES_MAX;   // 32768
-constexpr int UM_MAX_GEMMS = 8;
+constexpr int UM_MAX_GEMMS = 16;                             // contractions of all models of one launch (job-table field: 4 bits)
+constexpr int UM_MAX_MODELS = 3;                             // emulators evaluated on the same rows by one launch (TT + TE + EE)
 constexpr int UM_THREADS = 384;
 constexpr int UM_EPI_WARP0 = 4;
 constexpr int UM_EPI_WARPS = 8;
@@ -76,7 +77,7 @@ constexpr int UM_SMEM_STAGES = 0;
 constexpr int UM_PAR_SLOTS = UM_PAR_SLOTS_N;          // ring of per-chunk epilogue constants: deep enough that the loader never waits for an epilogue
 constexpr int UM_SMEM_EPIPAR = UM_STAGES * UM_STAGE_BYTES;                   // UM_PAR_SLOTS x 256 float4
 constexpr int UM_SMEM_BARS = UM_SMEM_EPIPAR + UM_PAR_SLOTS * UM_MAX_NC * 16;
-constexpr int UM_NUM_BARS = 2 * UM_STAGES + 2 * UM_TMEM_SLOTS + 4 + 2 + 2 + 2 * UM_PAR_SLOTS;
+constexpr int UM_NUM_BARS = 2 * UM_STAGES + 2 * UM_TMEM_SLOTS + 4 + 4 * UM_MAX_MODELS + 2 * UM_PAR_SLOTS;
 constexpr int UM_SMEM_TMEMPTR = UM_SMEM_BARS + UM_NUM_BARS * 8;
 constexpr int UM_MAX_JOBS = 320;         // entries of the job table (parts of jobs) per iteration
 constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // + alignment slack
@@ -91,22 +92,30 @@ struct UmmaGemm {
     int epi_kind;          // cpb::Epilogue
     float acc_scale;       // undoes the power-of-two operand pre-scales on the accumulator (EPI_ACT)
     int tri;               // upper-triangular weights: chunk c only needs the K stages up to its last column
+    short model;           // which emulator of the launch this contraction belongs to
+    short layer0;          // first contraction of its emulator: its operand comes from the standardiser
 };
 
-struct UmmaParams {
-    UmmaGemm g[UM_MAX_GEMMS];
-    int n_gemms;
-    int n_parameters;
-    int n_modes;
-    int ten_to;
-    int discard_ok;            // every operand-producing contraction has a chunk width that is a multiple of 64 (see the epilogue's discard)
-    int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM (results are garbage)
-    int accumulate;            // output layers add the log10 values already in `out` before the optional 10**
+// one emulator of a launch: its parameter columns, standardisation constants and where its spectra go
+struct UmmaModel {
     const float* params;       // (n_rows, n_parameters)
     const float* pmean;
     const float* pstd;
     float* out;
     long long out_pitch;
+    int n_parameters;
+    int n_modes;
+    int ten_to;
+    int accumulate;            // output layers add the log10 values already in `out` before the optional 10**
+};
+
+struct UmmaParams {
+    UmmaGemm g[UM_MAX_GEMMS];
+    int n_gemms;
+    int n_models;
+    UmmaModel m[UM_MAX_MODELS];
+    int discard_ok;            // every operand-producing contraction has a chunk width that is a multiple of 64 (see the epilogue's discard)
+    int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM (results are garbage)
     long long n_rows;
     long long n_pairs;         // ceil(n_tiles / 2)
     long long n_pairgroups;    // ceil(n_pairs / UM_CLUSTER): one pair per CTA of a cluster, processed in lockstep
@@ -694,14 +703,14 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const int lane = threadIdx.x & 31;
 
     const uint32_t bars = base + UM_SMEM_BARS;
-    constexpr int B_ACC = 2 * UM_STAGES, B_AREADY = B_ACC + 2 * UM_TMEM_SLOTS, B_A0 = B_AREADY + 4, B_PAR = B_A0 + 4;
+    constexpr int B_ACC = 2 * UM_STAGES, B_AREADY = B_ACC + 2 * UM_TMEM_SLOTS, B_A0 = B_AREADY + 4, B_PAR = B_A0 + 4 * UM_MAX_MODELS;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (UM_STAGES + s); };
     auto bar_accfull = [&](int sl) { return bars + 8u * (B_ACC + sl); };                    // per TMEM slot (a job signals its first slot)
     auto bar_accempty = [&](int sl) { return bars + 8u * (B_ACC + UM_TMEM_SLOTS + sl); };   // leader only: both CTAs' epilogues arrive
     auto bar_aready = [&](int ts) { return bars + 8u * (B_AREADY + ts); };                  // ts = 2 * (pair number & 1) + tile
-    auto bar_a0ready = [&](int t) { return bars + 8u * (B_A0 + t); };
-    auto bar_a0free = [&](int t) { return bars + 8u * (B_A0 + 2 + t); };
+    auto bar_a0ready = [&](int mt) { return bars + 8u * (B_A0 + mt); };                     // mt = 2 * model + tile
+    auto bar_a0free = [&](int mt) { return bars + 8u * (B_A0 + 2 * UM_MAX_MODELS + mt); };
     auto bar_parfull = [&](int b) { return bars + 8u * (B_PAR + b); };
     auto bar_parempty = [&](int b) { return bars + 8u * (B_PAR + UM_PAR_SLOTS + b); };
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sbase + UM_SMEM_TMEMPTR);
@@ -714,7 +723,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         for (int b = 0; b < UM_TMEM_SLOTS; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accempty(b), UM_CLUSTER * UM_EPI_WARPS); }
         for (int b = 0; b < UM_PAR_SLOTS; ++b) { mbar_init(bar_parfull(b), 1); mbar_init(bar_parempty(b), UM_EPI_WARPS); }
         for (int ts = 0; ts < 4; ++ts) mbar_init(bar_aready(ts), UM_EPI_WARPS);
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_a0ready(t), 1); mbar_init(bar_a0free(t), 1); }
+        for (int mt = 0; mt < 2 * UM_MAX_MODELS; ++mt) { mbar_init(bar_a0ready(mt), 1); mbar_init(bar_a0free(mt), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -730,7 +739,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t cta_rank = UM_CLUSTER > 1 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0;
     const int out_split = SPLIT ? P.out_split : 1, split_id = SPLIT ? static_cast<int>(blockIdx.x / UM_CLUSTER) % out_split : 0;
-    const int out_gemm = SPLIT ? P.n_gemms - 1 : -1;       // the contraction whose chunks are dealt out
+    const int out_gemm = SPLIT ? P.n_gemms - 1 : -1;       // the contraction whose chunks are dealt out (single-emulator launches only)
+    const uint32_t a0_area = 2u * P.n_models * P.a0_bytes;  // layer-0 operand tiles: one per (emulator, tile)
     const long long pg_first = (blockIdx.x / UM_CLUSTER) / out_split, pg_step = (gridDim.x / UM_CLUSTER) / out_split;
     // pair-groups this cluster walks; iteration `it` runs the table's "cur" entries for pair-group it-1 and its "next"
     // entries for pair-group it (layer 0 only, or the whole trunk when the output phase is overlapped): work of the next
@@ -739,7 +749,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     const int n_jobs = P.n_jobs;
 
     uint8_t* cta_scratch = P.scratch + static_cast<unsigned long long>(blockIdx.x) * P.scratch_cta_bytes;
-    // CTA-private scratch: [2 layer-0 operand tiles][UM_ACT_BUFS rotating activation buffers][4 parity buffers].
+    // CTA-private scratch: [2 layer-0 operand tiles per emulator][UM_ACT_BUFS rotating activation buffers][4 parity buffers].
     // Rotating buffers: with the job order X.g, Y.g, X.g+1, ... at most three 128 x K tiles are live at any time
     // (X.in, X.out, Y.in - or Y.in, Y.out, X.out); the host numbers them so that step n = 2(g-1) + t reads buffer 2n and
     // writes buffer 2n + 1 (mod 3), plus a per-pair offset (rot_mul) that lets the next pair's layer 0, which runs inside
@@ -748,9 +758,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
     // (pm3 = pair number mod 3, ppar = its parity: kept as small ints so that no 64-bit division sits on any role's path)
     auto buf_addr = [&](uint32_t code, int pm3, int ppar) -> uint8_t* {
         uint32_t off;
-        if (code & UM_BUF_ROT) off = 2u * P.a0_bytes + (((code & 0xf) + pm3 * P.rot_mul) % UM_ACT_BUFS) * P.abuf_bytes;
-        else if (code & UM_BUF_PAR) off = 2u * P.a0_bytes + UM_ACT_BUFS * P.abuf_bytes + (2 * ppar + (code & 1)) * P.pbuf_bytes;
-        else off = (code & 1) * P.a0_bytes;
+        if (code & UM_BUF_ROT) off = a0_area + (((code & 0xf) + pm3 * P.rot_mul) % UM_ACT_BUFS) * P.abuf_bytes;
+        else if (code & UM_BUF_PAR) off = a0_area + UM_ACT_BUFS * P.abuf_bytes + (2 * ppar + (code & 1)) * P.pbuf_bytes;
+        else off = (code & 0xf) * P.a0_bytes;                     // UM_BUF_A0 + 2 * model + tile
         return cta_scratch + off;
     };
 
@@ -793,11 +803,12 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 const UmmaGemm& L = P.g[g];
                 const uint32_t b_bytes = 2u * L.nc * UM_KS * 2u;
                 const long long j_t0 = now(), j_we0 = w_empty, j_wa0 = w_aready;
-                if (first && c == (g == out_gemm ? split_id : 0) && !(g == 0 && P.ext_a0)) {   // first chunk this cluster runs of (g, t): the whole K extent of the tile's operand must be written
-                    if (g == 0) { w_aready += mbar_wait(bar_a0ready(t), (ph_a0ready >> t) & 1, P.error_flag, 101); ph_a0ready ^= 1u << t; }
+                const int mt = 2 * L.model + t;
+                if (first && c == (g == out_gemm ? split_id : 0) && !(L.layer0 && P.ext_a0)) {   // first chunk this cluster runs of (g, t): the whole K extent of the tile's operand must be written
+                    if (L.layer0) { w_aready += mbar_wait(bar_a0ready(mt), (ph_a0ready >> mt) & 1, P.error_flag, 101); ph_a0ready ^= 1u << mt; }
                     else { w_aready += mbar_wait(bar_aready(ts), (ph_aready >> ts) & 1, P.error_flag, 102); ph_aready ^= 1u << ts; }
                 }
-                const uint8_t* a_src = (g == 0 && P.ext_a0) ? P.ext_a0 + static_cast<size_t>(pair * 2 + t) * P.a0_bytes
+                const uint8_t* a_src = (L.layer0 && P.ext_a0) ? P.ext_a0 + static_cast<size_t>(pair * 2 + t) * P.a0_bytes
                                                             : buf_addr(P.jobs_x[ji] & 0xff, pm3, ppar);
                 a_src += static_cast<size_t>(s0) * UM_A_STAGE_BYTES;
                 if (last) {   // this chunk's per-column epilogue constants -> shared memory (ring in the order the jobs COMPLETE)
@@ -806,7 +817,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     // float4, in two variants (plain, then pre-multiplied by log2(10) for ten_to)
                     const bool is_out = L.epi_kind == EPI_OUT;
                     const uint32_t par_bytes = is_out ? L.nc * 8u : L.nc * 16u;
-                    const float4* par_src = is_out ? L.epi + (P.ten_to ? L.n_chunks * (L.nc / 2) : 0) + c * (L.nc / 2) : L.epi + c * L.nc;
+                    const float4* par_src = is_out ? L.epi + (P.m[L.model].ten_to ? L.n_chunks * (L.nc / 2) : 0) + c * (L.nc / 2) : L.epi + c * L.nc;
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bar_parfull(pb), par_bytes);
                         bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), par_src, par_bytes, bar_parfull(pb));
@@ -902,7 +913,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 }
                 if (last && elect_one()) {
                     umma_commit_2cta(bar_accfull(slot));          // both CTAs' epilogues may drain their 128 rows
-                    if (g == 0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(t));   // layer-0 operand of tile t consumed
+                    if (L.layer0 && c == L.n_chunks - 1) umma_commit_2cta(bar_a0free(2 * L.model + t));   // layer-0 operand of (emulator, tile) consumed
                 }
                 if (PROF && P.counters && blockIdx.x == 0 && lane == 0) {
                     long long* jc = P.counters + (gridDim.x + ji) * UM_CNT_SLOTS;
@@ -920,15 +931,21 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         }
     } else if (warp == 2) {
         // ===================== parameter standardiser: builds the layer-0 A operand =====================
-        uint32_t ph_a0free[2] = {1, 1};
+        uint32_t ph_a0free = (1u << (2 * UM_MAX_MODELS)) - 1;     // one phase bit per (emulator, tile)
         long long w_in = 0; const long long t_begin = now();
-        const int np = P.n_parameters;
-        for (long long pgi = 0; pgi < (P.ext_a0 ? 0 : n_my_pg); ++pgi) {      // (prebuilt operand tiles: nothing to do)
+        // the tiles are consumed in the order (pair, emulator, tile): the job table runs the emulators of a launch one
+        // after the other on each pair of tiles
+        for (long long pgm = 0; pgm < (P.ext_a0 ? 0 : n_my_pg * P.n_models); ++pgm) {      // (prebuilt operand tiles: nothing to do)
+            const long long pgi = pgm / P.n_models;
+            const int mi = static_cast<int>(pgm % P.n_models);
+            const UmmaModel& M = P.m[mi];
+            const int np = M.n_parameters;
             const long long pair = (pg_first + pgi * pg_step) * UM_CLUSTER + cta_rank;      // rows beyond n_rows are padding
             for (int t = 0; t < 2; ++t) {
-                w_in += mbar_wait(bar_a0free(t), ph_a0free[t], P.error_flag, 301); ph_a0free[t] ^= 1;
+                const int mt = 2 * mi + t;
+                w_in += mbar_wait(bar_a0free(mt), (ph_a0free >> mt) & 1, P.error_flag, 301); ph_a0free ^= 1u << mt;
                 const long long row0 = (pair * 2 + t) * UM_TILE_M;
-                uint8_t* dst = cta_scratch + static_cast<size_t>(t) * P.a0_bytes;
+                uint8_t* dst = cta_scratch + static_cast<size_t>(mt) * P.a0_bytes;
                 for (int rr = 0; rr < UM_TILE_M / 32; ++rr) {
                     const int r = rr * 32 + lane;
                     const long long grow = row0 + r;
@@ -939,8 +956,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             const int k = k0 + u;
                             float v = 0.f;
                             if (k < np) {
-                                const float raw_v = (grow < P.n_rows) ? P.params[grow * np + k] : P.pmean[k];
-                                v = (raw_v - P.pmean[k]) / P.pstd[k] * UM_INPUT_SCALE;
+                                const float raw_v = (grow < P.n_rows) ? M.params[grow * np + k] : M.pmean[k];
+                                v = (raw_v - M.pmean[k]) / M.pstd[k] * UM_INPUT_SCALE;
                                 // beyond +-64 sigma (or non-finite) the split would saturate: flag the batch
                                 if (UM_RANGE_CHECK && !(fabsf(v) < UM_F16_MAX) && P.error_flag) *reinterpret_cast<volatile int*>(P.error_flag + 1) = 1;
                             }
@@ -957,7 +974,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 __threadfence();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a0ready(t));
+                if (lane == 0) mbar_arrive(bar_a0ready(mt));
             }
         }
         if (PROF && P.counters && lane == 0) {
@@ -972,9 +989,6 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         const int cw = ew >> 2;                      // which of the lane quarter's warps: takes every (UM_EPI_WARPS/4)-th 32-column piece
         const float4* epipar = reinterpret_cast<const float4*>(sbase + UM_SMEM_EPIPAR);
         const int tq = lane >> 2, tr = lane & 3;     // fragment coordinates: rows tq, tq+8 (+16 for the 2nd load); cols 2*tr, 2*tr+1
-        // 32-byte (16-byte) output stores need a 32-byte (16-byte) aligned base and a row pitch that is a multiple of 8 (4) floats
-        const int vec_mode = ((reinterpret_cast<uintptr_t>(P.out) & 31) | (static_cast<uintptr_t>(P.out_pitch) & 7)) == 0 ? OUT_VEC32
-                           : ((reinterpret_cast<uintptr_t>(P.out) & 15) | (static_cast<uintptr_t>(P.out_pitch) & 3)) == 0 ? OUT_VEC16 : OUT_SCALAR;
         uint32_t ph_accfull = 0, ph_parfull = 0;     // one phase bit per TMEM slot / constant slot
         long long w_accfull = 0, c_act = 0, c_out = 0; const long long t_begin = now();
         int pb = 0;
@@ -1014,15 +1028,20 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 epi_chunk_quadform(E, P.qf_d + (row0 + q * 32 + tq) * P.qf_pitch, P.qf_pitch, P.n_rows - row0, P.qf_cols,
                                    P.qf_partial + (row0 + q * 32 + tq) * (2 * L.n_chunks) + 2 * c + cw, 2 * L.n_chunks, lane);
             else {
-                const bool rows_ok = row0 + UM_TILE_M <= P.n_rows;
+                const UmmaModel& M = P.m[L.model];
+                // 32-byte (16-byte) output stores need a 32-byte (16-byte) aligned base and a row pitch that is a multiple of 8 (4)
+                // floats - and a tile that lies wholly inside the batch
+                const int vec_mode = row0 + UM_TILE_M > P.n_rows ? OUT_SCALAR
+                                   : ((reinterpret_cast<uintptr_t>(M.out) & 31) | (static_cast<uintptr_t>(M.out_pitch) & 7)) == 0 ? OUT_VEC32
+                                   : ((reinterpret_cast<uintptr_t>(M.out) & 15) | (static_cast<uintptr_t>(M.out_pitch) & 3)) == 0 ? OUT_VEC16 : OUT_SCALAR;
                 // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
-                float* orow0 = P.out + (row0 + q * 32 + tq) * P.out_pitch;
-                if (P.accumulate) {
-                    if (P.ten_to) epi_chunk_output<true, true>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
-                    else epi_chunk_output<false, true>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
+                float* orow0 = M.out + (row0 + q * 32 + tq) * M.out_pitch;
+                if (M.accumulate) {
+                    if (M.ten_to) epi_chunk_output<true, true>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
+                    else epi_chunk_output<false, true>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
                 } else {
-                    if (P.ten_to) epi_chunk_output<true, false>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
-                    else epi_chunk_output<false, false>(E, orow0, P.out_pitch, rows_ok ? vec_mode : OUT_SCALAR, P.n_rows - row0, P.n_modes);
+                    if (M.ten_to) epi_chunk_output<true, false>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
+                    else epi_chunk_output<false, false>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
                 }
             }
             // accumulator drained (every lane has passed tcgen05.wait::ld): hand the rest of its TMEM back to the MMA
@@ -1047,7 +1066,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_aready(ts));
             }
-            if (UM_DISCARD_DEAD_TILES && P.discard_ok && g >= 1 && c == L.n_chunks - 1) {
+            if (UM_DISCARD_DEAD_TILES && P.discard_ok && !L.layer0 && c == L.n_chunks - 1) {
                 // This was the last chunk to stream the tile's operand: every copy of it has landed and been consumed
                 // (its MMAs are complete), so its L2 lines are dead - drop them instead of letting them be written
                 // back to HBM on eviction.  The buffer is rewritten soon, possibly while slower warps

@@ -130,6 +130,24 @@ int cpb200_forward_host_f64(cpb200_engine* e, const float* params_host, int64_t 
                             double* out_host, int64_t out_pitch, int flags);
 
 /*
+ * Several emulators evaluated on the SAME rows by ONE launch.  Replaces the reference's back-to-back calls
+ *   tt.ten_to_predictions_tf(x); te.predictions_tf(x); ee.ten_to_predictions_tf(x)
+ *     (cosmopower/likelihoods/tf_planck2018_lite/tf_planck2018_lite.py:276-278: three emulators, one parameter tensor) and
+ *   10.**(lin.predictions_np(p_lin) + boost.predictions_np(p_boost))
+ *     (cosmopower/trained_models/CP_paper/PK/README.md:62-65: two emulators whose log-spectra are summed).
+ * cpb200_create_multi packs up to 3 emulators (tensor-core format) into one engine; one persistent launch then walks every
+ * pair of row tiles through all of them in turn - each emulator's first layer runs inside the previous emulator's output
+ * phase, so the tensor pipe never waits for a layer-0 epilogue between emulators - and writes each emulator's spectra to
+ * its own buffer.  params_dev[m] is emulator m's (n_rows, n_parameters[m]) array (the pointers may alias when the
+ * emulators share their parameter columns); flags[m] as for cpb200_forward_device.  CPB200_FLAG_ACCUMULATE on emulator
+ * m >= 1 adds its log10 result to what emulator m-1 has just written to the SAME buffer (same n_modes and pitch) before
+ * the optional 10**: the sum is read back from L2 by the lane that wrote it, never from HBM.  Asynchronous on `stream`.
+ */
+int cpb200_create_multi(const cpb200_model_desc* const* descs, int32_t n_models, int device, cpb200_engine** out);
+int cpb200_forward_multi_device(cpb200_engine* e, const float* const* params_dev, int64_t n_rows, float* const* out_dev,
+                                const int64_t* out_pitch, const int32_t* flags, void* stream);
+
+/*
  * The same two calls on several devices of one node from ONE process (rows are independent, every device
  * holds a full engine): `engines` lists one engine of the same model per device; rows are split into contiguous
  * shards (sizes differing by at most one row), one host thread per device - bound to the CPUs next to its GPU - runs the
@@ -184,9 +202,10 @@ int cpb200_engine_debug_counters(cpb200_engine* e, int enable, int64_t* out, int
  * build_jobs) for a network given by its contractions' logical K, N and epilogue kinds (0 activation, 1 affine, 2 output,
  * 3 quadratic form).  Writes up to `capacity` encoded entries (csrc/umma_kernel.cuh um_job_w0 / um_job_w1) and, in `info`
  * (3 + 3 * n_gemms ints): schedule, rot_mul, parity-buffer stages, then k_stages / chunk width / chunks per contraction.
+ * `model` (may be NULL) gives the emulator index of every contraction of a multi-emulator engine.
  * Returns the number of entries or a negative error.  Used by tests/test_job_table.py and tools/schedule_sim.py. */
-int cpb200_debug_job_table(int32_t n_gemms, const int32_t* k, const int32_t* n, const int32_t* epi_kind, int32_t tri,
-                           uint32_t* w0, uint32_t* w1, int32_t capacity, int32_t* info);
+int cpb200_debug_job_table(int32_t n_gemms, const int32_t* k, const int32_t* n, const int32_t* epi_kind, const int32_t* model,
+                           int32_t tri, uint32_t* w0, uint32_t* w1, int32_t capacity, int32_t* info);
 
 /* -------------------------------------------------------------------------------------------------
  * Planck 2018 plik-lite likelihood tail behind the TT / TE / EE emulators.

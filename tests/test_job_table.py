@@ -30,6 +30,13 @@ NETWORKS = {
     "300-4001": ([33, 300], [300, 4001], [ACT, OUT]),
     "narrow tail 512-48-900": ([6, 512, 512, 48], [512, 512, 48, 900], [ACT, ACT, ACT, OUT]),
     "pca 16": ([6, 256, 256, 16], [256, 256, 16, 700], [ACT, ACT, AFFINE, OUT]),
+    # several emulators in one launch (cpb200_create_multi): 4th element = emulator index of every contraction
+    "PKLIN + PKNLBOOST": ([6, 512, 512, 512, 8, 512, 512, 512], [512, 512, 512, 420, 512, 512, 512, 420],
+                          [ACT, ACT, ACT, OUT] * 2, [0] * 4 + [1] * 4),
+    "TT + TE + EE": ([6, 512, 512, 512, 512] + [6, 512, 512, 512, 512, 512] + [6, 512, 512, 512, 512],
+                     [512, 512, 512, 512, 2507] + [512, 512, 512, 512, 512, 199] + [512, 512, 512, 512, 2507],
+                     [ACT] * 4 + [OUT] + [ACT] * 4 + [AFFINE, OUT] + [ACT] * 4 + [OUT], [0] * 5 + [1] * 6 + [2] * 5),
+    "small pair": ([3, 64, 5, 100, 37], [64, 40, 100, 37, 333], [ACT, OUT, ACT, ACT, OUT], [0, 0, 1, 1, 1]),
 }
 
 
@@ -39,16 +46,19 @@ def _buffer(code, pair, info):
     if code & BUF_PAR:
         return ("par", 2 * (pair & 1) + (code & 1))
     if code & BUF_A0:
-        return ("a0", code & 1)
+        return ("a0", code & 0xf)
     return None
 
 
 @pytest.mark.parametrize("name", sorted(NETWORKS))
 def test_job_table_invariants(built_library, name):
-    K, N, kinds = NETWORKS[name]
-    entries, info = _engine.job_table(K, N, kinds)
+    K, N, kinds = NETWORKS[name][:3]
+    models = NETWORKS[name][3] if len(NETWORKS[name]) > 3 else [0] * len(K)
+    entries, info = _engine.job_table(K, N, kinds, models=models)
     G = len(K)
     gem = info["gemms"]
+    layer0 = [g == 0 or models[g] != models[g - 1] for g in range(G)]
+    lastg = [g == G - 1 or models[g + 1] != models[g] for g in range(G)]
     assert len(entries) <= 320
     # ---- every job once, parts contiguous and in order, one slot assignment per job
     jobs = {}
@@ -100,7 +110,7 @@ def test_job_table_invariants(built_library, name):
         if e["last"]:
             last_part_time[key] = tm
     for (pair, g, t, c), tm in first_part_time.items():
-        if g >= 1:
+        if not layer0[g]:
             for pc in range(gem[g - 1][2]):
                 assert last_part_time[(pair, g - 1, t, pc)] < tm, (name, "consumer before producer", pair, g, t, c)
     # barrier ts = 2 * (pair & 1) + t: arrivals by the last chunk's epilogue of a producing contraction, waits by the first
@@ -111,9 +121,9 @@ def test_job_table_invariants(built_library, name):
             if 2 * (pair & 1) + e["t"] != ts:
                 continue
             g = e["g"]
-            if g >= 1 and e["first"] and e["c"] == 0:
+            if not layer0[g] and e["first"] and e["c"] == 0:
                 seq.append((tm - 0.25, "wait", pair, g))             # the loader waits before it loads the part ...
-            if g < G - 1 and e["last"] and e["c"] == gem[g][2] - 1:
+            if not lastg[g] and e["last"] and e["c"] == gem[g][2] - 1:
                 seq.append((tm + 0.25, "arrive", pair, g))           # ... the epilogue arrives after the job's last part
         seq.sort()
         kinds_seq = [k for _, k, _, _ in seq]
@@ -127,10 +137,12 @@ def test_job_table_invariants(built_library, name):
     for tm, pair, pos, e in events:
         g = e["g"]
         rb = _buffer(e["in_code"], pair, info)
-        if g >= 1 and rb is not None:
+        if layer0[g]:
+            assert rb == ("a0", 2 * models[g] + e["t"]), (name, rb)
+        if not layer0[g] and rb is not None:
             assert contents.get(rb) == (pair, g - 1, e["t"]), "%s: pair %d g%d t%d c%d reads %r holding %r" % (
                 name, pair, g, e["t"], e["c"], rb, contents.get(rb))
-        if e["last"] and g < G - 1 and e["c"] == 0:
+        if e["last"] and not lastg[g] and e["c"] == 0:
             # chunk 0 is the first chunk of (g, t) to complete: from its epilogue on, the output buffer is being overwritten
             wb = _buffer(e["out_code"], pair, info)
             assert wb is not None
@@ -145,7 +157,7 @@ def test_job_table_invariants(built_library, name):
 
 
 def test_schedules_chosen_for_the_shipped_models(built_library):
-    sched = {name: _engine.job_table(*NETWORKS[name])[1]["schedule"] for name in NETWORKS}
+    sched = {name: _engine.job_table(*NETWORKS[name][:3])[1]["schedule"] for name in NETWORKS if len(NETWORKS[name]) == 3}
     assert sched["cmb_TT_NN"] == 1 and sched["PKLIN_NN"] == 1 and sched["cmb_TE_PCAplusNN"] == 1      # layer 0 merged into the output jobs
     assert sched["cmb_PP_PCAplusNN"] == 1                  # (the overlapped output phase measured no faster: profiling builds only)
     assert sched["single"] == 0

@@ -454,3 +454,46 @@ def test_single_process_multi_device_equals_one_device():
         assert y2.dtype == y1.dtype and np.array_equal(y1, y2)
         y_all = m.predictions_np({k: v.astype(np.float32) for k, v in d.items()}, devices="all")
         assert y_all.dtype == np.float32 and np.array_equal(y_all, m.predictions_np({k: v.astype(np.float32) for k, v in d.items()}))
+
+
+def test_three_emulators_in_one_launch_equal_three_launches():
+    """TT + TE + EE on the same parameter tensor (the likelihood's call pattern,
+    tf_planck2018_lite.py:276-278) as ONE launch - each element goes through the same arithmetic as in the emulator's own
+    launch, so the three spectra must be bit-identical to the single-emulator calls; ragged and multi-wave batches."""
+    import torch
+    names = ["cmb_TT_NN", "cmb_TE_PCAplusNN", "cmb_EE_NN"]
+    models = [get_model(nm)[0] for nm in names]
+    for n in (1, 300, 5000, 70001):
+        x = torch.from_numpy(priors.sample_prior(models[0].parameters, n, seed=900 + n, dtype=np.float32)).cuda()
+        launches0 = [m.engine().launch_count() for m in models]
+        outs = cp.predictions_multi_tf(models, [x, x, x], ten_to=[True, False, True])
+        assert [m.engine().launch_count() for m in models] == launches0          # none of the single engines ran
+        want = [models[0].ten_to_predictions_tf(x), models[1].predictions_tf(x), models[2].ten_to_predictions_tf(x)]
+        for nm, o, w in zip(names, outs, want):
+            assert o.shape == w.shape and torch.equal(o, w), (nm, n)
+    _, attrs = get_model("cmb_TE_PCAplusNN")
+    x64 = priors.sample_prior(models[0].parameters, 2000, seed=77)
+    outs = cp.predictions_multi_tf(models, [torch.from_numpy(x64.astype(np.float32)).cuda()] * 3, ten_to=[True, False, True])
+    assert parity.model_error("cmb_TE_PCAplusNN", outs[1].cpu().numpy(), oracle_np.forward_pass(attrs, x64)) <= parity.TOL_LINEAR
+
+
+def test_fused_pk_pair_is_one_launch_and_equals_the_two_launch_path():
+    """10**(log P_lin + log boost) (PK/README.md:62-65) through the multi-emulator engine: one launch, the log-sum read back
+    from L2 by the lane that wrote it.  Same bits as the two-launch ACCUMULATE path, oracle parity at 100 000 rows."""
+    import torch
+    lin, a_lin = get_model("PKLIN_NN")
+    nl, a_nl = get_model("PKNLBOOST_NN")
+    for n in (257, 100000):
+        x_nl = priors.sample_prior(nl.parameters, n, seed=321)
+        cols = [nl.parameters.index(k) for k in lin.parameters]
+        xb = torch.from_numpy(x_nl.astype(np.float32)).cuda()
+        xl = torch.from_numpy(np.ascontiguousarray(x_nl[:, cols]).astype(np.float32)).cuda()
+        y = cp.ten_to_sum_predictions_tf([lin, nl], [xl, xb])
+        pitch = 424
+        two = torch.empty((n, pitch), dtype=torch.float32, device="cuda")[:, :420]
+        lin.engine().forward_torch(xl, out=two)
+        nl.engine().forward_torch(xb, out=two, ten_to=True, accumulate=True)
+        assert torch.equal(y, two)
+        rows = np.random.default_rng(1).choice(n, min(n, 3000), replace=False)
+        total_log = oracle_np.forward_pass(a_lin, x_nl[rows][:, cols]) + oracle_np.forward_pass(a_nl, x_nl[rows])
+        assert parity.ten_to_error(y[torch.from_numpy(rows).cuda()].cpu().numpy(), total_log) <= 2 * parity.TOL_LOG
