@@ -410,14 +410,11 @@ class MultiEngine:
             _check(self._lib.cpb200_forward_multi_device(self._h, pp, n, po, pitch, fl, ctypes.c_void_p(stream)))
         return outs
 
-    def launch_count(self):
-        return int(self._lib.cpb200_engine_launch_count(self._h))
-
-    def set_timing(self, enabled):
-        _check(self._lib.cpb200_engine_set_timing(self._h, 1 if enabled else 0))
-
-    def last_kernel_cycles(self):
-        return int(self._lib.cpb200_engine_last_kernel_cycles(self._h))
+    launch_count = Engine.launch_count
+    set_timing = Engine.set_timing
+    debug_counters = Engine.debug_counters
+    last_kernel_cycles = Engine.last_kernel_cycles
+    last_kernel_ms = Engine.last_kernel_ms
 
 
 def forward_host_multi(engines, params, out=None, ten_to=False, dtype=np.float32):

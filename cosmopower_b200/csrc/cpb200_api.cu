@@ -716,13 +716,21 @@ int launch_umma(cpb200_engine* e, const float* const* params, int64_t n, float* 
         }
     }
     const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * p.out_split * cpb::UM_CLUSTER;
-    if (p.out_split > 1) {
-        if (p.counters) cpb::fused_mlp_umma_kernel<true, true><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
-        else cpb::fused_mlp_umma_kernel<false, true><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
-    } else {
-        if (p.counters) cpb::fused_mlp_umma_kernel<true, false><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
-        else cpb::fused_mlp_umma_kernel<false, false><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p);
+    bool acc = false;
+    for (int m = 0; m < e->n_models; ++m) acc = acc || p.m[m].accumulate;
+    const int variant = (p.counters ? 4 : 0) | (p.out_split > 1 ? 2 : 0) | (acc ? 1 : 0);
+#define UM_LAUNCH(PROF, SPLIT, ACC) cpb::fused_mlp_umma_kernel<PROF, SPLIT, ACC><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p)
+    switch (variant) {
+        case 0: UM_LAUNCH(false, false, false); break;
+        case 1: UM_LAUNCH(false, false, true); break;
+        case 2: UM_LAUNCH(false, true, false); break;
+        case 3: UM_LAUNCH(false, true, true); break;
+        case 4: UM_LAUNCH(true, false, false); break;
+        case 5: UM_LAUNCH(true, false, true); break;
+        case 6: UM_LAUNCH(true, true, false); break;
+        default: UM_LAUNCH(true, true, true); break;
     }
+#undef UM_LAUNCH
     ++e->launches;
     CU(cudaGetLastError());
     return 0;
@@ -785,10 +793,9 @@ int setup_umma(cpb200_engine* e) {
         cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
         return (fail(CPB200_E_CUDA, "status block allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
     memset(e->h_status, 0, 4 * sizeof(int));
-    if (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess)
+#define UM_OPT_IN(PROF, SPLIT, ACC) (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<PROF, SPLIT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess)
+    if (UM_OPT_IN(false, false, false) || UM_OPT_IN(false, false, true) || UM_OPT_IN(false, true, false) || UM_OPT_IN(false, true, true) ||
+        UM_OPT_IN(true, false, false) || UM_OPT_IN(true, false, true) || UM_OPT_IN(true, true, false) || UM_OPT_IN(true, true, true))
         return (fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
                          cudaGetErrorString(cudaGetLastError())));
     return 0;

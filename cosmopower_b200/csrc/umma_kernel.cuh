@@ -371,6 +371,9 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 #define UM_EARLY_RELEASE 0    // 1: a two-slot accumulator's first slot is handed back as soon as its columns are drained (measured
                               // on B200: the mid-job fence costs cmb_PP 3.5 % and no schedule in use needs the half accumulator)
 #endif
+#ifndef UM_ACC_HOIST
+#define UM_ACC_HOIST 0
+#endif
 #ifndef UM_RANGE_CHECK
 #define UM_RANGE_CHECK 1      // producers of split operands report values beyond the fp16 range (0: saturate silently)
 #endif
@@ -561,7 +564,10 @@ __device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const f
 // the common case of a half piece - 32-byte stores, every column a mode, every row inside the batch - without a
 // branch: both row groups' 16 values go through each step together (FMA, optional 2**y, two 32-byte stores)
 template <bool TEN_TO, bool ACC>
-__device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], const float2 (&pp)[8], float* d0, float* d1, int dbg) {
+// (ACC: p0 / p1 hold the log10 values already in the output rows - loaded by the caller at the top of the piece, so that
+// the L2 round trip, which queues behind this warp's own streaming stores, is paid once per piece and under the TMEM wait)
+__device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], const float2 (&pp)[8], float* d0, float* d1, int dbg,
+                                                     const float (&p0)[8], const float (&p1)[8]) {
     float y0[8], y1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -570,9 +576,6 @@ __device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], co
     }
     if (ACC) {
         const float ks = TEN_TO ? 3.3219280948873623f : 1.f;
-        float p0[8], p1[8];
-        ldg_v8(d0, p0);
-        ldg_v8(d1, p1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { y0[j] = fmaf(p0[j], ks, y0[j]); y1[j] = fmaf(p1[j], ks, y1[j]); }
     }
@@ -618,13 +621,20 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
         float* drow = orow0 + gc;                                       // row 32q + tq of the tile
         // warp-uniform: 32-byte stores, whole tile inside the batch (vec_mode), whole piece inside the spectrum
         const bool fast = vec_mode == OUT_VEC32 && E.chunk_col0 + pc + UM_PIECE <= n_modes;
+        // ACC: the log10 values already in the rows.  UM_ACC_HOIST: 0 = loaded where they are used (each load queues behind
+        // this warp's streaming stores), 1 = all four rows at the top of the piece, 2 = two at the top, two after the first half
+        float prev[UM_ACC_HOIST == 1 ? 4 : 2][8];
+        if (ACC && fast && UM_ACC_HOIST >= 1) { ldg_v8(drow, prev[0]); ldg_v8(drow + 8 * pitch, prev[1]); }
+        if (ACC && fast && UM_ACC_HOIST == 1) { ldg_v8(drow + 16 * pitch, prev[2]); ldg_v8(drow + 24 * pitch, prev[UM_ACC_HOIST == 1 ? 3 : 1]); }
         tmem_ld_wait16(va);
         tmem_ld_16x256b_x4(t_addr1 + pc, vb);
         if (fast) {
-            epi_output_half_fast<TEN_TO, ACC>(va, pp, drow, drow + 8 * pitch, E.dbg);
+            if (ACC && UM_ACC_HOIST == 0) { ldg_v8(drow, prev[0]); ldg_v8(drow + 8 * pitch, prev[1]); }
+            epi_output_half_fast<TEN_TO, ACC>(va, pp, drow, drow + 8 * pitch, E.dbg, prev[0], prev[1]);
+            if (ACC && UM_ACC_HOIST != 1) { ldg_v8(drow + 16 * pitch, prev[0]); ldg_v8(drow + 24 * pitch, prev[1]); }
             tmem_ld_wait16(vb);
             if (pc + kStep < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
-            epi_output_half_fast<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, drow + 24 * pitch, E.dbg);
+            epi_output_half_fast<TEN_TO, ACC>(vb, pp, drow + 16 * pitch, drow + 24 * pitch, E.dbg, prev[UM_ACC_HOIST == 1 ? 2 : 0], prev[UM_ACC_HOIST == 1 ? 3 : 1]);
             continue;
         }
         const int mode = gc + 8 <= n_modes ? vec_mode : gc < n_modes ? OUT_SCALAR : OUT_NONE;   // OUT_NONE: nothing of this lane's is a mode
@@ -681,7 +691,9 @@ __device__ __forceinline__ void epi_chunk_quadform(const EpiCtx& E, const float*
 // PROF = true instantiates the per-role cycle counters (cpb200_engine_debug_counters); the production
 // instantiation carries no clock reads on the single-thread issue paths
 // SPLIT = true instantiates the small-batch variant (UmmaParams::out_split > 1); the throughput kernel carries none of it
-template <bool PROF, bool SPLIT = false>
+// ACC = true instantiates the output epilogues that add the log10 values already in the output rows (fused sums of
+// emulators); the plain kernel carries none of that either (its register allocation is the epilogue's)
+template <bool PROF, bool SPLIT = false, bool ACC = false>
 __global__ void __cluster_dims__(UM_CLUSTER, 1, 1) __launch_bounds__(UM_THREADS, 1)
 fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 {
@@ -1036,7 +1048,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                                    : ((reinterpret_cast<uintptr_t>(M.out) & 15) | (static_cast<uintptr_t>(M.out_pitch) & 3)) == 0 ? OUT_VEC16 : OUT_SCALAR;
                 // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
                 float* orow0 = M.out + (row0 + q * 32 + tq) * M.out_pitch;
-                if (M.accumulate) {
+                if (ACC && M.accumulate) {
                     if (M.ten_to) epi_chunk_output<true, true>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
                     else epi_chunk_output<false, true>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
                 } else {

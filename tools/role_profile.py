@@ -20,19 +20,30 @@ NAMES = ["load_wait_empty", "load_wait_aready", "load_total", "mma_wait_full", "
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cmb_TT_NN"
     rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
-    kind, path = standins.model_path(name)
-    m = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
-    eng = m.engine()
-    x = torch.from_numpy(priors.sample_prior(m.parameters, rows, seed=1, dtype=np.float32)).cuda()
-    pitch = (m.n_modes + 7) // 8 * 8
-    out = torch.empty((rows, pitch), dtype=torch.float32, device="cuda")[:, :m.n_modes]
+    if name == "PK_PAIR":            # PKLIN + PKNLBOOST in one launch, log-sum fused
+        from cosmopower_b200 import fused
+        ms_ = [getattr(cp, standins.model_path(n)[0])(restore=True, restore_filename=standins.model_path(n)[1], device=0) for n in ("PKLIN_NN", "PKNLBOOST_NN")]
+        eng = fused._multi_engine(ms_, 0)
+        xb = priors.sample_prior(ms_[1].parameters, rows, seed=1, dtype=np.float32)
+        cols = [ms_[1].parameters.index(k) for k in ms_[0].parameters]
+        xs = [torch.from_numpy(np.ascontiguousarray(xb[:, cols])).cuda(), torch.from_numpy(xb).cuda()]
+        out = torch.empty((rows, 424), dtype=torch.float32, device="cuda")[:, :420]
+        run = lambda: eng.forward_torch(xs, outs=[out, out], ten_to=[False, True], accumulate=[False, True])
+    else:
+        kind, path = standins.model_path(name)
+        m = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
+        eng = m.engine()
+        x = torch.from_numpy(priors.sample_prior(m.parameters, rows, seed=1, dtype=np.float32)).cuda()
+        pitch = (m.n_modes + 7) // 8 * 8
+        out = torch.empty((rows, pitch), dtype=torch.float32, device="cuda")[:, :m.n_modes]
+        run = lambda: eng.forward_torch(x, out=out, ten_to=True)
     for _ in range(2):
-        eng.forward_torch(x, out=out, ten_to=True)
+        run()
     torch.cuda.synchronize()
     eng.debug_counters(enable=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    eng.forward_torch(x, out=out, ten_to=True)
+    run()
     e1.record()
     torch.cuda.synchronize()
     c = eng.debug_counters(enable=False, read=True).astype(np.float64)
