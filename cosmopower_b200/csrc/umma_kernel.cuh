@@ -187,6 +187,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Pure event signal: no data written by this thread is published through the barrier.  The default form has release
+// semantics and compiles to MEMBAR.ALL.CTA + SYNCS.ARRIVE: the fence waits until every store the thread has in flight is
+// performed - at the end of an epilogue job that is the whole burst of spectrum / activation stores still queued in the
+// LSU (ncu source view, round 2: 9 % of the cmb_PP launch's warp samples sat on that MEMBAR), and the warp could not
+// start the next job's TMEM loads meanwhile.  Handing back TMEM (its reads completed with tcgen05.wait::ld) or a
+// constants slot (its LDS results are already consumed) needs no such ordering.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -412,7 +421,7 @@ __device__ __forceinline__ void epi_release_first_slot(const EpiCtx& E) {
     tc_fence_before();
     __syncwarp();
     if (E.lane == 0) {
-        if (E.leader) mbar_arrive(E.rel_bar);
+        if (E.leader) mbar_arrive_relaxed(E.rel_bar);
         else mbar_arrive_remote_relaxed(E.rel_bar);        // pure event: the TMEM reads are complete
     }
 }
@@ -1062,13 +1071,13 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             __syncwarp();
             if (lane == 0) {
                 if (E.leader) {
-                    if (!E.rel_bar) mbar_arrive(accempty0 + 8u * slot);
-                    if (two) mbar_arrive(accempty0 + 8u * (slot + 1));
+                    if (!E.rel_bar) mbar_arrive_relaxed(accempty0 + 8u * slot);
+                    if (two) mbar_arrive_relaxed(accempty0 + 8u * (slot + 1));
                 } else {                                                          // TMEM reads are complete (wait::ld)
                     if (!E.rel_bar) mbar_arrive_remote_relaxed(accempty0 + 8u * slot);
                     if (two) mbar_arrive_remote_relaxed(accempty0 + 8u * (slot + 1));
                 }
-                mbar_arrive(bar_parempty(pb));
+                mbar_arrive_relaxed(bar_parempty(pb));
             }
             if (++pb == UM_PAR_SLOTS) pb = 0;
             if (L.epi_kind <= EPI_AFFINE && c == L.n_chunks - 1) {     // operand-producing kinds
