@@ -16,6 +16,7 @@ PREC_FP32_SIMT = 0
 PREC_F16X3 = 1
 FLAG_TEN_TO = 1
 FLAG_ACCUMULATE = 2
+FLAG_BINNED = 4
 PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "f16x3": PREC_F16X3}
 
 _fp = ctypes.POINTER(ctypes.c_float)
@@ -35,7 +36,8 @@ class ModelDesc(ctypes.Structure):
 class PlikDesc(ctypes.Structure):
     _fields_ = [("n_ell", ctypes.c_int32), ("n_bins", ctypes.c_int32), ("n_gather", ctypes.c_int32),
                 ("bin_start", ctypes.POINTER(ctypes.c_int32)), ("gather_first", ctypes.POINTER(ctypes.c_int32)),
-                ("window", _fp), ("x_data", _fp), ("fisher", _fp), ("units_factor", ctypes.c_float), ("te_binned", ctypes.c_int32)]
+                ("window", _fp), ("x_data", _fp), ("fisher", _fp), ("units_factor", ctypes.c_float), ("te_binned", ctypes.c_int32),
+                ("partials", ctypes.c_int32)]
 
 
 # every symbol include/cpb200.h declares: (name, restype, argtypes)
@@ -61,6 +63,8 @@ SYMBOLS = [
     ("cpb200_engine_last_kernel_ms", ctypes.c_float, [ctypes.c_void_p]),
     ("cpb200_engine_last_kernel_cycles", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_engine_set_timing", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    ("cpb200_engine_set_binning", ctypes.c_int, [ctypes.c_void_p, _fp, ctypes.POINTER(ctypes.c_int32)]),
+    ("cpb200_engine_binned_width", ctypes.c_int64, [ctypes.c_void_p]),
     ("cpb200_engine_status", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_int]),
     ("cpb200_engine_debug_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
                                                     ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
@@ -256,15 +260,38 @@ class Engine:
             pass
 
     # -- device-resident path -------------------------------------------------------------
-    def forward_device_ptr(self, params_ptr, n_rows, out_ptr, out_pitch, ten_to=False, stream=0, accumulate=False):
-        flags = (FLAG_TEN_TO if ten_to else 0) | (FLAG_ACCUMULATE if accumulate else 0)
+    def set_binning(self, weight, bin_of_mode):
+        """Attach band-power binning to the output epilogue (cpb200_engine_set_binning): weight[n] = window weight of mode
+        n, bin_of_mode[n] = its bin or -1.  forward_torch(..., ten_to=True, binned=True) then returns the partial band
+        powers (N, binned_width) instead of the spectra."""
+        w = _f32(weight)
+        b = np.ascontiguousarray(bin_of_mode, dtype=np.int32)
+        if w.shape != (self.n_modes,) or b.shape != (self.n_modes,):
+            raise ValueError("weight and bin_of_mode must have n_modes entries")
+        with self._call_lock:
+            _check(self._lib.cpb200_engine_set_binning(self._h, _ptr(w), b.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        self.binned_width = int(self._lib.cpb200_engine_binned_width(self._h))
+
+    def forward_device_ptr(self, params_ptr, n_rows, out_ptr, out_pitch, ten_to=False, stream=0, accumulate=False, binned=False):
+        flags = (FLAG_TEN_TO if ten_to else 0) | (FLAG_ACCUMULATE if accumulate else 0) | (FLAG_BINNED if binned else 0)
         with self._call_lock:
             _check(self._lib.cpb200_forward_device(self._h, ctypes.c_void_p(params_ptr), int(n_rows),
                                                    ctypes.c_void_p(out_ptr), int(out_pitch), flags, ctypes.c_void_p(stream)))
 
-    def forward_torch(self, params, out=None, ten_to=False, accumulate=False):
-        """params: CUDA float32 tensor (N, P) on this engine's device -> CUDA float32 (N, n_modes)."""
+    def forward_torch(self, params, out=None, ten_to=False, accumulate=False, binned=False):
+        """params: CUDA float32 tensor (N, P) on this engine's device -> CUDA float32 (N, n_modes); with binned=True (after
+        set_binning, with ten_to=True) -> (N, binned_width) partial band powers of 10**y."""
         import torch
+        if binned:
+            if not (params.is_cuda and params.dtype == torch.float32 and params.dim() == 2 and params.shape[1] == self.n_parameters
+                    and params.device.index == self.device):
+                raise ValueError("expected a CUDA float32 tensor of shape (N, %d) on device %d" % (self.n_parameters, self.device))
+            params = params.contiguous()
+            n = params.shape[0]
+            out = torch.empty((n, self.binned_width), dtype=torch.float32, device=params.device)
+            stream = torch.cuda.current_stream(params.device).cuda_stream
+            self.forward_device_ptr(params.data_ptr(), n, out.data_ptr(), self.binned_width, ten_to, stream, False, True)
+            return out
         if not (params.is_cuda and params.dtype == torch.float32 and params.dim() == 2
                 and params.shape[1] == self.n_parameters):
             raise ValueError("expected a CUDA float32 tensor of shape (N, %d)" % self.n_parameters)
@@ -450,7 +477,7 @@ def forward_host_multi(engines, params, out=None, ten_to=False, dtype=np.float32
 class PlikEngine:
     """Device-side Planck-lite likelihood tail (cpb200_plik_*): band-power binning + Fisher quadratic form."""
 
-    def __init__(self, n_ell, bin_start, gather_first, window, x_data, fisher, units_factor, device=0, te_binned=False):
+    def __init__(self, n_ell, bin_start, gather_first, window, x_data, fisher, units_factor, device=0, te_binned=False, partials=False):
         lib = load_library()
         self._lib = lib
         self._keep = [np.ascontiguousarray(bin_start, dtype=np.int32), np.ascontiguousarray(gather_first, dtype=np.int32),
@@ -461,8 +488,10 @@ class PlikEngine:
             raise ValueError("inconsistent likelihood tables")
         ip = ctypes.POINTER(ctypes.c_int32)
         desc = PlikDesc(self.n_ell, self.n_bins, int(w.size), bs.ctypes.data_as(ip), gf.ctypes.data_as(ip),
-                        _ptr(w), _ptr(xd), _ptr(f), float(units_factor), 1 if te_binned else 0)
+                        _ptr(w), _ptr(xd), _ptr(f), float(units_factor), 1 if te_binned else 0, 1 if partials else 0)
         self.te_binned = bool(te_binned)
+        self.partials = bool(partials)
+        self.tt_ee_width = 2 * ((self.n_ell + 3) // 4) if partials else self.n_ell
         self.n_te_bins = int(np.sum(gf // self.n_ell == 1))
         h = ctypes.c_void_p()
         _check(lib.cpb200_plik_create(ctypes.byref(desc), self.device, ctypes.byref(h)))
@@ -488,12 +517,12 @@ class PlikEngine:
         Returns loglike (N,) [and the (N, n_bins) model band powers]."""
         import torch
         n = int(cl_tt.shape[0])
-        for t, width in ((cl_tt, self.n_ell), (cl_te, self.n_te_bins if self.te_binned else self.n_ell), (cl_ee, self.n_ell)):
-            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[0] == n and t.shape[1] == width and
+        for t, width in ((cl_tt, self.tt_ee_width), (cl_te, self.n_te_bins if self.te_binned else self.n_ell), (cl_ee, self.tt_ee_width)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[0] == n and t.shape[1] >= width and
                     t.stride(1) == 1 and t.device.index == self.device):
                 raise ValueError("inputs must be CUDA float32 (N, %d) tensors on device %d" % (width, self.device))
-        if cl_tt.stride(0) != cl_ee.stride(0) or (not self.te_binned and cl_te.stride(0) != cl_tt.stride(0)):
-            raise ValueError("the spectra must share one row stride")
+        if cl_tt.stride(0) != cl_ee.stride(0):
+            raise ValueError("the TT and EE inputs must share one row stride")
         cal = cal.to(device=cl_tt.device, dtype=torch.float32).contiguous().reshape(-1)
         if cal.numel() != n:
             raise ValueError("cal must hold one A_planck per row")

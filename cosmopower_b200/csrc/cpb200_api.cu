@@ -71,6 +71,7 @@ struct Gemm {
     bool tri = false;              // upper-triangular weights (quadratic form): chunk c skips the K stages past its columns
     __half* dwpack = nullptr;
     float4* depi = nullptr;
+    float4* depi_b = nullptr;      // binned-output constants (cpb200_engine_set_binning)
 };
 
 constexpr int64_t HOST_CHUNK_BYTES = 128ll << 20;  // output bytes per pipelined host chunk
@@ -666,11 +667,13 @@ int launch_umma(cpb200_engine* e, const float* const* params, int64_t n, float* 
         M.n_modes = e->mModes[m];
         M.ten_to = (flags && (flags[m] & CPB200_FLAG_TEN_TO)) ? 1 : 0;
         M.accumulate = (flags && (flags[m] & CPB200_FLAG_ACCUMULATE)) ? 1 : 0;
+        M.binned = (flags && (flags[m] & CPB200_FLAG_BINNED)) ? 1 : 0;
     }
     for (int i = 0; i < p.n_gemms; ++i) {
         const Gemm& g = e->gemms[i];
         p.g[i].wpack = g.dwpack;
         p.g[i].epi = g.depi;
+        p.g[i].epi_b = g.depi_b;
         p.g[i].k_stages = g.k_stages;
         p.g[i].nc = g.nc;
         p.g[i].n_chunks = g.n_chunks;
@@ -716,19 +719,26 @@ int launch_umma(cpb200_engine* e, const float* const* params, int64_t n, float* 
         }
     }
     const int grid = static_cast<int>(std::min<int64_t>(p.n_pairgroups, max_clusters)) * p.out_split * cpb::UM_CLUSTER;
-    bool acc = false;
-    for (int m = 0; m < e->n_models; ++m) acc = acc || p.m[m].accumulate;
-    const int variant = (p.counters ? 4 : 0) | (p.out_split > 1 ? 2 : 0) | (acc ? 1 : 0);
-#define UM_LAUNCH(PROF, SPLIT, ACC) cpb::fused_mlp_umma_kernel<PROF, SPLIT, ACC><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p)
+    int mode = cpb::UM_MODE_PLAIN;
+    for (int m = 0; m < e->n_models; ++m) {
+        if (p.m[m].binned) mode = cpb::UM_MODE_BINNED;
+        else if (p.m[m].accumulate && mode == cpb::UM_MODE_PLAIN) mode = cpb::UM_MODE_ACC;
+    }
+    const int variant = (p.counters ? 6 : 0) + (p.out_split > 1 ? 3 : 0) + mode;
+#define UM_LAUNCH(PROF, SPLIT, MODE) cpb::fused_mlp_umma_kernel<PROF, SPLIT, MODE><<<grid, cpb::UM_THREADS, cpb::UM_SMEM_BYTES, st>>>(p)
     switch (variant) {
-        case 0: UM_LAUNCH(false, false, false); break;
-        case 1: UM_LAUNCH(false, false, true); break;
-        case 2: UM_LAUNCH(false, true, false); break;
-        case 3: UM_LAUNCH(false, true, true); break;
-        case 4: UM_LAUNCH(true, false, false); break;
-        case 5: UM_LAUNCH(true, false, true); break;
-        case 6: UM_LAUNCH(true, true, false); break;
-        default: UM_LAUNCH(true, true, true); break;
+        case 0: UM_LAUNCH(false, false, 0); break;
+        case 1: UM_LAUNCH(false, false, 1); break;
+        case 2: UM_LAUNCH(false, false, 2); break;
+        case 3: UM_LAUNCH(false, true, 0); break;
+        case 4: UM_LAUNCH(false, true, 1); break;
+        case 5: UM_LAUNCH(false, true, 2); break;
+        case 6: UM_LAUNCH(true, false, 0); break;
+        case 7: UM_LAUNCH(true, false, 1); break;
+        case 8: UM_LAUNCH(true, false, 2); break;
+        case 9: UM_LAUNCH(true, true, 0); break;
+        case 10: UM_LAUNCH(true, true, 1); break;
+        default: UM_LAUNCH(true, true, 2); break;
     }
 #undef UM_LAUNCH
     ++e->launches;
@@ -793,9 +803,10 @@ int setup_umma(cpb200_engine* e) {
         cudaMemset(e->d_max_cycles, 0, sizeof(unsigned long long)) != cudaSuccess)
         return (fail(CPB200_E_CUDA, "status block allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
     memset(e->h_status, 0, 4 * sizeof(int));
-#define UM_OPT_IN(PROF, SPLIT, ACC) (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<PROF, SPLIT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess)
-    if (UM_OPT_IN(false, false, false) || UM_OPT_IN(false, false, true) || UM_OPT_IN(false, true, false) || UM_OPT_IN(false, true, true) ||
-        UM_OPT_IN(true, false, false) || UM_OPT_IN(true, false, true) || UM_OPT_IN(true, true, false) || UM_OPT_IN(true, true, true))
+#define UM_OPT_IN(PROF, SPLIT, MODE) (cudaFuncSetAttribute(cpb::fused_mlp_umma_kernel<PROF, SPLIT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cpb::UM_SMEM_BYTES) != cudaSuccess)
+    if (UM_OPT_IN(false, false, 0) || UM_OPT_IN(false, false, 1) || UM_OPT_IN(false, false, 2) || UM_OPT_IN(false, true, 0) ||
+        UM_OPT_IN(false, true, 1) || UM_OPT_IN(false, true, 2) || UM_OPT_IN(true, false, 0) || UM_OPT_IN(true, false, 1) ||
+        UM_OPT_IN(true, false, 2) || UM_OPT_IN(true, true, 0) || UM_OPT_IN(true, true, 1) || UM_OPT_IN(true, true, 2))
         return (fail(CPB200_E_CUDA, "cannot opt in to %d bytes of shared memory: %s", cpb::UM_SMEM_BYTES,
                          cudaGetErrorString(cudaGetLastError())));
     return 0;
@@ -929,6 +940,7 @@ int cpb200_forward_multi_device(cpb200_engine* e, const float* const* params_dev
         if (!params_dev[m] || !out_dev[m]) return fail(CPB200_E_INVALID, "null buffer for emulator %d", m);
         if (out_pitch[m] < e->mModes[m]) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d (emulator %d)", static_cast<long long>(out_pitch[m]), e->mModes[m], m);
         fl[m] = flags[m];
+        if (flags[m] & CPB200_FLAG_BINNED) return fail(CPB200_E_INVALID, "CPB200_FLAG_BINNED is a single-emulator option");
         if (flags[m] & CPB200_FLAG_ACCUMULATE) {
             // the sum is read back by the very lane that wrote it (same chunking): emulator m adds to what emulator m-1 left in
             // the same buffer, a few microseconds earlier and still in L2
@@ -953,7 +965,7 @@ int cpb200_destroy(cpb200_engine* e) {
     cudaDeviceSynchronize();
     for (auto& g : e->gemms) {
         cudaFree(g.dW); cudaFree(g.dp0); cudaFree(g.dp1); cudaFree(g.dp2);
-        cudaFree(g.dwpack); cudaFree(g.depi);
+        cudaFree(g.dwpack); cudaFree(g.depi); cudaFree(g.depi_b);
     }
     for (int m = 0; m < cpb::UM_MAX_MODELS; ++m) { cudaFree(e->md_pmean[m]); cudaFree(e->md_pstd[m]); }
     cudaFree(e->simt_buf[0]); cudaFree(e->simt_buf[1]);
@@ -980,6 +992,14 @@ int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_r
     if (n_rows == 0) return 0;
     if (!params_dev || !out_dev) return fail(CPB200_E_INVALID, "null buffer");
     if (e->n_models != 1) return fail(CPB200_E_INVALID, "a multi-emulator engine is driven through cpb200_forward_multi_device");
+    if (flags & CPB200_FLAG_BINNED) {
+        const Gemm& last = e->gemms.back();
+        if (e->precision != CPB200_PREC_F16X3 || !last.depi_b) return fail(CPB200_E_INVALID, "CPB200_FLAG_BINNED needs cpb200_engine_set_binning first");
+        if (!(flags & CPB200_FLAG_TEN_TO) || (flags & CPB200_FLAG_ACCUMULATE)) return fail(CPB200_E_INVALID, "CPB200_FLAG_BINNED bins 10**y: it goes with CPB200_FLAG_TEN_TO, without ACCUMULATE");
+        const int64_t need = cpb200_engine_binned_width(e);
+        if (out_pitch < need || (out_pitch & 3) || (reinterpret_cast<uintptr_t>(out_dev) & 15))
+            return fail(CPB200_E_INVALID, "binned output rows are %lld floats; the buffer must be 16-byte aligned with a pitch that is a multiple of 4", static_cast<long long>(need));
+    } else
     if (out_pitch < e->n_modes) return fail(CPB200_E_INVALID, "out_pitch %lld < n_modes %d", static_cast<long long>(out_pitch), e->n_modes);
     DeviceGuard guard(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1300,6 +1320,41 @@ int cpb200_debug_job_table(int32_t n_gemms, const int32_t* k, const int32_t* n, 
 
 int64_t cpb200_engine_launch_count(const cpb200_engine* e) { return e ? e->launches : 0; }
 
+int64_t cpb200_engine_binned_width(const cpb200_engine* e) {
+    if (!e) return 0;
+    return round_up(2 * ((e->n_modes + 3) / 4), 4);
+}
+
+int cpb200_engine_set_binning(cpb200_engine* e, const float* weight, const int32_t* bin_of_mode) {
+    if (!e || !weight || !bin_of_mode) return fail(CPB200_E_INVALID, "null argument");
+    if (e->precision != CPB200_PREC_F16X3 || e->n_models != 1) return fail(CPB200_E_UNSUPPORTED, "binning is fused into single-emulator tensor-core engines");
+    Gemm& g = e->gemms.back();
+    if (g.epi != cpb::EPI_OUT) return fail(CPB200_E_UNSUPPORTED, "the engine has no spectrum output layer");
+    // a group of four multipoles may touch two bins at most (first / second partial of the group), bins ascend with the mode
+    for (int n = 0; n + 1 < g.N; ++n)
+        if (bin_of_mode[n] >= 0 && bin_of_mode[n + 1] >= 0 && bin_of_mode[n + 1] < bin_of_mode[n])
+            return fail(CPB200_E_INVALID, "bins must ascend with the mode index");
+    std::vector<float4> epi(static_cast<size_t>(g.n_chunks) * g.nc, make_float4(0.f, 0.f, 0.f, 0.f));
+    const double l2_10 = 3.321928094887362;
+    for (int g0 = 0; g0 < g.N; g0 += 4) {
+        int first = -1;
+        for (int n = g0; n < std::min(g0 + 4, g.N); ++n) if (bin_of_mode[n] >= 0) { first = bin_of_mode[n]; break; }
+        for (int n = g0; n < std::min(g0 + 4, g.N); ++n) {
+            const int b = bin_of_mode[n];
+            if (b >= 0 && b != first && b != first + 1) return fail(CPB200_E_UNSUPPORTED, "modes %d .. %d touch more than two bins", g0, g0 + 3);
+            const int nb = n & 31, t = nb >> 3, j = nb & 7;
+            float4& dst = epi[(n & ~31) + 4 * j + t];
+            dst.x = static_cast<float>(static_cast<double>(g.p0[n]) * g.acc_scale * l2_10);
+            dst.y = static_cast<float>(static_cast<double>(g.p1[n]) * l2_10);
+            dst.z = (b >= 0 && b == first) ? weight[n] : 0.f;
+            dst.w = (b >= 0 && b == first + 1) ? weight[n] : 0.f;
+        }
+    }
+    DeviceGuard guard(e->device);
+    if (g.depi_b) { cudaDeviceSynchronize(); cudaFree(g.depi_b); g.depi_b = nullptr; }
+    return upload(&g.depi_b, epi.data(), epi.size());
+}
+
 int cpb200_engine_status(cpb200_engine* e, int32_t* watchdog_code, int32_t* range_flag, int clear_range) {
     if (!e) return fail(CPB200_E_INVALID, "null engine");
     volatile int* st = reinterpret_cast<volatile int*>(e->h_status);
@@ -1348,6 +1403,7 @@ struct cpb200_plik {
     int n_ell = 0, n_bins = 0, n_gather = 0, pad = 0, n_jt = 0, num_sms = 0;
     int in_len[3] = {0, 0, 0};          // floats per input row: n_ell, or the TE bin count when TE arrives binned
     bool te_binned = false;
+    bool partials = false;              // TT and EE arrive as per-4-multipole partial band powers
     float units_factor = 0.f;
     cpb::PlikSlot* d_slots = nullptr;   // runs of <= PLIK_SEG consecutive multipoles of one bin (plik_bin_kernel)
     int n_passes = 0;
@@ -1414,7 +1470,21 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     for (int b = 0; b < d->n_bins; ++b)
         if (d->gather_first[b] / d->n_ell == 1) { if (te_bin0 < 0) te_bin0 = b; ++te_bins; }
     if (te_binned && te_bins == 0) return fail(CPB200_E_INVALID, "te_binned set, but no bin gathers from the TE spectrum");
-    const int in_len[3] = {d->n_ell, te_binned ? te_bins : d->n_ell, d->n_ell};
+    const bool partials = d->partials != 0;
+    const int part_len = 2 * ((d->n_ell + 3) / 4);
+    const int in_len[3] = {partials ? part_len : d->n_ell, te_binned ? te_bins : d->n_ell, partials ? part_len : d->n_ell};
+    // partial layout: which of a 4-multipole group's two partials belongs to bin b = is b the first bin the group touches
+    std::vector<int> first_bin_of_group;
+    if (partials) {
+        first_bin_of_group.assign(static_cast<size_t>(3) * ((d->n_ell + 3) / 4), -1);
+        for (int b = 0; b < d->n_bins; ++b) {
+            const int sp = d->gather_first[b] / d->n_ell, lo = d->gather_first[b] % d->n_ell, len = d->bin_start[b + 1] - d->bin_start[b];
+            for (int l = lo; l < lo + len; ++l) {
+                int& fb = first_bin_of_group[static_cast<size_t>(sp) * ((d->n_ell + 3) / 4) + l / 4];
+                if (fb < 0) fb = b;
+            }
+        }
+    }
     const int in_off[3] = {0, round_up(in_len[0], 4), round_up(in_len[0], 4) + round_up(in_len[1], 4)};
     const int row_floats = in_off[2] + round_up(in_len[2], 4);
     std::vector<cpb::PlikSlot> slots;
@@ -1430,6 +1500,32 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
             continue;
         }
         const int len = d->bin_start[b + 1] - d->bin_start[b];
+        if (partials && sp != 1) {
+            // the bin's partials: one per 4-multipole group it touches, at 2 * group + (0: first bin of the group, 1: second);
+            // covered by slots of PLIK_SEG consecutive elements with weight 1 on the bin's own partials
+            std::vector<int> pos;
+            const int ng = (d->n_ell + 3) / 4;
+            for (int gq = lo / 4; gq <= (lo + len - 1) / 4; ++gq) {
+                const int fb = first_bin_of_group[static_cast<size_t>(sp) * ng + gq];
+                if (fb != b && fb + 1 != b) return fail(CPB200_E_UNSUPPORTED, "multipoles %d .. %d touch more than two bins", 4 * gq, 4 * gq + 3);
+                pos.push_back(2 * gq + (fb == b ? 0 : 1));
+            }
+            std::vector<cpb::PlikSlot> mine;
+            for (size_t i = 0; i < pos.size();) {
+                cpb::PlikSlot s = dummy();
+                const int p0 = pos[i];
+                s.off = in_off[sp] + p0;
+                while (i < pos.size() && pos[i] - p0 < cpb::PLIK_SEG) { s.w[pos[i] - p0] = 1.f; s.last = pos[i] - p0; ++i; }
+                mine.push_back(s);
+            }
+            const int nsl = static_cast<int>(mine.size());
+            if (nsl < 1 || nsl > cpb::PLIK_MAX_SLOTS_PER_BIN)
+                return fail(CPB200_E_UNSUPPORTED, "bin %d spans %d partial slots; 1 .. %d are supported", b, nsl, cpb::PLIK_MAX_SLOTS_PER_BIN);
+            while (static_cast<int>(slots.size() % 32) + nsl > 32) slots.push_back(dummy());
+            mine[0].bin = b; mine[0].n_slots = nsl; mine[0].x_data = d->x_data[b]; mine[0].sqrt_f = sqrt_f;
+            for (const cpb::PlikSlot& s : mine) slots.push_back(s);
+            continue;
+        }
         const int ns = (len + cpb::PLIK_SEG - 1) / cpb::PLIK_SEG;
         if (ns < 1 || ns > cpb::PLIK_MAX_SLOTS_PER_BIN)
             return fail(CPB200_E_UNSUPPORTED, "bin %d gathers %d multipoles; 1 .. %d are supported", b, len, cpb::PLIK_SEG * cpb::PLIK_MAX_SLOTS_PER_BIN);
@@ -1458,6 +1554,7 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     p->num_sms = prop.multiProcessorCount;
     p->n_ell = d->n_ell; p->n_bins = d->n_bins; p->n_gather = d->n_gather;
     p->te_binned = te_binned;
+    p->partials = partials;
     for (int i = 0; i < 3; ++i) p->in_len[i] = in_len[i];
     p->units_factor = d->units_factor;
     p->pad = round_up(d->n_bins, cpb::PLIK_QF_BN);
@@ -1542,7 +1639,7 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
     if (n_rows < 0) return fail(CPB200_E_INVALID, "negative row count");
     if (n_rows == 0) return 0;
     if (!cl_tt || !cl_te || !cl_ee || !cal || !loglike) return fail(CPB200_E_INVALID, "null device pointer");
-    if (pitch < p->n_ell) return fail(CPB200_E_INVALID, "pitch %lld < n_ell %d", static_cast<long long>(pitch), p->n_ell);
+    if (pitch < p->in_len[0]) return fail(CPB200_E_INVALID, "pitch %lld < %d floats per TT / EE row", static_cast<long long>(pitch), p->in_len[0]);
     if (te_pitch < p->in_len[1]) return fail(CPB200_E_INVALID, "te_pitch %lld < %d", static_cast<long long>(te_pitch), p->in_len[1]);
     if (binned && binned_pitch < p->n_bins) return fail(CPB200_E_INVALID, "binned_pitch < n_bins");
     DeviceGuard guard(p->device);

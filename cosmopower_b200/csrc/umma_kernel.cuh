@@ -84,6 +84,9 @@ constexpr int UM_SMEM_BYTES = UM_SMEM_TMEMPTR + 16 + 1024;                   // 
 
 struct UmmaGemm {
     const __half* wpack;   // [n_chunks][k_stages][CTA0: hi|lo half tiles][CTA1: hi|lo half tiles], core-matrix order
+    const float4* epi_b;   // last contraction of an emulator with band-power binning attached (cpb200_engine_set_binning): per
+                           // column {scale * log2 10, shift * log2 10, window weight if the column falls into the FIRST bin its
+                           // group of four columns touches, window weight if into the SECOND}, lane-interleaved like ACT
     const float4* epi;     // per padded output column (lane-interleaved inside 32-column blocks):
                            // ACT {b, -alpha*log2e, beta*s, (1-beta)*s}; AFFINE {scale, shift}; OUT {scale, shift, *log2 10}
     int k_stages;          // K_pad / 32
@@ -107,6 +110,8 @@ struct UmmaModel {
     int n_modes;
     int ten_to;
     int accumulate;            // output layers add the log10 values already in `out` before the optional 10**
+    int binned;                // output layers write per-4-column partial band powers of 10**y instead of the spectrum:
+                               // row r, columns 4g .. 4g+3 -> out[r * pitch + 2g + {0, 1}] (first / second bin of the group)
 };
 
 struct UmmaParams {
@@ -656,6 +661,47 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     }
 }
 
+// Band-power binning fused into the output epilogue (Planck-lite likelihood, tf_planck2018_lite.py:281-291: window * C_l,
+// segment sum): a lane's 8 consecutive multipoles are two groups of four, a group touches at most two bins (the narrowest
+// bin is five multipoles wide), so the lane emits four partial sums per row - 16 bytes instead of 32 - in a fixed order;
+// cpb200_plik's binning pass adds a bin's partials, again in a fixed order.  Rows leave the SM at half the bytes and the
+// tail reads half as much.
+__device__ __forceinline__ void epi_binned_half(const uint32_t (&v)[16], const float4 (&pp)[8], float* d0, float* d1, bool ok0, bool ok1) {
+    float pa[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, pb[2][2] = {{0.f, 0.f}, {0.f, 0.f}};          // [row group][column group]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float c0 = ex2_approx(fmaf(__uint_as_float(v[4 * (j >> 1) + (j & 1)]), pp[j].x, pp[j].y));
+        const float c1 = ex2_approx(fmaf(__uint_as_float(v[4 * (j >> 1) + 2 + (j & 1)]), pp[j].x, pp[j].y));
+        pa[0][j >> 2] = fmaf(pp[j].z, c0, pa[0][j >> 2]); pb[0][j >> 2] = fmaf(pp[j].w, c0, pb[0][j >> 2]);
+        pa[1][j >> 2] = fmaf(pp[j].z, c1, pa[1][j >> 2]); pb[1][j >> 2] = fmaf(pp[j].w, c1, pb[1][j >> 2]);
+    }
+    if (ok0) __stcs(reinterpret_cast<float4*>(d0), make_float4(pa[0][0], pb[0][0], pa[0][1], pb[0][1]));
+    if (ok1) __stcs(reinterpret_cast<float4*>(d1), make_float4(pa[1][0], pb[1][0], pa[1][1], pb[1][1]));
+}
+// (orow0: partial row of tile row 32q + tq; the buffer must be 16-byte aligned with a pitch that is a multiple of 4 floats)
+__device__ __forceinline__ void epi_chunk_binned(const EpiCtx& E, float* orow0, long long pitch, long long rows_left, int n_modes) {
+    const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
+    const int kStep = (UM_EPI_WARPS / 4) * UM_PIECE;
+    int pc = E.cw * UM_PIECE;
+    const int nc_valid = min(E.nc, n_modes - E.chunk_col0);
+    const int row_in_q = E.q * 32 + E.tq;
+    uint32_t va[16], vb[16];
+    if (pc < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc, va);
+    for (; pc < nc_valid; pc += kStep) {
+        float4 pp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pp[j] = E.par[pc + 4 * j + E.tr];
+        const int gc = E.chunk_col0 + pc + 8 * E.tr;                       // this lane's first multipole: partials at gc / 2
+        float* drow = orow0 + (gc >> 1);
+        tmem_ld_wait16(va);
+        tmem_ld_16x256b_x4(t_addr1 + pc, vb);
+        epi_binned_half(va, pp, drow, drow + 8 * pitch, row_in_q < rows_left && gc < n_modes, row_in_q + 8 < rows_left && gc < n_modes);
+        tmem_ld_wait16(vb);
+        if (pc + kStep < nc_valid) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
+        epi_binned_half(vb, pp, drow + 16 * pitch, drow + 24 * pitch, row_in_q + 16 < rows_left && gc < n_modes, row_in_q + 24 < rows_left && gc < n_modes);
+    }
+}
+
 // quadratic form: partial[row] = sum over this warp's columns of acc[row][col] * d[row][col], where d is the fp32 copy
 // of the operand rows (the contraction's own A operand).  Columns follow the operand packing: a lane owns 8 consecutive
 // logical columns, so d is read 32 bytes at a time, four lanes covering a 128-byte line of a row.
@@ -700,9 +746,11 @@ __device__ __forceinline__ void epi_chunk_quadform(const EpiCtx& E, const float*
 // PROF = true instantiates the per-role cycle counters (cpb200_engine_debug_counters); the production
 // instantiation carries no clock reads on the single-thread issue paths
 // SPLIT = true instantiates the small-batch variant (UmmaParams::out_split > 1); the throughput kernel carries none of it
-// ACC = true instantiates the output epilogues that add the log10 values already in the output rows (fused sums of
-// emulators); the plain kernel carries none of that either (its register allocation is the epilogue's)
-template <bool PROF, bool SPLIT = false, bool ACC = false>
+// MODE = 1 (UM_MODE_ACC) instantiates the output epilogues that add the log10 values already in the output rows (fused sums
+// of emulators), MODE = 2 (UM_MODE_BINNED) the ones that write partial band powers; the plain kernel (MODE = 0) carries
+// neither (its register allocation is the epilogue's)
+enum { UM_MODE_PLAIN = 0, UM_MODE_ACC = 1, UM_MODE_BINNED = 2 };
+template <bool PROF, bool SPLIT = false, int MODE = UM_MODE_PLAIN>
 __global__ void __cluster_dims__(UM_CLUSTER, 1, 1) __launch_bounds__(UM_THREADS, 1)
 fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
 {
@@ -836,9 +884,11 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     w_empty += mbar_wait(bar_parempty(pb), (ph_parempty >> pb) & 1, P.error_flag, 104); ph_parempty ^= 1u << pb;
                     // operand layers: one float4 per column; output layers: {scale, shift} pairs, two columns per
                     // float4, in two variants (plain, then pre-multiplied by log2(10) for ten_to)
-                    const bool is_out = L.epi_kind == EPI_OUT;
+                    const bool is_binned = MODE == UM_MODE_BINNED && L.epi_kind == EPI_OUT && P.m[L.model].binned;
+                    const bool is_out = L.epi_kind == EPI_OUT && !is_binned;
                     const uint32_t par_bytes = is_out ? L.nc * 8u : L.nc * 16u;
-                    const float4* par_src = is_out ? L.epi + (P.m[L.model].ten_to ? L.n_chunks * (L.nc / 2) : 0) + c * (L.nc / 2) : L.epi + c * L.nc;
+                    const float4* par_src = is_binned ? L.epi_b + c * L.nc
+                                          : is_out ? L.epi + (P.m[L.model].ten_to ? L.n_chunks * (L.nc / 2) : 0) + c * (L.nc / 2) : L.epi + c * L.nc;
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bar_parfull(pb), par_bytes);
                         bulk_g2s(base + UM_SMEM_EPIPAR + pb * (UM_MAX_NC * 16), par_src, par_bytes, bar_parfull(pb));
@@ -1057,7 +1107,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                                    : ((reinterpret_cast<uintptr_t>(M.out) & 15) | (static_cast<uintptr_t>(M.out_pitch) & 3)) == 0 ? OUT_VEC16 : OUT_SCALAR;
                 // row handled by fragment slot (h, rr): row0 + 32q + 16h + 8rr + tq
                 float* orow0 = M.out + (row0 + q * 32 + tq) * M.out_pitch;
-                if (ACC && M.accumulate) {
+                if (MODE == UM_MODE_BINNED && M.binned) {
+                    epi_chunk_binned(E, orow0, M.out_pitch, P.n_rows - row0, M.n_modes);
+                } else if (MODE == UM_MODE_ACC && M.accumulate) {
                     if (M.ten_to) epi_chunk_output<true, true>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
                     else epi_chunk_output<false, true>(E, orow0, M.out_pitch, vec_mode, P.n_rows - row0, M.n_modes);
                 } else {

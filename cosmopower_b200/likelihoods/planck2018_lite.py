@@ -119,7 +119,7 @@ class _Prior:
 class tf_planck2018_lite:
     def __init__(self, parameters=None, tf_planck2018_lite_path=None, spectra="TTTEEE", use_low_ell_bins=False,
                  units_factor=(2.7255e6) ** 2, tt_emu_model=None, te_emu_model=None, ee_emu_model=None, device=None,
-                 chunk_rows=262144, fold_te=True, cuda_graphs=False):
+                 chunk_rows=262144, fold_te=True, cuda_graphs=False, fuse_binning=True):
         self.parameters = parameters
         self.priors = _Prior(parameters) if parameters is not None else None
         self.spectra = spectra
@@ -187,8 +187,23 @@ class tf_planck2018_lite:
             folded = fold_binning_into_pca_emulator(te_emu_model._attrs(), first, start, self.window_ttteee.reshape(-1),
                                                     self.nbintt, self.nbinte, n_ell)
             self._te_binned = _engine.Engine(folded, device=self.device, precision=getattr(te_emu_model, "_precision", "f16x3"))
+        # fuse_binning=True (the default when TT and EE are tensor-core NN emulators): the window weights are applied and the
+        # multipoles summed into per-4-multipole partial band powers inside the emulators' output epilogues
+        # (cpb200_engine_set_binning): 5 KB per spectrum row leave the SM instead of 10 KB and the tail adds partials.
+        self._binned = False
+        if fuse_binning and all(hasattr(m, "engine") and getattr(m, "_precision", "") == "f16x3" and not hasattr(m, "pca_transform_matrix_")
+                                for m in (tt_emu_model, ee_emu_model)):
+            w = self.window_ttteee.reshape(-1)
+            for m, b0, nb, off in ((tt_emu_model, 0, self.nbintt, 0), (ee_emu_model, self.nbintt + self.nbinte, self.nbinee, 2 * n_ell)):
+                weight, bin_of = np.zeros(n_ell, np.float32), np.full(n_ell, -1, np.int32)
+                for b in range(b0, b0 + nb):
+                    lo, ln = int(first[b]) - off, int(start[b + 1] - start[b])
+                    weight[lo:lo + ln] = w[start[b]:start[b + 1]]
+                    bin_of[lo:lo + ln] = b - b0
+                m.engine(self.device).set_binning(weight, bin_of)
+            self._binned = True
         self._engine = _engine.PlikEngine(n_ell, start, first, self.window_ttteee.reshape(-1), x_data, self.fisher,
-                                          units_factor, device=self.device, te_binned=self._te_binned is not None)
+                                          units_factor, device=self.device, te_binned=self._te_binned is not None, partials=self._binned)
 
     # ===== INVERSE COVARIANCE ======  (:206-230)
     def get_inverse_covmat(self, cov):
@@ -210,19 +225,25 @@ class tf_planck2018_lite:
         small-batch mode), so the three launches go to three streams and share the device instead of queueing."""
         import torch
         te = (lambda: self._te_binned.forward_torch(x, ten_to=False)) if self._te_binned is not None else (lambda: self.te_emu_model.predictions_tf(x))
+        if self._binned:
+            tt = lambda: self.tt_emu_model.engine(self.device).forward_torch(x, ten_to=True, binned=True)
+            ee = lambda: self.ee_emu_model.engine(self.device).forward_torch(x, ten_to=True, binned=True)
+        else:
+            tt = lambda: self.tt_emu_model.ten_to_predictions_tf(x)
+            ee = lambda: self.ee_emu_model.ten_to_predictions_tf(x)
         if x.shape[0] > self.concurrent_rows:
-            return self.tt_emu_model.ten_to_predictions_tf(x), te(), self.ee_emu_model.ten_to_predictions_tf(x)
+            return tt(), te(), ee()
         main = torch.cuda.current_stream(x.device)
         if self._side_streams is None:
             self._side_streams = [torch.cuda.Stream(device=x.device), torch.cuda.Stream(device=x.device)]
         s1, s2 = self._side_streams
         s1.wait_stream(main)                       # x is ready
         s2.wait_stream(main)
-        cl_tt = self.tt_emu_model.ten_to_predictions_tf(x)
+        cl_tt = tt()
         with torch.cuda.stream(s1):
             cl_te = te()
         with torch.cuda.stream(s2):
-            cl_ee = self.ee_emu_model.ten_to_predictions_tf(x)
+            cl_ee = ee()
         main.wait_stream(s1)
         main.wait_stream(s2)
         if not torch.cuda.is_current_stream_capturing():

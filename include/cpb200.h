@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CPB200_ABI_VERSION 2
+#define CPB200_ABI_VERSION 3
 
 /* error codes */
 #define CPB200_OK            0
@@ -44,6 +44,9 @@ extern "C" {
 #define CPB200_FLAG_ACCUMULATE 2  /* device path only: add the log10 values already in out_dev before the optional
                                      10**x - fuses `10.**(lin.predictions_np(p) + boost.predictions_np(q))`
                                      (reference cosmopower/trained_models/CP_paper/PK/README.md:62-65)        */
+
+#define CPB200_FLAG_BINNED     4  /* device path, with TEN_TO, after cpb200_engine_set_binning: write partial band powers of
+                                     10**y instead of the spectrum (see cpb200_engine_set_binning)                          */
 
 typedef struct cpb200_engine cpb200_engine;
 
@@ -160,6 +163,21 @@ int cpb200_forward_host_multi(cpb200_engine* const* engines, int32_t n_engines, 
 int cpb200_forward_host_multi_f64(cpb200_engine* const* engines, int32_t n_engines, const float* params_host, int64_t n_rows,
                                   double* out_host, int64_t out_pitch, int flags);
 
+/*
+ * Band-power binning fused into the emulator's output epilogue.  Replaces, for one spectrum, the gather * window and
+ * segment sum of the reference likelihood (tf_planck2018_lite.py:281-291; tables :126-202) at the point where the
+ * spectrum leaves the tensor core.  `weight[n]` is the window weight of mode n and `bin_of_mode[n]` its bin (-1: in no
+ * bin); bins ascend with n and a group of four consecutive modes touches at most two bins (plik-lite's narrowest bin is
+ * five multipoles wide).  A later cpb200_forward_device call with CPB200_FLAG_TEN_TO | CPB200_FLAG_BINNED writes, per
+ * row, cpb200_engine_binned_width() floats instead of n_modes: for every group g of four modes the two partial sums
+ *   out[row][2g]   = sum of weight[n] * 10**y[n] over the group's modes that fall into the FIRST bin the group touches,
+ *   out[row][2g+1] = the same for the SECOND bin
+ * (fixed order; half the bytes of the spectrum).  cpb200_plik objects created with `partials` set consume that layout.
+ * The output buffer must be 16-byte aligned with a row pitch that is a multiple of 4 floats.
+ */
+int cpb200_engine_set_binning(cpb200_engine* e, const float* weight, const int32_t* bin_of_mode);
+int64_t cpb200_engine_binned_width(const cpb200_engine* e);
+
 /* Pinned host memory for zero-bounce cpb200_forward_host calls. */
 int cpb200_host_alloc(void** ptr, uint64_t bytes);
 int cpb200_host_free(void* ptr);
@@ -232,6 +250,10 @@ typedef struct {
     int32_t te_binned;          /* != 0: the TE input of cpb200_plik_loglike_device holds that spectrum's band powers (bins
                                    215 .. 413 of the vector, before units and calibration) instead of multipoles - for a TE
                                    emulator whose linear PCA basis was folded with the window functions on the host */
+    int32_t partials;           /* != 0: the TT and EE inputs hold the partial band powers written by emulators with
+                                   cpb200_engine_set_binning + CPB200_FLAG_BINNED (2 * ceil(n_ell / 4) floats per row, pitch
+                                   `pitch` of cpb200_plik_loglike_device) instead of multipoles: the binning pass then only
+                                   adds a bin's partials */
 } cpb200_plik_desc;
 
 int cpb200_plik_create(const cpb200_plik_desc* desc, int32_t device, cpb200_plik** out);

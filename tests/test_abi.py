@@ -27,7 +27,7 @@ def test_header_symbols_are_all_bound_and_exported(built_library):
 
 
 def test_abi_version(built_library):
-    assert built_library.cpb200_abi_version() == 2
+    assert built_library.cpb200_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device(built_library):

@@ -35,21 +35,29 @@ def main():
         models[key] = getattr(cp, kind)(restore=True, restore_filename=path, device=0)
     params = list(models["tt"].parameters)
     fold = os.environ.get("CPB200_FOLD_TE", "1") != "0"
-    like = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"], fold_te=fold)
+    fuse = os.environ.get("CPB200_FUSE_BINNING", "1") != "0"
+    like = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"], fold_te=fold,
+                              fuse_binning=fuse)
     x = priors.sample_prior(params, rows, seed=5, dtype=np.float32)
     full = torch.from_numpy(np.concatenate([x, np.ones((rows, 1), np.float32)], axis=1)).cuda()
     cosmo = full[:, :len(params)].contiguous()
-    cl_tt = models["tt"].ten_to_predictions_tf(cosmo)
+    if like._binned:      # TT / EE leave their emulators as per-4-multipole partial band powers
+        tt = lambda: models["tt"].engine(0).forward_torch(cosmo, ten_to=True, binned=True)
+        ee = lambda: models["ee"].engine(0).forward_torch(cosmo, ten_to=True, binned=True)
+    else:
+        tt = lambda: models["tt"].ten_to_predictions_tf(cosmo)
+        ee = lambda: models["ee"].ten_to_predictions_tf(cosmo)
+    cl_tt = tt()
     te = (lambda: like._te_binned.forward_torch(cosmo, ten_to=False)) if fold else (lambda: models["te"].predictions_tf(cosmo))
     cl_te = te()
-    cl_ee = models["ee"].ten_to_predictions_tf(cosmo)
+    cl_ee = ee()
     cal = full[:, -1].contiguous()
     ms_tail = timed(lambda: like._engine.loglike_torch(cl_tt, cl_te, cl_ee, cal))
-    ms_emu = timed(lambda: (models["tt"].ten_to_predictions_tf(cosmo), te(), models["ee"].ten_to_predictions_tf(cosmo)))
+    ms_emu = timed(lambda: (tt(), te(), ee()))
     ms_all = timed(lambda: like.get_loglkl(full))
-    n_ell, nb = 2507, 613
+    n_ell, nb = like._engine.tt_ee_width, 613
     te_len = cl_te.shape[1]
-    out = {"rows": rows, "fold_te": fold, "likelihood_tail_ms": ms_tail, "three_emulators_ms": ms_emu, "get_loglkl_ms": ms_all,
+    out = {"rows": rows, "fold_te": fold, "fuse_binning": bool(like._binned), "likelihood_tail_ms": ms_tail, "three_emulators_ms": ms_emu, "get_loglkl_ms": ms_all,
            "tail_hbm_gbs": rows * (2 * n_ell + te_len + 2 * 640) * 4 / ms_tail / 1e6,
            "tail_quadform_tflops_dense_equiv": rows * 2.0 * nb * nb / ms_tail / 1e9,
            "loglike_per_s": rows / ms_all * 1e3}
