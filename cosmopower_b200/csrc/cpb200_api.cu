@@ -251,11 +251,15 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
         }
     }
     // Epilogue constants, stored in the order the epilogue lanes read them: inside each 32-column block lane
-    // group t (= lane & 3) owns the 8 logical columns 8t..8t+7.  Operand-producing layers: one float4 per column,
-    // the group's j-th column at position 4j + t.  Output layers: {scale, shift} pairs, two columns per float4,
-    // the group's m-th pair (columns 8t+2m, 8t+2m+1) at position 4m + t of the block's 16 float4; the whole
-    // array once for predictions and once more multiplied by log2(10) for 10**y = 2**(y*log2 10).
+    // group t (= lane & 3) owns the 8 logical columns 8t..8t+7 as four column pairs i (columns 8t+2i, 8t+2i+1), and
+    // every constant is stored per pair so that the epilogue's packed fp32 instructions (FFMA2 ...) find both
+    // columns' values in one aligned register pair.  Operand-producing layers: two float4 per pair at positions
+    // 4(2i) + t and 4(2i+1) + t of the block's 32 - ACT {b0, b1, a0, a1} and {c0, c1, d0, d1} (a = -alpha*log2e,
+    // c = beta*s, d = (1-beta)*s), AFFINE {scale0, scale1, shift0, shift1} in the first.  Output layers: one float4
+    // {scale0, scale1, shift0, shift1} per pair at position 4i + t of the block's 16; the whole array once for
+    // predictions and once more multiplied by log2(10) for 10**y = 2**(y*log2 10).
     std::vector<float4> epi;
+    auto put = [](float4& q, int cc, float lo, float hi) { if (cc) { q.y = lo; q.w = hi; } else { q.x = lo; q.z = hi; } };
     if (g.epi == cpb::EPI_OUT) {
         const size_t per_variant = static_cast<size_t>(g.n_chunks) * (g.nc / 2);
         epi.assign(2 * per_variant, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -266,23 +270,22 @@ int pack_umma(Gemm& g, int k_pad, float s_in, float s_out) {
             const float sc = g.p0[n] * inv, sh = g.p1[n];
             const float sc10 = static_cast<float>(static_cast<double>(g.p0[n]) * inv * l2_10);
             const float sh10 = static_cast<float>(static_cast<double>(g.p1[n]) * l2_10);
-            float4& a = epi[idx];
-            float4& b10 = epi[per_variant + idx];
-            if (n & 1) { a.z = sc; a.w = sh; b10.z = sc10; b10.w = sh10; }
-            else { a.x = sc; a.y = sh; b10.x = sc10; b10.y = sh10; }
+            put(epi[idx], n & 1, sc, sh);
+            put(epi[per_variant + idx], n & 1, sc10, sh10);
         }
     } else {
         epi.assign(static_cast<size_t>(g.n_chunks) * g.nc, make_float4(0.f, 0.f, 0.f, 0.f));
         for (int n = 0; n < g.N; ++n) {
-            const int nb = n & 31, t = nb >> 3, j = nb & 7;
-            float4& dst = epi[(n & ~31) + 4 * j + t];
+            const int nb = n & 31, t = nb >> 3, i = (nb & 7) >> 1, cc = nb & 1;
+            float4& qa = epi[(n & ~31) + 4 * (2 * i) + t];
+            float4& qb = epi[(n & ~31) + 4 * (2 * i + 1) + t];
             if (g.epi == cpb::EPI_ACT) {
                 const float alpha = g.p1[n], beta = g.p2[n];
                 // a = acc*acc_scale + b;  h*s_out = ((1-beta)*s_out * sigmoid + beta*s_out) * a
-                dst = make_float4(g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634),
-                                  beta * s_out, (1.f - beta) * s_out);
+                put(qa, cc, g.p0[n], static_cast<float>(-static_cast<double>(alpha) * 1.4426950408889634));
+                put(qb, cc, beta * s_out, (1.f - beta) * s_out);
             } else if (g.epi == cpb::EPI_AFFINE) {
-                dst = make_float4(g.p0[n] * inv * s_out, g.p1[n] * s_out, 0.f, 0.f);
+                put(qa, cc, g.p0[n] * inv * s_out, g.p1[n] * s_out);
             }                                   // EPI_QUADFORM: no per-column constants
         }
     }

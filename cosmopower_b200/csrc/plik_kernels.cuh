@@ -42,11 +42,12 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
 }
 
-// fp16 hi/lo split of two floats (same arithmetic as the fused kernel's split2)
+// fp16 hi / -lo split of two floats (same values as the fused kernel's split2n: its A operand tiles hold the lo part
+// negated, the tensor core's negate-A bit takes the sign back)
 __device__ __forceinline__ void plik_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    const __half2 l = __floats2half2_rn(hf.x - a, hf.y - b);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }

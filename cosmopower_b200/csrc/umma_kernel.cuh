@@ -5,7 +5,8 @@
 // de-standardisation, 10**x).  Every dense contraction runs on the 5th-gen tensor cores
 // (tcgen05.mma.cta_group::2 kind::f16, M = 256 across the pair, N <= 256, fp32 accumulators in each
 // CTA's TMEM) as a 3-product fp16 split:
-//     A.W  ~=  A_hi.W_hi + A_lo.W_hi + A_hi.W_lo      (x_hi = fp16(x), x_lo = fp16(x - x_hi))
+//     A.W  ~=  A_hi.W_hi + A_lo.W_hi + A_hi.W_lo      (x_hi = fp16(x), x_lo = fp16(x - x_hi); the A tiles hold -A_lo and the
+//                                                      middle product is issued with the negate-A descriptor bit)
 // which keeps ~22 significand bits per operand (single-pass bf16/tf32 miss the 1e-5 tolerance,
 // SURVEY 7.2).
 //
@@ -120,7 +121,7 @@ struct UmmaParams {
     int n_models;
     UmmaModel m[UM_MAX_MODELS];
     int discard_ok;            // every operand-producing contraction has a chunk width that is a multiple of 64 (see the epilogue's discard)
-    int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM (results are garbage)
+    int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM, 64 = no MMAs, 128 = no operand copies, 256 = no discards (results are garbage)
     long long n_rows;
     long long n_pairs;         // ceil(n_tiles / 2)
     long long n_pairgroups;    // ceil(n_pairs / UM_CLUSTER): one pair per CTA of a cluster, processed in lockstep
@@ -365,6 +366,7 @@ __device__ __forceinline__ uint32_t a_tile_off(int r, int kchunk) {
 __device__ __forceinline__ uint32_t umma_idesc(int nc) {
     return (1u << 4) | (static_cast<uint32_t>(nc >> 3) << 17) | (static_cast<uint32_t>((UM_CLUSTER * UM_TILE_M) >> 4) << 24);
 }
+constexpr uint32_t UM_IDESC_NEG_A = 1u << 13;     // negate the A operand: the lo halves of the A tiles are stored negated (split2n)
 
 // split two floats into fp16 hi and lo parts (hi = rn(x), lo = rn(x - hi)), packed as half2.  The conversions
 // saturate (F2FP.SATFINITE, same cost as the plain form): a value beyond the fp16 range becomes +-65504 instead of
@@ -376,10 +378,49 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));   // first source -> upper half
     return h;
 }
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    hi = pack_f16x2_sat(a, b);
-    float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi));
-    lo = pack_f16x2_sat(a - hf.x, b - hf.y);
+// Packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 work on an aligned 64-bit register pair): the epilogues are bound by
+// instruction issue next to the special-function unit, and a pair instruction does two lanes' worth of work per slot.
+__device__ __forceinline__ uint64_t pk2(float x, float y) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& x, float& y) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// Split two floats into fp16 hi and the NEGATED lo part, packed as half2 pairs: hi = rn(x), nlo = rn(hi - x).
+// `sub.f32.f16` (sm_100 mixed-precision add: SASS FHADD) widens the half operand inside the instruction, so the
+// residual costs one instruction per value instead of an unpack and a subtract; the difference hi - x is exact in
+// fp32.  The tensor core takes the sign back: the A_lo product is issued with the descriptor's negate-A bit
+// (umma_idesc | UM_IDESC_NEG_A), so every A operand tile in scratch holds [hi | -lo].
+__device__ __forceinline__ void split2n(float a, float b, uint32_t& hi, uint32_t& nlo) {
+    asm("{\n\t.reg .b16 l, u;\n\t.reg .f32 n0, n1;\n\t"
+        "cvt.rn.satfinite.f16x2.f32 %0, %3, %2;\n\t"      // first source -> upper half
+        "mov.b32 {l, u}, %0;\n\t"
+        "sub.rn.f32.f16 n0, l, %2;\n\t"
+        "sub.rn.f32.f16 n1, u, %3;\n\t"
+        "cvt.rn.satfinite.f16x2.f32 %1, n1, n0;\n\t}"
+        : "=&r"(hi), "=r"(nlo) : "f"(a), "f"(b));
+}
+__device__ __forceinline__ void split2n(uint64_t ab, uint32_t& hi, uint32_t& nlo) {
+    float a, b;
+    upk2(ab, a, b);
+    split2n(a, b, hi, nlo);
 }
 #ifndef UM_EARLY_RELEASE
 #define UM_EARLY_RELEASE 0    // 1: a two-slot accumulator's first slot is handed back as soon as its columns are drained (measured
@@ -387,6 +428,9 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 #endif
 #ifndef UM_ACC_HOIST
 #define UM_ACC_HOIST 0
+#endif
+#ifndef UM_EPI_INLINE
+#define UM_EPI_INLINE __forceinline__
 #endif
 #ifndef UM_RANGE_CHECK
 #define UM_RANGE_CHECK 1      // producers of split operands report values beyond the fp16 range (0: saturate silently)
@@ -435,54 +479,70 @@ __device__ __forceinline__ void epi_release_first_slot(const EpiCtx& E) {
 // be issued into it while this epilogue continues.
 
 // hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
-// contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
+// contraction's A operand, split into fp16 hi / -lo, in the swizzled K-major tile layout.
 // One half piece = 16 TMEM lanes (rows tq, tq+8 of this warp's lower or upper 16 rows) x 32 accumulator columns:
-// v[4i + 2rr + cc] = (row 8rr + tq, lane value j = 2i + cc).
-// both row groups (rr = 0, 1) of the half piece walk the activation stage by stage together: 16 independent chains,
-// so the special-function unit always has a queued instruction while the FMA pipe works on the other stages
+// (v[4i + 2rr], v[4i + 2rr + 1]) = row 8rr + tq, the lane's logical columns 2i, 2i + 1 - an aligned register pair, so
+// the whole chain runs on packed fp32 pairs.  Constants per column pair i: pa[i] = {b0, b1, a0, a1} (bias,
+// -alpha*log2e), pb[i] = {c0, c1, d0, d1} (beta*s, (1-beta)*s); EPI_AFFINE: pa[i] = {scale0, scale1, shift0, shift1}.
+// All eight pairs of the half piece walk the activation stage by stage together: 16 independent chains, so the
+// special-function unit always has a queued instruction while the FMA pipe works on the other stages.
 template <int KIND>
-__device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const float4 (&pp)[8], float acc_scale,
+__device__ __forceinline__ void epi_operand_half(const uint32_t (&v)[16], const float4 (&pa)[4], const float4 (&pb)[4], uint64_t scale2,
                                                  uint8_t* dst, uint64_t pol_keep, int dbg, int* status) {
-    float hv[16];                                  // hv[8rr + j]
+    uint64_t h[8];                                  // h[2i + rr]
     if (KIND == EPI_ACT) {
-        float z[16], e[16];
+        uint64_t z[8];
+        float e[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const int rr = i >> 3, j = i & 7; z[i] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), acc_scale, pp[j].x); }
+        for (int p = 0; p < 8; ++p) {
+            const int i = p >> 1, rr = p & 1;
+            z[p] = ffma2(pk2(__uint_as_float(v[4 * i + 2 * rr]), __uint_as_float(v[4 * i + 2 * rr + 1])), scale2, pk2(pa[i].x, pa[i].y));
+        }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) e[i] = ex2_approx(z[i] * pp[i & 7].y);
+        for (int p = 0; p < 8; ++p) upk2(fmul2(z[p], pk2(pa[p >> 1].z, pa[p >> 1].w)), e[2 * p], e[2 * p + 1]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) e[i] = rcp_approx(1.f + e[i]);
+        for (int k = 0; k < 16; ++k) e[k] = ex2_approx(e[k]);
+        const uint64_t one2 = pk2(1.f, 1.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hv[i] = fmaf(pp[i & 7].w, e[i], pp[i & 7].z) * z[i];
+        for (int p = 0; p < 8; ++p) upk2(fadd2(pk2(e[2 * p], e[2 * p + 1]), one2), e[2 * p], e[2 * p + 1]);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = rcp_approx(e[k]);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int i = p >> 1;
+            h[p] = fmul2(ffma2(pk2(pb[i].z, pb[i].w), pk2(e[2 * p], e[2 * p + 1]), pk2(pb[i].x, pb[i].y)), z[p]);
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const int rr = i >> 3, j = i & 7; hv[i] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), pp[j].x, pp[j].y); }
+        for (int p = 0; p < 8; ++p) {
+            const int i = p >> 1, rr = p & 1;
+            h[p] = ffma2(pk2(__uint_as_float(v[4 * i + 2 * rr]), __uint_as_float(v[4 * i + 2 * rr + 1])), pk2(pa[i].x, pa[i].y), pk2(pa[i].z, pa[i].w));
+        }
     }
     if (UM_RANGE_CHECK) {
-        // one FMNMX per value on the otherwise idle ALU pipe; NaN cannot occur (exp overflow gives sigma = 0)
-        float m = fabsf(hv[0]);
+        // one FMNMX3 per pair on the otherwise idle ALU pipe; NaN cannot occur (exp overflow gives sigma = 0)
+        float m = 0.f;
 #pragma unroll
-        for (int i = 1; i < 16; ++i) m = fmaxf(m, fabsf(hv[i]));
+        for (int p = 0; p < 8; ++p) { float x, y; upk2(h[p], x, y); m = fmaxf(m, fmaxf(fabsf(x), fabsf(y))); }
         if (m >= UM_F16_MAX && status) *reinterpret_cast<volatile int*>(status + 1) = 1;   // same value from every writer: no atomic
     }
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
         uint4 hi, lo;
-        split2(hv[8 * rr + 0], hv[8 * rr + 1], hi.x, lo.x);
-        split2(hv[8 * rr + 2], hv[8 * rr + 3], hi.y, lo.y);
-        split2(hv[8 * rr + 4], hv[8 * rr + 5], hi.z, lo.z);
-        split2(hv[8 * rr + 6], hv[8 * rr + 7], hi.w, lo.w);
+        split2n(h[0 + rr], hi.x, lo.x);
+        split2n(h[2 + rr], hi.y, lo.y);
+        split2n(h[4 + rr], hi.z, lo.z);
+        split2n(h[6 + rr], hi.w, lo.w);
         if (dbg & 4) { if (hi.x == 0x7fff7fffu && lo.y == 0x12345u) st_global_v4_hint(dst, hi, pol_keep); continue; }
         st_global_v4_hint(dst + rr * 512, hi, pol_keep);
         st_global_v4_hint(dst + rr * 512 + UM_A_HALF_BYTES, lo, pol_keep);
     }
 }
 
-// hidden layers (KIND = EPI_ACT) and the PCA-coefficient rescale (EPI_AFFINE): produce the next
-// contraction's A operand, split into fp16 hi/lo, in the swizzled K-major tile layout.
 template <int KIND>
-__device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_scale, uint8_t* a_dst, int* status) {
+__device__ UM_EPI_INLINE void epi_chunk_operand(const EpiCtx& E, float acc_scale, uint8_t* a_dst, int* status) {
     const uint64_t pol_keep = policy_evict_last();
+    const uint64_t scale2 = pk2(acc_scale, acc_scale);
     const uint32_t t_addr1 = E.t_addr0 + (16u << 16);
     // accumulator column 8i+2tr+cc of a 32-column piece holds logical column 8tr+2i+cc (packing order),
     // so this lane owns 8 consecutive logical columns = one 16-byte row chunk of the next A tile
@@ -495,20 +555,23 @@ __device__ __forceinline__ void epi_chunk_operand(const EpiCtx& E, float acc_sca
     for (int leg = 0; leg < (UM_EARLY_RELEASE ? 2 : 1); ++leg) {
     const int leg_end = (UM_EARLY_RELEASE && leg == 0 && E.rel_bar) ? min(E.nc, UM_SLOT_COLS) : E.nc;
     for (; pc < leg_end; pc += kStep) {
-        // the constants of a 32-column block are stored lane-interleaved (value j of lane group tr at 4j + tr):
-        // the four lane groups read 64 contiguous bytes - no shared-memory bank conflicts
-        float4 pp[8];
+        // the constants of a 32-column block are stored lane-interleaved (float4 j of lane group tr at 4j + tr, j = 2i for
+        // pa[i], 2i + 1 for pb[i]): the four lane groups read 64 contiguous bytes - no shared-memory bank conflicts
+        float4 pa[4], pb[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pp[j] = (E.dbg & 8) ? make_float4(0.1f, -1.f, 0.5f, 0.5f) : E.par[pc + 4 * j + E.tr];
+        for (int i = 0; i < 4; ++i) {
+            pa[i] = (E.dbg & 8) ? make_float4(0.1f, 0.1f, -1.f, -1.f) : E.par[pc + 8 * i + E.tr];
+            if (KIND == EPI_ACT) pb[i] = (E.dbg & 8) ? make_float4(0.5f, 0.5f, 0.5f, 0.5f) : E.par[pc + 8 * i + 4 + E.tr];
+        }
         const int kk = E.chunk_col0 + lcol0 + pc;                      // next layer's k index of this lane's 8 values
         // (kk % 32) >> 3 == tr; rows 32q + 16h + 8rr + tq share (row >> 1) & 3 == (tq >> 1) & 3
         uint8_t* dst = a_dst + static_cast<size_t>(kk / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(E.q * 32 + E.tq, E.tr);
         tmem_ld_wait16(va);
         tmem_ld_16x256b_x4(t_addr1 + pc, vb);
-        epi_operand_half<KIND>(va, pp, acc_scale, dst, pol_keep, E.dbg, status);
+        epi_operand_half<KIND>(va, pa, pb, scale2, dst, pol_keep, E.dbg, status);
         tmem_ld_wait16(vb);
         if (pc + kStep < E.nc) tmem_ld_16x256b_x4(E.t_addr0 + pc + kStep, va);
-        epi_operand_half<KIND>(vb, pp, acc_scale, dst + 1024, pol_keep, E.dbg, status);          // rows +16
+        epi_operand_half<KIND>(vb, pa, pb, scale2, dst + 1024, pol_keep, E.dbg, status);          // rows +16
     }
     if (UM_EARLY_RELEASE && leg == 0 && E.rel_bar) epi_release_first_slot(E);
     }
@@ -528,14 +591,17 @@ __device__ __forceinline__ void ldg_v8(const float* p, float (&y)[8]) {
 enum { OUT_NONE = -1, OUT_SCALAR = 0, OUT_VEC16 = 1, OUT_VEC32 = 2 };
 
 template <bool TEN_TO, bool ACC>
-__device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const float2 (&pp)[8], float* drow, long long pitch,
+__device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const float4 (&q)[4], float* drow, long long pitch,
                                                 int mode, int row_in_q, long long rows_left, int gc, int n_modes, int dbg) {
     if (mode == OUT_NONE) return;
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
         float y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 * rr + (j & 1)]), pp[j].x, pp[j].y);
+        for (int i = 0; i < 4; ++i) {
+            y[2 * i] = fmaf(__uint_as_float(v[4 * i + 2 * rr]), q[i].x, q[i].z);
+            y[2 * i + 1] = fmaf(__uint_as_float(v[4 * i + 2 * rr + 1]), q[i].y, q[i].w);
+        }
         float* dst = drow + static_cast<long long>(8 * rr) * pitch;
         const bool row_ok = row_in_q + 8 * rr < rows_left;
         if (ACC) {
@@ -580,13 +646,14 @@ __device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const f
 template <bool TEN_TO, bool ACC>
 // (ACC: p0 / p1 hold the log10 values already in the output rows - loaded by the caller at the top of the piece, so that
 // the L2 round trip, which queues behind this warp's own streaming stores, is paid once per piece and under the TMEM wait)
-__device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], const float2 (&pp)[8], float* d0, float* d1, int dbg,
+__device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], const float4 (&q)[4], float* d0, float* d1, int dbg,
                                                      const float (&p0)[8], const float (&p1)[8]) {
     float y0[8], y1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        y0[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + (j & 1)]), pp[j].x, pp[j].y);
-        y1[j] = fmaf(__uint_as_float(v[4 * (j >> 1) + 2 + (j & 1)]), pp[j].x, pp[j].y);
+    for (int i = 0; i < 4; ++i) {       // packed pairs: (scale0, scale1) x (acc0, acc1) + (shift0, shift1)
+        const uint64_t sc = pk2(q[i].x, q[i].y), sh = pk2(q[i].z, q[i].w);
+        upk2(ffma2(pk2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), sc, sh), y0[2 * i], y0[2 * i + 1]);
+        upk2(ffma2(pk2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), sc, sh), y1[2 * i], y1[2 * i + 1]);
     }
     if (ACC) {
         const float ks = TEN_TO ? 3.3219280948873623f : 1.f;
@@ -608,8 +675,8 @@ __device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], co
 }
 
 // output layers: de-standardise (+ 10**y) and store rows of the spectrum.  Columns are packed like the operand
-// layers' (a lane owns 8 consecutive logical columns), constants are {scale, shift} pairs, two columns per float4,
-// lane-interleaved (float4 4m + tr of a 32-column block = columns 8tr + 2m, 8tr + 2m + 1).
+// layers' (a lane owns 8 consecutive logical columns), constants are {scale0, scale1, shift0, shift1}, two columns per
+// float4, lane-interleaved (float4 4m + tr of a 32-column block = columns 8tr + 2m, 8tr + 2m + 1).
 template <bool TEN_TO, bool ACC>
 __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, long long pitch, int vec_mode,
                                                  long long rows_left, int n_modes) {
@@ -624,13 +691,9 @@ __device__ __forceinline__ void epi_chunk_output(const EpiCtx& E, float* orow0, 
     for (int leg = 0; leg < (UM_EARLY_RELEASE ? 2 : 1); ++leg) {
     const int leg_end = (UM_EARLY_RELEASE && leg == 0 && E.rel_bar) ? min(nc_valid, UM_SLOT_COLS) : nc_valid;
     for (; pc < leg_end; pc += kStep) {
-        float2 pp[8];
+        float4 pp[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const float4 q4 = (E.dbg & 8) ? make_float4(1.f, 0.f, 1.f, 0.f) : E.par[(pc >> 1) + 4 * m + E.tr];
-            pp[2 * m] = make_float2(q4.x, q4.y);
-            pp[2 * m + 1] = make_float2(q4.z, q4.w);
-        }
+        for (int m = 0; m < 4; ++m) pp[m] = (E.dbg & 8) ? make_float4(1.f, 1.f, 0.f, 0.f) : E.par[(pc >> 1) + 4 * m + E.tr];
         const int gc = E.chunk_col0 + pc + 8 * E.tr;
         float* drow = orow0 + gc;                                       // row 32q + tq of the tile
         // warp-uniform: 32-byte stores, whole tile inside the batch (vec_mode), whole piece inside the spectrum
@@ -905,6 +968,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     w_empty += mbar_wait(bar_empty(stage), ph_empty, P.error_flag, 103);
                     if (PROF && P.counters && blockIdx.x == 0 && it == UM_JOB_TRACE_ITERATION && s < UM_TRACE_STAGES && lane == 0)
                         P.counters[(gridDim.x + UM_MAX_JOBS) * UM_CNT_SLOTS + (ji * UM_TRACE_STAGES + s) * 2] = now();
+                    if (PROF && (P.debug_flags & 128)) {      // ablation: no operand traffic (the stage is only handed on)
+                        if (elect_one()) mbar_arrive(bar_full(stage));
+                    } else
                     if (elect_one()) {
                         const uint32_t dst = base + UM_SMEM_STAGES + stage * UM_STAGE_BYTES;
                         mbar_arrive_expect_tx(bar_full(stage), tx_bytes);
@@ -967,6 +1033,9 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                     if (PROF && P.counters && blockIdx.x == 0 && it == UM_JOB_TRACE_ITERATION && s < UM_TRACE_STAGES && lane == 0)
                         P.counters[(gridDim.x + UM_MAX_JOBS) * UM_CNT_SLOTS + (ji * UM_TRACE_STAGES + s) * 2 + 1] = now();
                     tc_fence_after();
+                    if (PROF && (P.debug_flags & 64)) {       // ablation: no tensor-core work at all (stages and accumulators are only handed on)
+                        if (elect_one()) umma_commit_2cta(bar_empty(stage));
+                    } else
                     if (elect_one()) {
                         const uint64_t adv = static_cast<uint64_t>(stage) * (UM_STAGE_BYTES >> 4);
                         const uint64_t a_hi = a_hi0 + adv, a_lo = a_lo0 + adv, b_hi = b_hi0 + adv, b_lo = b_hi + b_lo_off;
@@ -975,7 +1044,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             const uint64_t adv_b = static_cast<uint64_t>((kk * 256) >> 4);  // B: 2 core matrices along K
                             const uint64_t adv_a = static_cast<uint64_t>((kk * 32) >> 4);   // A: 16 k = 32 B inside the swizzled row
                             umma_f16_2cta(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, ((s0 + s) | kk) != 0);
-                            umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, 1u);
+                            umma_f16_2cta(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc | UM_IDESC_NEG_A, 1u);   // the tile holds -lo
                             umma_f16_2cta(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
                         }
                         umma_commit_2cta(bar_empty(stage));       // frees the stage in both CTAs
@@ -1035,8 +1104,8 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                             x[u] = v;
                         }
                         uint4 hi, lo;
-                        split2(x[0], x[1], hi.x, lo.x); split2(x[2], x[3], hi.y, lo.y);
-                        split2(x[4], x[5], hi.z, lo.z); split2(x[6], x[7], hi.w, lo.w);
+                        split2n(x[0], x[1], hi.x, lo.x); split2n(x[2], x[3], hi.y, lo.y);
+                        split2n(x[4], x[5], hi.z, lo.z); split2n(x[6], x[7], hi.w, lo.w);
                         const size_t off = static_cast<size_t>(k0 / UM_KS) * UM_A_STAGE_BYTES + a_tile_off(r, (k0 % UM_KS) >> 3);
                         *reinterpret_cast<uint4*>(dst + off) = hi;
                         *reinterpret_cast<uint4*>(dst + off + UM_A_HALF_BYTES) = lo;
@@ -1065,7 +1134,11 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
         int pb = 0;
         EpiCtx E;
         E.q = q; E.tq = tq; E.tr = tr; E.cw = cw; E.lane = lane;
+#ifdef UM_PROF_NO_DBG
+        E.dbg = 0;                               // profiling build whose epilogue loops are the production ones (no ablation paths)
+#else
         E.dbg = PROF ? P.debug_flags : 0;
+#endif
         E.leader = cta_rank == 0;
         const uint32_t accempty0 = E.leader ? bar_accempty(0) : map_to_cta(bar_accempty(0), 0);     // the leader's MMA issuer owns the TMEM hand-back
         UM_FOR_EACH_ENTRY({
@@ -1139,7 +1212,7 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_aready(ts));
             }
-            if (UM_DISCARD_DEAD_TILES && P.discard_ok && !L.layer0 && c == L.n_chunks - 1) {
+            if (UM_DISCARD_DEAD_TILES && P.discard_ok && !L.layer0 && c == L.n_chunks - 1 && !(PROF && (P.debug_flags & 256))) {
                 // This was the last chunk to stream the tile's operand: every copy of it has landed and been consumed
                 // (its MMAs are complete), so its L2 lines are dead - drop them instead of letting them be written
                 // back to HBM on eviction.  The buffer is rewritten soon, possibly while slower warps
