@@ -134,6 +134,24 @@ class _EmulatorBase:
     predictions_device = predictions_tf
     ten_to_predictions_device = ten_to_predictions_tf
 
+    def activation(self, x, alpha, beta):
+        """Non-linear activation function (reference cosmopower_NN.py:136-156 / cosmopower_PCAplusNN.py:139-158):
+        (beta + sigmoid(alpha x) (1 - beta)) x, on NumPy arrays or torch tensors.  (The engine evaluates it inside the
+        fused kernel's epilogue; this is the stand-alone helper of the reference API.)"""
+        try:
+            import torch
+            if isinstance(x, torch.Tensor):
+                return (beta + torch.sigmoid(alpha * x) * (1.0 - beta)) * x
+        except ImportError:
+            pass
+        with np.errstate(over="ignore"):
+            return (beta + (1.0 - beta) / (1.0 + np.exp(-alpha * x))) * x
+
+    def update_emulator_parameters(self):
+        """reference cosmopower_NN.py:258-272 / cosmopower_PCAplusNN.py:243-262 copy the TensorFlow variables into the
+        NumPy attributes before saving; here the NumPy attributes ARE the parameters, so there is nothing to copy."""
+        return None
+
     # -- out of scope, named so that callers get a clear message ---------------------------------------
     def train(self, *a, **k):
         raise NotImplementedError("cosmopower_b200 is an inference engine; training is out of scope")

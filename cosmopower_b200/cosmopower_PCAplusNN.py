@@ -27,6 +27,37 @@ class cosmopower_PCAplusNN(_EmulatorBase):
                   "The model uses %d hidden layers, \nwith %s nodes, respectively. \n"
                   % (self.n_parameters, self.n_pcas, self.n_modes, len(self.n_hidden), list(self.n_hidden)))
 
+    # -- PCA coefficients (reference cosmopower_PCAplusNN.py:163-193) -----------------------------------------
+    def _coefficient_attrs(self):
+        """The network up to the PCA coefficients is a cosmopower_NN whose output de-standardisation is (pca_std_, pca_mean_):
+        `(x.W + b) * pca_std + pca_mean` (reference :190-193) is exactly the NN output layer (cosmopower_NN.py:381-384)."""
+        a = {k: getattr(self, k) for k in ("parameters", "n_parameters", "n_hidden", "n_layers", "W_", "b_", "alphas_", "betas_",
+                                            "parameters_mean_", "parameters_std_")}
+        a["n_modes"] = int(self.n_pcas)
+        a["modes"] = np.arange(int(self.n_pcas))
+        a["architecture"] = [int(self.n_parameters)] + list(self.n_hidden) + [int(self.n_pcas)]
+        a["features_mean_"] = self.pca_mean_
+        a["features_std_"] = self.pca_std_
+        return a
+
+    def forward_pass_tf(self, parameters_tensor):
+        """Forward pass through the network to the PCA coefficients (reference cosmopower_PCAplusNN.py:163-193), as the
+        array-in/array-out twin on CUDA float32 torch tensors: (N, n_parameters) -> (N, n_pcas).  Runs on its own engine
+        (same fused kernel, the coefficient layer as the output layer), created on first use."""
+        from . import _engine
+        dev = parameters_tensor.device.index
+        if not hasattr(self, "_coef_engines"):
+            self._coef_engines = {}
+        if dev not in self._coef_engines:
+            self._coef_engines[dev] = _engine.Engine(self._coefficient_attrs(), device=dev, precision=self._precision)
+        return self._coef_engines[dev].forward_torch(parameters_tensor, ten_to=False)
+
+    def close(self):
+        for e in getattr(self, "_coef_engines", {}).values():
+            e.close()
+        self._coef_engines = {}
+        super().close()
+
     def _validate(self):
         super()._validate()
         if tuple(np.shape(self.pca_transform_matrix_)) != (int(self.n_pcas), int(self.n_modes)):

@@ -45,6 +45,15 @@ def forward_pass_pcann(m, parameters_arr):
             * m["features_std_"] + m["features_mean_"])            # :381
 
 
+def pca_coefficients(m, parameters_arr):
+    """cosmopower/cosmopower_PCAplusNN.py:163-193 (`forward_pass_tf`: the network up to the rescaled PCA coefficients),
+    restated in NumPy with the arithmetic of the class's own NumPy pass (:367-378)."""
+    with np.errstate(over="ignore"):
+        x = _trunk(m, parameters_arr)
+    c = np.dot(x, m["W_"][-1]) + m["b_"][-1]                       # :187
+    return c * m["pca_std_"] + m["pca_mean_"]                      # :190-193
+
+
 def forward_pass(m, parameters_arr):
     with np.errstate(over="ignore"):
         if "pca_transform_matrix_" in m:

@@ -103,6 +103,36 @@ def restore_reference(name, filename_without_suffix):
     return obj
 
 
+def reference_tf_twin(name, filename_without_suffix, method, x):
+    """Execute one of the reference's TensorFlow-side methods (`forward_pass_tf`, `predictions_tf`, `ten_to_predictions_tf`;
+    cosmopower_NN.py:160-211, cosmopower_PCAplusNN.py:163-239) on a restored reference object, with the handful of tf.*
+    calls they make bound to NumPy and the TF-side attributes (W, b, ... - variables that only __init__ creates) set to
+    the restored arrays.  The arithmetic is the reference's own source, evaluated in x's dtype."""
+    import numpy as np
+    obj = restore_reference(name, filename_without_suffix)
+    tf = type(obj).restore.__globals__["tf"]          # the module object the reference source bound at import
+    np_ops = {"divide": lambda a, b: a / b, "subtract": lambda a, b: a - b, "add": lambda a, b: a + b,
+              "multiply": lambda a, b: a * b, "matmul": lambda a, b: np.matmul(a, b),
+              "sigmoid": lambda v: 1. / (1. + np.exp(-v)), "pow": lambda a, b: np.power(a, b)}
+    saved = {k: getattr(tf, k, None) for k in np_ops}
+    for k, f in np_ops.items():
+        setattr(tf, k, f)
+    try:
+        obj.W, obj.b, obj.alphas, obj.betas = obj.W_, obj.b_, obj.alphas_, obj.betas_
+        obj.parameters_mean, obj.parameters_std = obj.parameters_mean_, obj.parameters_std_
+        obj.features_mean, obj.features_std = obj.features_mean_, obj.features_std_
+        if hasattr(obj, "pca_mean_"):
+            obj.pca_mean, obj.pca_std, obj.pca_transform_matrix = obj.pca_mean_, obj.pca_std_, obj.pca_transform_matrix_
+        with np.errstate(over="ignore"):
+            return getattr(obj, method)(x)
+    finally:
+        for k, f in saved.items():
+            if f is None:
+                delattr(tf, k)
+            else:
+                setattr(tf, k, f)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Planck-lite likelihood: execute the unmodified reference source with a NumPy-backed TensorFlow stub
 # ---------------------------------------------------------------------------------------------------

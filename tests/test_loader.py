@@ -104,3 +104,40 @@ def test_non_restore_constructor_with_weights():
         cp.cosmopower_NN(parameters=["a"], modes=np.arange(5), n_hidden=[8])
     with pytest.raises(NotImplementedError):
         m.train()
+
+
+def test_rescaled_predictions_follow_the_reference_contract():
+    """reference cosmopower_NN.py:429-466: `rescaled_predictions_np` applies `postprocessing_np` (set by train(), never pickled)
+    to the network output; a restored model has no such attribute and raises AttributeError, here as there."""
+    kind, path = standins.REAL_MODELS["PKLIN_NN"]
+    m = cp.cosmopower_NN(restore=True, restore_filename=path)
+    for call in (m.rescaled_predictions_np, m.ten_to_rescaled_predictions_np):
+        with pytest.raises(AttributeError):
+            call({k: np.zeros(1) for k in m.parameters})
+    with pytest.raises(AttributeError):
+        m.processing_vectors_tf
+    n = int(m.n_modes)
+    y = np.linspace(-1., 1., 3 * n).reshape(3, n)
+    mean, sigma = np.arange(n) * 0.5, 1. + np.arange(n) * 0.01
+    m.set_feature_processing('mean_sigma', {'mean': mean, 'sigma': sigma})       # train(): cosmopower_NN.py:666-677
+    assert np.array_equal(m.postprocessing_np(y, m.processing_vectors_np), y * sigma + mean)
+    lo, hi = -np.ones(n), 2. + np.arange(n) * 0.1
+    m.set_feature_processing('min_max', {'min': lo, 'max': hi})                   # :680-691
+    assert np.array_equal(m.postprocessing_np(y, m.processing_vectors_np), y * (hi - lo) + lo)
+    m.set_feature_processing(None)                                               # :694-703
+    assert m.postprocessing_np(y, m.processing_vectors_np) is y and m.processing_vectors_np == {}
+    with pytest.raises(ValueError):
+        m.set_feature_processing('mean_sigma', {'mean': mean[:-1], 'sigma': sigma[:-1]})
+    with pytest.raises(ValueError):
+        m.set_feature_processing('standard')
+
+
+def test_activation_helper_matches_the_reference_formula():
+    kind, path = standins.REAL_MODELS["PKLIN_NN"]
+    m = cp.cosmopower_NN(restore=True, restore_filename=path)
+    x = np.linspace(-30., 30., 13)
+    a, b = 0.7, 0.2
+    want = (b + (1. / (1. + np.exp(-a * x))) * (1. - b)) * x          # cosmopower_NN.py:156
+    np.testing.assert_allclose(m.activation(x, a, b), want, rtol=1e-15)
+    assert np.all(np.isfinite(m.activation(np.array([-1e4, 1e4]), 1.0, 0.5)))
+    assert m.update_emulator_parameters() is None

@@ -497,3 +497,49 @@ def test_fused_pk_pair_is_one_launch_and_equals_the_two_launch_path():
         rows = np.random.default_rng(1).choice(n, min(n, 3000), replace=False)
         total_log = oracle_np.forward_pass(a_lin, x_nl[rows][:, cols]) + oracle_np.forward_pass(a_nl, x_nl[rows])
         assert parity.ten_to_error(y[torch.from_numpy(rows).cuda()].cpu().numpy(), total_log) <= 2 * parity.TOL_LOG
+
+
+def test_rescaled_predictions_against_oracle():
+    """reference cosmopower_NN.py:213-251, 429-466: the network output through the feature post-processing of train()."""
+    import torch
+    m, attrs = get_model("PKLIN_NN")
+    n = int(m.n_modes)
+    rng = np.random.default_rng(5)
+    mean, sigma = rng.normal(size=n), rng.uniform(0.5, 2., size=n)
+    x = priors.sample_prior(m.parameters, 257, seed=23)
+    d = {k: x[:, i] for i, k in enumerate(m.parameters)}
+    ref = oracle_np.forward_pass(attrs, x)
+    try:
+        m.set_feature_processing('mean_sigma', {'mean': mean, 'sigma': sigma})
+        y = m.rescaled_predictions_np(d)
+        want = ref * sigma + mean
+        assert y.dtype == np.float64 and y.shape == want.shape
+        # the post-processing is exact float64 arithmetic on the emulator's output: the emulator's own tolerance, scaled
+        assert np.max(np.abs(y - want) / (sigma * np.maximum(np.abs(ref), 1.0))) <= parity.TOL_LOG
+        t = m.ten_to_rescaled_predictions_np(d)
+        assert np.allclose(np.log10(t), want, rtol=0, atol=2e-5 * np.max(sigma) * np.max(np.abs(ref)))
+        xt = torch.from_numpy(x.astype(np.float32)).cuda()
+        yt = m.rescaled_predictions_tf(xt)
+        assert yt.is_cuda and yt.dtype == torch.float32
+        assert np.allclose(yt.cpu().numpy(), y, rtol=2e-6, atol=2e-5)
+        assert torch.equal(m.ten_to_rescaled_predictions_tf(xt), 10.**yt)
+        assert set(m.processing_vectors_tf[xt.device]) == {'mean', 'sigma'}
+    finally:
+        for a in ("postprocessing_np", "postprocessing_tf", "processing_vectors_np", "_processing_vectors_tf"):
+            if hasattr(m, a):
+                delattr(m, a)
+
+
+@pytest.mark.parametrize("name", ["cmb_PP_PCAplusNN", "cmb_TE_PCAplusNN"])
+def test_pca_coefficients_against_oracle(name):
+    """cosmopower_PCAplusNN.forward_pass_tf (reference :163-193): the network up to the rescaled PCA coefficients.
+    Tolerance: 1e-5 of max(|coefficient|, its training spread pca_std_) - the coefficients cross zero, pca_std_ is their scale."""
+    import torch
+    m, attrs = get_model(name)
+    x = priors.sample_prior(m.parameters, 1000, seed=31)
+    c = m.forward_pass_tf(torch.from_numpy(x.astype(np.float32)).cuda())
+    assert c.is_cuda and tuple(c.shape) == (1000, int(m.n_pcas))
+    ref = oracle_np.pca_coefficients(attrs, x.astype(np.float32).astype(np.float64))
+    err = float(np.max(np.abs(c.cpu().numpy() - ref) / np.maximum(np.abs(ref), attrs["pca_std_"])))
+    print("%s PCA coefficients: max error %.3g of max(|c|, pca_std)" % (name, err))
+    assert err <= 1e-5
