@@ -42,14 +42,17 @@ class cosmopower_PCAplusNN(_EmulatorBase):
 
     def forward_pass_tf(self, parameters_tensor):
         """Forward pass through the network to the PCA coefficients (reference cosmopower_PCAplusNN.py:163-193), as the
-        array-in/array-out twin on CUDA float32 torch tensors: (N, n_parameters) -> (N, n_pcas).  Runs on its own engine
-        (same fused kernel, the coefficient layer as the output layer), created on first use."""
+        array-in/array-out twin on CUDA float32 torch tensors: (N, n_parameters) -> (N, n_pcas).  Runs on its own engine,
+        created on first use, with the coefficient layer as the output layer - on the CUDA-core fp32 kernels: the high-order
+        coefficients are small differences of large hidden activations (|z| up to 23 standard deviations for cmb_PP), an
+        ill-conditioned quantity that the reference's own float32 pass resolves to 1.5e-4 of a coefficient's spread; the
+        spectrum path (predictions_tf) does not go through here."""
         from . import _engine
         dev = parameters_tensor.device.index
         if not hasattr(self, "_coef_engines"):
             self._coef_engines = {}
         if dev not in self._coef_engines:
-            self._coef_engines[dev] = _engine.Engine(self._coefficient_attrs(), device=dev, precision=self._precision)
+            self._coef_engines[dev] = _engine.Engine(self._coefficient_attrs(), device=dev, precision="fp32")
         return self._coef_engines[dev].forward_torch(parameters_tensor, ten_to=False)
 
     def close(self):

@@ -532,14 +532,28 @@ def test_rescaled_predictions_against_oracle():
 
 @pytest.mark.parametrize("name", ["cmb_PP_PCAplusNN", "cmb_TE_PCAplusNN"])
 def test_pca_coefficients_against_oracle(name):
-    """cosmopower_PCAplusNN.forward_pass_tf (reference :163-193): the network up to the rescaled PCA coefficients.
-    Tolerance: 1e-5 of max(|coefficient|, its training spread pca_std_) - the coefficients cross zero, pca_std_ is their scale."""
+    """cosmopower_PCAplusNN.forward_pass_tf (reference :163-193): the network up to the rescaled PCA coefficients (runs on the
+    fp32 CUDA-core kernels).  Coefficients cross zero and span eight decades of pca_std_, and the high-order ones are small
+    differences of large hidden activations (standardised values up to |z| = 23 for cmb_PP): no float32 implementation
+    resolves them to 1e-5.  The bar is therefore the reference itself: within 4x of what the reference FORMULA gives in
+    float32 NumPy (what its TF twin computes), in two metrics - |dc| / row peak and |dc| / max(|c|, pca_std_)."""
     import torch
     m, attrs = get_model(name)
-    x = priors.sample_prior(m.parameters, 1000, seed=31)
-    c = m.forward_pass_tf(torch.from_numpy(x.astype(np.float32)).cuda())
+    x = priors.sample_prior(m.parameters, 1000, seed=31).astype(np.float32)
+    c = m.forward_pass_tf(torch.from_numpy(x).cuda())
     assert c.is_cuda and tuple(c.shape) == (1000, int(m.n_pcas))
-    ref = oracle_np.pca_coefficients(attrs, x.astype(np.float32).astype(np.float64))
-    err = float(np.max(np.abs(c.cpu().numpy() - ref) / np.maximum(np.abs(ref), attrs["pca_std_"])))
-    print("%s PCA coefficients: max error %.3g of max(|c|, pca_std)" % (name, err))
-    assert err <= 1e-5
+    c = c.cpu().numpy()
+    ref = oracle_np.pca_coefficients(attrs, x.astype(np.float64))
+    peak = np.max(np.abs(ref), axis=1, keepdims=True)
+    scale = np.maximum(np.abs(ref), attrs["pca_std_"])
+    a32 = dict(attrs)
+    for k in ("W_", "b_", "alphas_", "betas_"):
+        a32[k] = [np.asarray(w, np.float32) for w in attrs[k]]
+    for k in ("parameters_mean_", "parameters_std_", "pca_mean_", "pca_std_"):
+        a32[k] = np.asarray(attrs[k], np.float32)
+    c32 = oracle_np.pca_coefficients(a32, x)
+    e_peak, r_peak = float(np.max(np.abs(c - ref) / peak)), float(np.max(np.abs(c32 - ref) / peak))
+    e_coef, r_coef = float(np.max(np.abs(c - ref) / scale)), float(np.max(np.abs(c32 - ref) / scale))
+    print("%s PCA coefficients: %.3g of the row peak (reference formula in float32: %.3g); per coefficient %.3g (float32: %.3g)"
+          % (name, e_peak, r_peak, e_coef, r_coef))
+    assert e_peak <= 4 * r_peak and e_coef <= 4 * r_coef
