@@ -15,6 +15,8 @@ roofline of the fused kernel; `per_model` = every BASELINE config's emulator at 
 time from CUDA events, tensor / HBM fractions, DRAM bytes of the committed ncu capture, parity of a
 4096-row sample against the oracle computed in the same run, outside the timed region); `strong` = ONE
 1,048,576-row batch per model split over the N ranks (the BASELINE metric read literally);
+`likelihood` = the Planck-lite consumer of the CMB emulators (get_loglkl on 262,144 parameter sets, parity against the oracle
+pipeline); `sweep` = BASELINE configs[4] at bench size (six emulators streamed over 8 M parameter sets per rank);
 `cpu_baseline` = the reference's NumPy predictions path on the host cores, bounded sample.
 `--impl reference` times that CPU path alone, same metric/config.
 """
@@ -285,6 +287,71 @@ def per_model_section(torch, cp, dev, local, peaks, batch):
     return out
 
 
+def likelihood_section(torch, cp, dev, local, rows=1 << 18):
+    """SURVEY 8f.1 (the in-repo consumer of the CMB emulators): tf_planck2018_lite.get_loglkl on `rows` in-prior parameter
+    sets - three emulators + Planck-lite tail on the device; parity of a 512-row sample against the oracle pipeline
+    (oracle emulators + oracle likelihood, float64) computed outside the timed region."""
+    from cosmopower_b200 import priors, standins
+    from cosmopower_b200.likelihoods import tf_planck2018_lite
+    from oracle import oracle_np, planck_lite_np
+    models, attrs = {}, {}
+    for key, name in (("tt", "cmb_TT_NN"), ("te", "cmb_TE_PCAplusNN"), ("ee", "cmb_EE_NN")):
+        kind, path = standins.model_path(name)
+        models[key] = getattr(cp, kind)(restore=True, restore_filename=path, device=local)
+        attrs[key] = standins.load_attrs(kind, path)
+    params = list(models["tt"].parameters)
+    like = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"])
+    x = priors.sample_prior(params, rows, seed=20260501, dtype=np.float32)
+    cal = (1 + 0.0025 * np.random.default_rng(5).standard_normal(rows)).astype(np.float32)
+    full_np = np.concatenate([x, cal[:, None]], axis=1)
+    full = torch.from_numpy(full_np).to(dev)
+    for _ in range(3):
+        ll = like.get_loglkl(full)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ll = like.get_loglkl(full)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    n_par = 512
+    x64 = full_np[:n_par, :len(params)].astype(np.float64)
+    with np.errstate(over="ignore"):
+        ref = planck_lite_np.PlanckLiteOracle().loglike_from_spectra(
+            10.0 ** oracle_np.forward_pass(attrs["tt"], x64), oracle_np.forward_pass(attrs["te"], x64),
+            10.0 ** oracle_np.forward_pass(attrs["ee"], x64), full_np[:n_par, -1].astype(np.float64))
+    got = ll[:n_par].cpu().numpy().reshape(-1)
+    rel = float(np.max(np.abs(got - ref.reshape(-1)) / np.abs(ref.reshape(-1))))
+    med = float(np.median(ms))
+    out = {"rows": rows, "get_loglkl_ms": med, "get_loglkl_ms_min": float(min(ms)), "loglkl_per_s": rows / med * 1e3,
+           "call": "tf_planck2018_lite.get_loglkl (TT + TE + EE emulators and the plik-lite tail on the device)",
+           "parity_rel_err": rel, "parity_tol": 1e-3, "parity_rows": n_par,
+           "parity_metric": "max |ll - ll_ref| / |ll_ref| against oracle emulators + oracle likelihood (float64)",
+           "weights": "synthetic stand-ins (TT / TE / EE pickles stripped upstream)"}
+    like.close()
+    for m in models.values():
+        m.close()
+    return out
+
+
+def sweep_section(torch, cp, local, world, rank, rows_per_rank=8 << 20):
+    """BASELINE configs[4] scaled to a bench-sized run: all six emulators streamed over `rows_per_rank` parameter sets
+    per rank in 1,048,576-row chunks (parameters drawn on the device, one reused output buffer; the 100 M-set run is
+    tools/run_sweep.py).  Returns this rank's device seconds per model."""
+    from cosmopower_b200 import standins, sweep
+    models = {}
+    for name in ALL_MODELS:
+        kind, path = standins.model_path(name)
+        models[name] = getattr(cp, kind)(restore=True, restore_filename=path, device=local)
+    res = sweep.sweep(models, rows_per_rank * world, chunk_rows=1 << 20, seed=3, device=local, ten_to=False, checksum=False,
+                      world_size=world, rank=rank)
+    for m in models.values():
+        m.close()
+    return {k: v["seconds"] for k, v in res.items()}, rows_per_rank
+
+
 def run_ours(args):
     import torch
     import cosmopower_b200 as cp
@@ -433,6 +500,28 @@ def run_ours(args):
             per_model = {"error": repr(err)}
     barrier()
 
+    likelihood = None
+    if rank == 0 and not args.no_per_model:
+        try:
+            likelihood = likelihood_section(torch, cp, dev, local)
+        except Exception as err:
+            likelihood = {"error": repr(err)}
+    barrier()
+    sweep_line = None
+    if not args.no_per_model:
+        try:   # every rank streams its own shard of chunks (no collective); the job's time is the slowest rank's
+            secs, rows_rank = sweep_section(torch, cp, local, world, rank)
+            tot = {k: max_over_ranks(v) for k, v in secs.items()}
+            total_s = max_over_ranks(sum(secs.values()))
+            sweep_line = {"workload": "BASELINE configs[4] at bench size: six emulators x %d parameter sets per rank, 1,048,576-row chunks, "
+                                      "parameters drawn on the device, predictions (log / linear spectra)" % rows_rank,
+                          "rows_per_model": rows_rank * world, "seconds_per_model": tot, "seconds_total": total_s,
+                          "spectra_per_s": len(ALL_MODELS) * rows_rank * world / total_s,
+                          "extrapolated_100M_sets_s": total_s * 1e8 / (rows_rank * world)}
+        except Exception as err:
+            sweep_line = {"error": repr(err)}
+    barrier()
+
     if rank == 0:
         peaks = load_peaks()
         avg_launch_s = float(np.mean(launch_ms)) * 1e-3
@@ -482,6 +571,10 @@ def run_ours(args):
             line["strong"] = strong
         if per_model is not None:
             line["per_model"] = per_model
+        if likelihood is not None:
+            line["likelihood"] = likelihood
+        if sweep_line is not None:
+            line["sweep"] = sweep_line
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)
