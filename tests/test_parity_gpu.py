@@ -557,3 +557,38 @@ def test_pca_coefficients_against_oracle(name):
     print("%s PCA coefficients: %.3g of the row peak (reference formula in float32: %.3g); per coefficient %.3g (float32: %.3g)"
           % (name, e_peak, r_peak, e_coef, r_coef))
     assert e_peak <= 4 * r_peak and e_coef <= 4 * r_coef
+
+
+@pytest.mark.parametrize("name", ["cmb_TT_NN", "cmb_EE_NN"])
+def test_stand_in_head_scaled_to_unit_rms_outputs_against_the_float32_reference_pass(name):
+    """How much of the TT / EE parity figure is the stand-in's doing?  Its synthetic head gives standardised outputs of rms
+    1/8; a trained emulator's are ~1 (PKLIN 1.01, PKNLBOOST 0.89, cmb_PP 0.93 over their priors).  The same network with the
+    head scaled by 8 transfers the (real, cmb_PP) trunk's rounding errors to the spectrum eight times more strongly: there
+    even the reference's own float32 pass (NumPy on float32 inputs, cosmopower_NN.py:371-384) reaches 5-7e-6 on its worst
+    in-prior rows.  The tensor path must stay inside 1e-5 on all but the worst 0.1 % of rows and within 3x the float32
+    pass's worst row.  Measured on B200, these 20 000 rows: tensor path worst row 6.0e-6 (TT) / 6.6e-6 (EE), 99th percentile
+    2.1e-6, against 6.9e-6 / 5.1e-6 and 5e-7 for the float32 reference pass; 50 000 rows of another seed
+    (tests/manual/accuracy_sweep.py on the rescaled stand-ins): worst rows 1.5e-5 / 9.8e-6 - at this output scale the 1e-5
+    tolerance sits at the float32 limit of the trunk itself, which is why the bound here is relative to the reference's pass."""
+    _, attrs = get_model(name)
+    W = [np.asarray(w, dtype=np.float32) for w in attrs["W_"]]
+    W[-1] = W[-1] * np.float32(8.0)
+    stress = dict(attrs, W_=W)
+    kw = dict(parameters=list(attrs["parameters"]), modes=np.asarray(attrs["modes"]), n_hidden=[512, 512, 512, 512],
+              parameters_mean=attrs["parameters_mean_"], parameters_std=attrs["parameters_std_"],
+              features_mean=attrs["features_mean_"], features_std=attrs["features_std_"],
+              weights=dict(W_=W, b_=list(attrs["b_"]), alphas_=list(attrs["alphas_"]), betas_=list(attrs["betas_"])))
+    m = cp.cosmopower_NN(device=0, **kw)
+    x32 = priors.sample_prior(attrs["parameters"], 20000, seed=11, dtype=np.float32)
+    ref = oracle_np.forward_chunked(stress, x32.astype(np.float64))
+    f32 = oracle_np.forward_pass(stress, x32)                       # the reference's float32 pass
+    assert f32.dtype == np.float32
+    y = m.forward_pass_np(x32)
+    row = lambda a: (np.abs(a - ref) / np.maximum(np.abs(ref), 1.0)).max(axis=1)
+    e_gpu, e_f32 = row(y.astype(np.float64)), row(f32.astype(np.float64))
+    print("%s, head x8: tensor path max %.3g, 99.9 %% %.3g, 99 %% %.3g, rows above 1e-5: %d of %d; float32 reference pass max %.3g, 99 %% %.3g"
+          % (name, e_gpu.max(), np.percentile(e_gpu, 99.9), np.percentile(e_gpu, 99), int((e_gpu > 1e-5).sum()), e_gpu.size,
+             e_f32.max(), np.percentile(e_f32, 99)))
+    assert np.percentile(e_gpu, 99.9) <= parity.TOL_LOG
+    assert e_gpu.max() <= max(parity.TOL_LOG, 3.0 * e_f32.max())
+    m.close()
