@@ -509,17 +509,24 @@ def run_ours(args):
     barrier()
     sweep_line = None
     if not args.no_per_model:
-        try:   # every rank streams its own shard of chunks (no collective); the job's time is the slowest rank's
+        # every rank streams its own shard of chunks (no collective on the path); the job's time is the slowest rank's.
+        # A failure on one rank must not leave the others waiting in a reduction: the outcome is agreed on first.
+        secs, rows_rank, sweep_err = None, 0, None
+        try:
             secs, rows_rank = sweep_section(torch, cp, local, world, rank)
-            tot = {k: max_over_ranks(v) for k, v in secs.items()}
+        except Exception as err:
+            sweep_err = repr(err)
+        all_ok = max_over_ranks(0.0 if sweep_err is None else 1.0) == 0.0
+        if all_ok:
+            tot = {k: max_over_ranks(secs[k]) for k in ALL_MODELS}
             total_s = max_over_ranks(sum(secs.values()))
             sweep_line = {"workload": "BASELINE configs[4] at bench size: six emulators x %d parameter sets per rank, 1,048,576-row chunks, "
                                       "parameters drawn on the device, predictions (log / linear spectra)" % rows_rank,
                           "rows_per_model": rows_rank * world, "seconds_per_model": tot, "seconds_total": total_s,
                           "spectra_per_s": len(ALL_MODELS) * rows_rank * world / total_s,
                           "extrapolated_100M_sets_s": total_s * 1e8 / (rows_rank * world)}
-        except Exception as err:
-            sweep_line = {"error": repr(err)}
+        else:
+            sweep_line = {"error": sweep_err or "another rank failed"}
     barrier()
 
     if rank == 0:
