@@ -1548,7 +1548,7 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     if (n_passes > cpb::PLIK_MAX_PASSES)
         return fail(CPB200_E_UNSUPPORTED, "%zu window slots exceed %d", slots.size(), cpb::PLIK_MAX_PASSES * cpb::PLIK_BIN_THREADS);
     const size_t bin_smem = (cpb::PLIK_BAR_FLOATS + static_cast<size_t>(cpb::PLIK_RING) * (row_floats + cpb::PLIK_ROW_PAD) +
-                             round_up(d->n_bins, cpb::PLIK_QF_BN) + 8) * sizeof(float);
+                             2 * (round_up(d->n_bins, cpb::PLIK_QF_BN) + cpb::PLIK_BIN_THREADS / 32)) * sizeof(float);
     if (bin_smem > prop.sharedMemPerBlockOptin)
         return fail(CPB200_E_UNSUPPORTED, "the row ring of 3 x %d multipoles does not fit one block's shared memory", d->n_ell);
     cpb200_plik* p = new cpb200_plik();
@@ -1621,7 +1621,8 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     // the padding columns n_bins .. pad-1 of the difference vectors are never written: zero them once
     if (cudaMemset(p->d_diff, 0, static_cast<size_t>(p->chunk_rows) * p->pad * sizeof(float)) != cudaSuccess)
         return bail(fail(CPB200_E_CUDA, "memset failed"));
-    if (cudaFuncSetAttribute(cpb::plik_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bin_smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(cpb::plik_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bin_smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(cpb::plik_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bin_smem)) != cudaSuccess)
         return bail(fail(CPB200_E_CUDA, "cannot size the binning kernel's shared memory"));
     *out = p;
     return 0;
@@ -1655,9 +1656,14 @@ int cpb200_plik_loglike_device(cpb200_plik* p, const float* cl_tt, const float* 
         in.ptr[0] = cl_tt + r0 * pitch; in.ptr[1] = cl_te + r0 * te_pitch; in.ptr[2] = cl_ee + r0 * pitch;
         in.pitch[0] = pitch; in.pitch[1] = te_pitch; in.pitch[2] = pitch;
         for (int i = 0; i < 3; ++i) in.len[i] = p->in_len[i];
-        cpb::plik_bin_kernel<<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
-            in, cal + r0, m, p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,
-            binned ? binned + r0 * binned_pitch : nullptr, binned_pitch, p->qf ? p->d_tiles : nullptr, p->d_row_scale);
+        if (p->qf)
+            cpb::plik_bin_kernel<true><<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
+                in, cal + r0, m, p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,
+                binned ? binned + r0 * binned_pitch : nullptr, binned_pitch, p->d_tiles, p->d_row_scale);
+        else
+            cpb::plik_bin_kernel<false><<<grid_bin, cpb::PLIK_BIN_THREADS, smem, st>>>(
+                in, cal + r0, m, p->d_slots, p->n_passes, p->units_factor, p->d_diff, p->pad,
+                binned ? binned + r0 * binned_pitch : nullptr, binned_pitch, nullptr, nullptr);
         if (p->qf) {
             cpb200_engine* q = p->qf;
             q->qf_ext_a0 = p->d_tiles; q->qf_d = p->d_diff; q->qf_pitch = p->pad; q->qf_cols = p->pad; q->qf_partial = p->d_partial;

@@ -76,6 +76,8 @@ struct PlikInputs {
 constexpr int PLIK_ROW_PAD = 8;
 constexpr int PLIK_BAR_FLOATS = 8;
 
+// TILES: tensor-core quadratic form behind it (scaled differences + operand tiles); false: plain differences for the fp32 one
+template <bool TILES>
 __global__ void __launch_bounds__(PLIK_BIN_THREADS, PLIK_BLOCKS_PER_SM)
 plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                 const PlikSlot* __restrict__ slots, int n_passes, float units_factor,
@@ -83,15 +85,19 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                 uint8_t* __restrict__ tiles, float* __restrict__ row_scale)
 {
     extern __shared__ __align__(16) float plik_smem[];
-    const int off1 = (in.len[0] + 3) & ~3, off2 = off1 + ((in.len[1] + 3) & ~3);
-    const int buf_floats = off2 + ((in.len[2] + 3) & ~3) + PLIK_ROW_PAD;
+    int off1 = (in.len[0] + 3) & ~3, off2 = off1 + ((in.len[1] + 3) & ~3);
+    int buf_floats = off2 + ((in.len[2] + 3) & ~3) + PLIK_ROW_PAD;
+    asm volatile("" : "+r"(off1), "+r"(off2), "+r"(buf_floats));      // pinned in registers: the compiler would otherwise re-derive
+                                                                      // every loop invariant from the parameters in each iteration
     float* ring = plik_smem + PLIK_BAR_FLOATS;
-    // tensor-core mode (tiles != nullptr): the row's scaled differences, then the per-warp maxima
-    float* vrow = ring + PLIK_RING * buf_floats;
-    float* wmax = vrow + diff_pitch;
+    // tensor-core mode (tiles != nullptr): TWO copies of {the row's scaled differences, the per-warp maxima} - a row is
+    // binned in one loop iteration and scaled / written out in the next, so one block barrier per row separates both the
+    // ring hand-over and the row-maximum exchange (the first version needed two, and the kernel is bound by them)
+    float* vrow0 = ring + PLIK_RING * buf_floats;
+    const int vstride = diff_pitch + PLIK_BIN_THREADS / 32;
     const uint32_t bar0 = static_cast<uint32_t>(__cvta_generic_to_shared(plik_smem));
     // zero everything once: the pads between and after the inputs stay zero for the whole launch
-    for (int i = threadIdx.x; i < PLIK_RING * buf_floats + diff_pitch; i += PLIK_BIN_THREADS) ring[i] = 0.f;
+    for (int i = threadIdx.x; i < PLIK_RING * buf_floats + 2 * vstride; i += PLIK_BIN_THREADS) ring[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < PLIK_RING; ++i) mbar_init(bar0 + 8u * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,7 +125,38 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                for (int j = 0; j < PLIK_SEG; ++j) my[p].w[j] = 0.f; }
     }
 
+    // (the kernel is bound by instruction issue - ncu, round 2: 65 % of the issue slots, 490 instructions per thread and row
+    // in its first form - so everything a single warp can do is kept away from the other seven)
+    int all_vec = vec[0] && vec[1] && vec[2];
+    asm volatile("" : "+r"(all_vec), "+r"(bulk_bytes));                           // pinned: otherwise re-derived from the parameters in every iteration
     auto fetch = [&](long long r, int buf) {                    // always commits a group (empty past the last row)
+        if (all_vec) {
+            // warp 0 alone: lane 0 issues the three bulk copies, lanes 1 .. 9 the (at most three per input) tail elements
+            if (threadIdx.x >= 32) return;
+            if (r < n_rows) {
+                float* dst0 = ring + buf * buf_floats;
+                const uint32_t bar = bar0 + 8u * buf;
+                if (threadIdx.x == 0) {
+                    mbar_arrive_expect_tx(bar, bulk_bytes);
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const int n4 = in.len[s] >> 2;
+                        if (n4) bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(dst0 + (s == 0 ? 0 : s == 1 ? off1 : off2))),
+                                         in.ptr[s] + r * in.pitch[s], static_cast<uint32_t>(n4) * 16u, bar);
+                    }
+                } else if (threadIdx.x < 10) {
+                    const int s = (static_cast<int>(threadIdx.x) - 1) / 3, u = (static_cast<int>(threadIdx.x) - 1) % 3;
+                    const int len = s == 0 ? in.len[0] : s == 1 ? in.len[1] : in.len[2];
+                    const int i = (len & ~3) + u;
+                    if (i < len) {
+                        const float* src = (s == 0 ? in.ptr[0] : s == 1 ? in.ptr[1] : in.ptr[2]) + r * (s == 0 ? in.pitch[0] : s == 1 ? in.pitch[1] : in.pitch[2]);
+                        cp_async_4(dst0 + (s == 0 ? 0 : s == 1 ? off1 : off2) + i, src + i);
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+        }
         if (r < n_rows) {
             float* dst0 = ring + buf * buf_floats;
             const uint32_t bar = bar0 + 8u * buf;
@@ -145,79 +182,124 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    // Tensor-core quadratic form: v_i = d_i sqrt(F_ii), scaled by a power of two q so that max |v_i| q lies in
+    // [0.5, 1).  Written twice: fp32 (the epilogue's dot product) and as the contraction's A operand - split
+    // fp16 hi/lo of 1024 q v in the swizzled K-major tile layout the fused kernel's loader streams.
+    // Only the diff_pitch / 8 threads that own a 16-byte chunk of the operand tile take part: each reads its eight values
+    // once and writes both forms (the fp32 row and the split tile) with 16-byte stores.
+    const int tile_stage_off = (static_cast<int>(threadIdx.x) >> 2) * 16384, tile_kchunk = static_cast<int>(threadIdx.x) & 3;
+    const long long tile_bytes = static_cast<long long>(diff_pitch / 32) * 16384;
+    auto write_row = [&](long long rr, const float* vrow) {
+        if (static_cast<int>(threadIdx.x) >= diff_pitch / 8) return;
+        const float4 m0 = *reinterpret_cast<const float4*>(vrow + diff_pitch), m1 = *reinterpret_cast<const float4*>(vrow + diff_pitch + 4);
+        const float m = fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w)));
+        // q = 2^-ex with m = f 2^ex, f in [0.5, 1): the exponent field alone (zero, subnormal, inf / NaN maxima keep q = 1)
+        const uint32_t be = (__float_as_uint(m) >> 23) & 0xffu;
+        const float q = (be >= 1u && be <= 253u) ? __uint_as_float((253u - be) << 23) : 1.f;
+        const float4 a = *reinterpret_cast<const float4*>(vrow + 8 * threadIdx.x), b = *reinterpret_cast<const float4*>(vrow + 8 * threadIdx.x + 4);
+        const float x[8] = {a.x * q, a.y * q, a.z * q, a.w * q, b.x * q, b.y * q, b.z * q, b.w * q};
+        float* drow = diff + rr * diff_pitch + 8 * threadIdx.x;
+        *reinterpret_cast<float4*>(drow) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(drow + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        const int rt = static_cast<int>(rr & 127);
+        uint4 hi, lo;
+        plik_split2(x[0] * 1024.f, x[1] * 1024.f, hi.x, lo.x); plik_split2(x[2] * 1024.f, x[3] * 1024.f, hi.y, lo.y);
+        plik_split2(x[4] * 1024.f, x[5] * 1024.f, hi.z, lo.z); plik_split2(x[6] * 1024.f, x[7] * 1024.f, hi.w, lo.w);
+        uint8_t* t = tiles + (rr >> 7) * tile_bytes + tile_stage_off + rt * 64 + ((tile_kchunk ^ (rt >> 1)) & 3) * 16;
+        *reinterpret_cast<uint4*>(t) = hi;
+        *reinterpret_cast<uint4*>(t + 8192) = lo;
+        if (threadIdx.x == 0) row_scale[rr] = q;
+    };
+
     const long long stride = gridDim.x;
     long long r = blockIdx.x;
 #pragma unroll
     for (int i = 0; i < PLIK_RING - 1; ++i) fetch(r + i * stride, i);
-    int buf = 0;
+    uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring)), vrow0_s = static_cast<uint32_t>(__cvta_generic_to_shared(vrow0));
+    uint32_t buf_bytes = 4u * buf_floats, vstride_bytes = 4u * vstride;
+    asm volatile("" : "+r"(ring_s), "+r"(vrow0_s), "+r"(buf_bytes), "+r"(vstride_bytes));      // pinned in registers
+#pragma unroll
+    for (int p = 0; p < PLIK_MAX_PASSES; ++p) { my[p].off *= 4; asm volatile("" : "+r"(my[p].off), "+r"(my[p].bin)); }
+    int buf = 0, par = 0;
+    float c_next = r < n_rows ? cal[r] : 1.f;
+    long long r_prev = -1;                                       // binned in the previous iteration, not yet written out
     uint32_t phases = 0;                                         // one parity bit per ring buffer
     for (; r < n_rows; r += stride) {
         asm volatile("cp.async.wait_group %0;" ::"n"(PLIK_RING - 2) : "memory");    // this thread's 4-byte copies of row r have landed
         while (!mbar_try_wait(bar0 + 8u * buf, (phases >> buf) & 1u)) { }          // ... and the row's bulk copies
         phases ^= 1u << buf;
-        const float c = cal[r];
+        const float c = c_next;                                  // loaded one iteration ahead: a dependent global load per row
+        if (r + stride < n_rows) c_next = cal[r + stride];       // would sit on the critical path (9 % of the stall samples)
         const float scale = units_factor / (c * c);
         float vmax = 0.f;
-        __syncthreads();                                         // row r is complete for every thread, and every thread has
-                                                                 // finished the previous row (its buffer, vrow, wmax are free)
+        __syncthreads();                                         // row r is complete for every thread; every thread has binned the
+                                                                 // previous row (its ring buffer is free, its differences and maxima are
+                                                                 // complete) and written out the row before that (its copy is free)
         fetch(r + (PLIK_RING - 1) * stride, buf == 0 ? PLIK_RING - 1 : buf - 1);     // refill the buffer of the previous row
-        const float* row = ring + buf * buf_floats;
+        // shared-memory addresses as 32-bit integers behind explicit ld / st.shared: left to itself the compiler re-derives
+        // `ring + buf * buf_floats + off` from the kernel parameters in every pass (a dozen instructions each time)
+        const uint32_t row_s = ring_s + static_cast<uint32_t>(buf) * buf_bytes;
+        const uint32_t vrow_s = vrow0_s + static_cast<uint32_t>(par) * vstride_bytes;
+        float* vrow = vrow0 + par * vstride;
+        float* brow = binned ? binned + r * binned_pitch : nullptr;          // (optional) band powers of this row
+        float* drow = TILES ? nullptr : diff + r * diff_pitch;
+        asm volatile("" : "+l"(brow), "+l"(drow));
+        // all passes' loads first, then the arithmetic: the passes are independent chains, and a pass that does not exist
+        // (p >= n_passes) has off = 0, weights 0 and bin = -1 - it costs its instructions but keeps the code branch-free
+        float v[PLIK_MAX_PASSES][PLIK_SEG];
 #pragma unroll
         for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
-            if (p < n_passes) {                                  // uniform across the block
-                const float* q = row + my[p].off;
-                float v[PLIK_SEG];
+            const uint32_t qa = row_s + static_cast<uint32_t>(my[p].off);              // byte offset (scaled before the loop)
 #pragma unroll
-                for (int j = 0; j < PLIK_SEG; ++j) v[j] = q[j];  // beyond the slot's end: neighbouring data or zero pad, weight 0
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < PLIK_SEG; ++j) acc = fmaf(v[j], my[p].w[j], acc);
-                float sum = acc;
-#pragma unroll
-                for (int k = 1; k < PLIK_MAX_SLOTS_PER_BIN; ++k) {
-                    const float o = __shfl_down_sync(0xffffffffu, acc, k);
-                    if (k < my[p].n_slots) sum += o;
-                }
-                if (my[p].bin >= 0) {
-                    const float model = sum * scale;
-                    if (binned) binned[r * binned_pitch + my[p].bin] = model;
-                    const float d = my[p].x_data - model;
-                    if (tiles) { const float v = d * my[p].sqrt_f; vrow[my[p].bin] = v; vmax = fmaxf(vmax, fabsf(v)); }
-                    else diff[r * diff_pitch + my[p].bin] = d;
-                }
-            }
+            for (int j = 0; j < PLIK_SEG; ++j)                   // beyond the slot's end: neighbouring data or zero pad, weight 0
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[p][j]) : "r"(qa + 4u * j));
         }
-        if (tiles) {
-            // Tensor-core quadratic form: v_i = d_i sqrt(F_ii), scaled by a power of two q so that max |v_i| q lies in
-            // [0.5, 1).  Written twice: fp32 (the epilogue's dot product) and as the contraction's A operand - split
-            // fp16 hi/lo of 1024 q v in the swizzled K-major tile layout the fused kernel's loader streams.
+        float acc[PLIK_MAX_PASSES];
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-            if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = vmax;
-            __syncthreads();
-            float m = 0.f;
+        for (int p = 0; p < PLIK_MAX_PASSES; ++p) {              // three partial sums of three: a 9-deep FMA chain is 36 cycles
+            float a0 = v[p][0] * my[p].w[0], a1 = v[p][1] * my[p].w[1], a2 = v[p][2] * my[p].w[2];
 #pragma unroll
-            for (int i = 0; i < PLIK_BIN_THREADS / 32; ++i) m = fmaxf(m, wmax[i]);
-            float q = 1.f;
-            if (m > 0.f && m < 3.0e38f) { int ex; frexpf(m, &ex); q = ldexpf(1.f, -ex); }
-            for (int k = threadIdx.x; k < diff_pitch; k += PLIK_BIN_THREADS) diff[r * diff_pitch + k] = vrow[k] * q;
-            if (threadIdx.x < diff_pitch / 8) {
-                const int ch = threadIdx.x, stage = ch >> 2, kchunk = ch & 3;
-                const int rt = static_cast<int>(r & 127);
-                float x[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = vrow[8 * ch + j] * q * 1024.f;
-                uint4 hi, lo;
-                plik_split2(x[0], x[1], hi.x, lo.x); plik_split2(x[2], x[3], hi.y, lo.y);
-                plik_split2(x[4], x[5], hi.z, lo.z); plik_split2(x[6], x[7], hi.w, lo.w);
-                uint8_t* t = tiles + (r >> 7) * (static_cast<long long>(diff_pitch / 32) * 16384) + stage * 16384
-                           + rt * 64 + ((kchunk ^ (rt >> 1)) & 3) * 16;
-                *reinterpret_cast<uint4*>(t) = hi;
-                *reinterpret_cast<uint4*>(t + 8192) = lo;
+            for (int j = 3; j < PLIK_SEG; j += 3) {
+                a0 = fmaf(v[p][j], my[p].w[j], a0);
+                if (j + 1 < PLIK_SEG) a1 = fmaf(v[p][j + 1], my[p].w[j + 1], a1);
+                if (j + 2 < PLIK_SEG) a2 = fmaf(v[p][j + 2], my[p].w[j + 2], a2);
             }
-            if (threadIdx.x == 0) row_scale[r] = q;
+            acc[p] = (a0 + a1) + a2;
+        }
+#pragma unroll
+        for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
+            float sum = acc[p];
+#pragma unroll
+            for (int k = 1; k < PLIK_MAX_SLOTS_PER_BIN; ++k) {
+                const float o = __shfl_down_sync(0xffffffffu, acc[p], k);
+                if (k < my[p].n_slots) sum += o;
+            }
+            const bool owner = my[p].bin >= 0;
+            const float model = sum * scale;
+            if (brow && owner) brow[my[p].bin] = model;
+            const float d = my[p].x_data - model;
+            if (TILES) {
+                const float vv = d * my[p].sqrt_f;
+                if (owner) {
+                    asm volatile("st.shared.f32 [%0], %1;" :: "r"(vrow_s + 4u * static_cast<uint32_t>(my[p].bin)), "f"(vv) : "memory");
+                    vmax = fmaxf(vmax, fabsf(vv));
+                }
+            } else if (owner) drow[my[p].bin] = d;
+        }
+        if (TILES) {
+            // warp maximum in one instruction: non-negative floats order like their bit patterns (a NaN sorts above inf and
+            // leaves q = 1 in write_row, like inf)
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+            if ((threadIdx.x & 31) == 0) vrow[diff_pitch + (threadIdx.x >> 5)] = __uint_as_float(wm);
+            if (r_prev >= 0) write_row(r_prev, vrow0 + (par ^ 1) * vstride);
+            r_prev = r;
+            par ^= 1;
         }
         buf = buf + 1 == PLIK_RING ? 0 : buf + 1;
+    }
+    if (TILES && r_prev >= 0) {
+        __syncthreads();
+        write_row(r_prev, vrow0 + (par ^ 1) * vstride);
     }
 }
 
