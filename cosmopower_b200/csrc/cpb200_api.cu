@@ -1547,10 +1547,10 @@ int cpb200_plik_create(const cpb200_plik_desc* d, int32_t device, cpb200_plik** 
     const int n_passes = static_cast<int>(slots.size() / cpb::PLIK_BIN_THREADS);
     if (n_passes > cpb::PLIK_MAX_PASSES)
         return fail(CPB200_E_UNSUPPORTED, "%zu window slots exceed %d", slots.size(), cpb::PLIK_MAX_PASSES * cpb::PLIK_BIN_THREADS);
-    const size_t bin_smem = (cpb::PLIK_BAR_FLOATS + static_cast<size_t>(cpb::PLIK_RING) * (row_floats + cpb::PLIK_ROW_PAD) +
-                             2 * (round_up(d->n_bins, cpb::PLIK_QF_BN) + cpb::PLIK_BIN_THREADS / 32)) * sizeof(float);
+    const size_t bin_smem = (cpb::PLIK_BAR_FLOATS + static_cast<size_t>(cpb::PLIK_GROUPS * cpb::PLIK_R) * (row_floats + cpb::PLIK_ROW_PAD) +
+                             2 * cpb::PLIK_R * (round_up(d->n_bins, cpb::PLIK_QF_BN) + cpb::PLIK_BIN_THREADS / 32)) * sizeof(float);
     if (bin_smem > prop.sharedMemPerBlockOptin)
-        return fail(CPB200_E_UNSUPPORTED, "the row ring of 3 x %d multipoles does not fit one block's shared memory", d->n_ell);
+        return fail(CPB200_E_UNSUPPORTED, "the row ring of 4 x 3 x %d multipoles does not fit one block's shared memory", d->n_ell);
     cpb200_plik* p = new cpb200_plik();
     auto bail = [&](int rc) { plik_free(p); return rc; };
     p->device = device;

@@ -22,8 +22,8 @@ namespace cpb {
 constexpr int PLIK_BIN_THREADS = 256;
 constexpr int PLIK_QF_BM = 128, PLIK_QF_BN = 128, PLIK_QF_BK = 16;
 
-// Persistent blocks (three per SM) walking rows with a PLIK_RING-deep shared-memory ring: while a row is being binned
-// the next two rows are already on their way (one bulk copy per input and row, completion on the buffer's mbarrier;
+// Persistent blocks (three per SM) walking rows through a shared-memory ring of PLIK_GROUPS groups of PLIK_R row buffers: while a group is being binned
+// the next one is already on its way (one bulk copy per input and row, completion on the group's mbarrier;
 // each input starts 16-byte aligned in shared memory).  A slot is a run of at most PLIK_SEG consecutive multipoles of one bin; the host splits the 5 ... 33
 // wide bins into slots so that the per-thread work is short, balanced and fully unrolled, and lays a bin's slots out on
 // neighbouring lanes of one warp.  Every thread owns the same <= PLIK_MAX_PASSES slots for every row, so their window
@@ -32,7 +32,8 @@ constexpr int PLIK_QF_BM = 128, PLIK_QF_BN = 128, PLIK_QF_BK = 16;
 constexpr int PLIK_SEG = 9;
 constexpr int PLIK_MAX_PASSES = 3;
 constexpr int PLIK_MAX_SLOTS_PER_BIN = 4;
-constexpr int PLIK_RING = 3;             // row buffers per block: one being binned, two in flight
+constexpr int PLIK_R = 2;                // rows binned per loop iteration (per block barrier)
+constexpr int PLIK_GROUPS = 2;           // ring of row-buffer groups per block: one group being binned, one in flight
 constexpr int PLIK_BLOCKS_PER_SM = 3;      // 80 registers per thread, 3 x 63 KB of shared memory
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
@@ -70,13 +71,20 @@ struct PlikInputs {
     int len[3];            // floats per row
 };
 
-// Shared memory of one block: PLIK_RING mbarriers (32 bytes), the row ring - each buffer holds the three inputs back to
+// Shared memory of one block: the groups' mbarriers (32 bytes), the row ring - each buffer holds the three inputs back to
 // back (every one starting 16-byte aligned) plus PLIK_ROW_PAD zero floats, because a slot always reads PLIK_SEG
 // elements (those beyond its end carry weight 0) -, the row's scaled differences and the per-warp maxima.
 constexpr int PLIK_ROW_PAD = 8;
 constexpr int PLIK_BAR_FLOATS = 8;
 
 // TILES: tensor-core quadratic form behind it (scaled differences + operand tiles); false: plain differences for the fp32 one
+//
+// What bounds this kernel is instruction issue and the block barrier, not HBM (ncu, round 2: 65 % of the issue slots and 490
+// instructions per thread and row in its first form; 30 % of the warp time in the barrier once those were halved).  Hence:
+// PLIK_R rows per loop iteration and barrier (the window weights in a thread's registers serve both), a row written out one
+// iteration after it was binned (so that ONE barrier per iteration separates the ring hand-over and the row-maximum
+// exchange), the fetch left to warp 0, the row / tile stores to the 80 threads that own a 16-byte chunk, shared-memory
+// addresses kept as pinned 32-bit integers (the compiler otherwise re-derives every loop invariant from the parameters).
 template <bool TILES>
 __global__ void __launch_bounds__(PLIK_BIN_THREADS, PLIK_BLOCKS_PER_SM)
 plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
@@ -85,28 +93,26 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
                 uint8_t* __restrict__ tiles, float* __restrict__ row_scale)
 {
     extern __shared__ __align__(16) float plik_smem[];
+    constexpr int R = PLIK_R, G = PLIK_GROUPS;
     int off1 = (in.len[0] + 3) & ~3, off2 = off1 + ((in.len[1] + 3) & ~3);
     int buf_floats = off2 + ((in.len[2] + 3) & ~3) + PLIK_ROW_PAD;
-    asm volatile("" : "+r"(off1), "+r"(off2), "+r"(buf_floats));      // pinned in registers: the compiler would otherwise re-derive
-                                                                      // every loop invariant from the parameters in each iteration
+    asm volatile("" : "+r"(off1), "+r"(off2), "+r"(buf_floats));      // pinned in registers
+    // shared memory: G mbarriers | ring of G groups x R row buffers | 2 x R copies of {scaled differences, per-warp maxima}
     float* ring = plik_smem + PLIK_BAR_FLOATS;
-    // tensor-core mode (tiles != nullptr): TWO copies of {the row's scaled differences, the per-warp maxima} - a row is
-    // binned in one loop iteration and scaled / written out in the next, so one block barrier per row separates both the
-    // ring hand-over and the row-maximum exchange (the first version needed two, and the kernel is bound by them)
-    float* vrow0 = ring + PLIK_RING * buf_floats;
+    float* vrow0 = ring + G * R * buf_floats;
     const int vstride = diff_pitch + PLIK_BIN_THREADS / 32;
     const uint32_t bar0 = static_cast<uint32_t>(__cvta_generic_to_shared(plik_smem));
     // zero everything once: the pads between and after the inputs stay zero for the whole launch
-    for (int i = threadIdx.x; i < PLIK_RING * buf_floats + 2 * vstride; i += PLIK_BIN_THREADS) ring[i] = 0.f;
+    for (int i = threadIdx.x; i < G * R * buf_floats + 2 * R * vstride; i += PLIK_BIN_THREADS) ring[i] = 0.f;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < PLIK_RING; ++i) mbar_init(bar0 + 8u * i, 1);
+        for (int i = 0; i < G; ++i) mbar_init(bar0 + 8u * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill is ordered before the bulk copies' writes
     __syncthreads();
 
     // An input whose rows are 16-byte aligned arrives by one bulk copy per row (issued by thread 0, completion counted on
-    // the buffer's mbarrier) plus at most three 4-byte cp.async for the elements beyond the last multiple of four; any
+    // the group's mbarrier) plus at most three 4-byte cp.async for the elements beyond the last multiple of four; any
     // other input is gathered 4 bytes at a time by the whole block.
     bool vec[3];
     uint32_t bulk_bytes = 0;
@@ -115,57 +121,72 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
         vec[s] = (in.pitch[s] & 3) == 0 && (reinterpret_cast<uintptr_t>(in.ptr[s]) & 15) == 0;
         if (vec[s]) bulk_bytes += static_cast<uint32_t>(in.len[s] >> 2) * 16u;
     }
+    int all_vec = vec[0] && vec[1] && vec[2];
+    asm volatile("" : "+r"(all_vec), "+r"(bulk_bytes));
 
     PlikSlot my[PLIK_MAX_PASSES];
 #pragma unroll
     for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
         if (p < n_passes) my[p] = slots[p * PLIK_BIN_THREADS + threadIdx.x];
-        else { my[p].off = 0; my[p].last = 0; my[p].bin = -1; my[p].n_slots = 0; my[p].x_data = 0.f;
+        else { my[p].off = 0; my[p].last = 0; my[p].bin = -1; my[p].n_slots = 0; my[p].x_data = 0.f; my[p].sqrt_f = 0.f;
 #pragma unroll
                for (int j = 0; j < PLIK_SEG; ++j) my[p].w[j] = 0.f; }
     }
 
-    // (the kernel is bound by instruction issue - ncu, round 2: 65 % of the issue slots, 490 instructions per thread and row
-    // in its first form - so everything a single warp can do is kept away from the other seven)
-    int all_vec = vec[0] && vec[1] && vec[2];
-    asm volatile("" : "+r"(all_vec), "+r"(bulk_bytes));                           // pinned: otherwise re-derived from the parameters in every iteration
-    auto fetch = [&](long long r, int buf) {                    // always commits a group (empty past the last row)
-        if (all_vec) {
-            // warp 0 alone: lane 0 issues the three bulk copies, lanes 1 .. 9 the (at most three per input) tail elements
-            if (threadIdx.x >= 32) return;
-            if (r < n_rows) {
-                float* dst0 = ring + buf * buf_floats;
-                const uint32_t bar = bar0 + 8u * buf;
-                if (threadIdx.x == 0) {
-                    mbar_arrive_expect_tx(bar, bulk_bytes);
+    const long long stride = gridDim.x;
+    // rows r, r + stride, ... r + (R - 1) stride into the R buffers of group g; always commits a cp.async group
+    auto fetch = [&](long long r, int g) {
+        const uint32_t bar = bar0 + 8u * g;
+        int n_valid = 0;
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        const int n4 = in.len[s] >> 2;
-                        if (n4) bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(dst0 + (s == 0 ? 0 : s == 1 ? off1 : off2))),
-                                         in.ptr[s] + r * in.pitch[s], static_cast<uint32_t>(n4) * 16u, bar);
+        for (int j = 0; j < R; ++j) n_valid += (r + j * stride < n_rows) ? 1 : 0;
+        if (all_vec) {
+            // the LAST warp alone (the first ones carry the row write-out): its lane 0 issues the bulk copies, lanes
+            // 1 + 10 j + (0 .. 8) the (at most three per input) tail elements of row j
+            if (threadIdx.x < PLIK_BIN_THREADS - 32) return;
+            const int lane = static_cast<int>(threadIdx.x) - (PLIK_BIN_THREADS - 32);
+            if (lane == 0) {
+                if (n_valid) mbar_arrive_expect_tx(bar, bulk_bytes * n_valid);
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const long long rj = r + j * stride;
+                    if (rj < n_rows) {
+                        float* dst0 = ring + (g * R + j) * buf_floats;
+#pragma unroll
+                        for (int s = 0; s < 3; ++s) {
+                            const int n4 = in.len[s] >> 2;
+                            if (n4) bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(dst0 + (s == 0 ? 0 : s == 1 ? off1 : off2))),
+                                             in.ptr[s] + rj * in.pitch[s], static_cast<uint32_t>(n4) * 16u, bar);
+                        }
                     }
-                } else if (threadIdx.x < 10) {
-                    const int s = (static_cast<int>(threadIdx.x) - 1) / 3, u = (static_cast<int>(threadIdx.x) - 1) % 3;
+                }
+            } else {
+                const int l = lane - 1, j = l / 10, k = l % 10;
+                const long long rj = r + j * stride;
+                if (j < R && k < 9 && rj < n_rows) {
+                    const int s = k / 3, u = k % 3;
                     const int len = s == 0 ? in.len[0] : s == 1 ? in.len[1] : in.len[2];
                     const int i = (len & ~3) + u;
                     if (i < len) {
-                        const float* src = (s == 0 ? in.ptr[0] : s == 1 ? in.ptr[1] : in.ptr[2]) + r * (s == 0 ? in.pitch[0] : s == 1 ? in.pitch[1] : in.pitch[2]);
-                        cp_async_4(dst0 + (s == 0 ? 0 : s == 1 ? off1 : off2) + i, src + i);
+                        const float* src = (s == 0 ? in.ptr[0] : s == 1 ? in.ptr[1] : in.ptr[2]) + rj * (s == 0 ? in.pitch[0] : s == 1 ? in.pitch[1] : in.pitch[2]);
+                        cp_async_4(ring + (g * R + j) * buf_floats + (s == 0 ? 0 : s == 1 ? off1 : off2) + i, src + i);
                     }
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             return;
         }
-        if (r < n_rows) {
-            float* dst0 = ring + buf * buf_floats;
-            const uint32_t bar = bar0 + 8u * buf;
-            if (threadIdx.x == 0) {
-                if (bulk_bytes) mbar_arrive_expect_tx(bar, bulk_bytes); else mbar_arrive(bar);
-            }
+        if (threadIdx.x == 0 && n_valid) {
+            if (bulk_bytes) mbar_arrive_expect_tx(bar, bulk_bytes * n_valid); else mbar_arrive(bar);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const long long rj = r + j * stride;
+            if (rj >= n_rows) continue;
+            float* dst0 = ring + (g * R + j) * buf_floats;
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const float* src = in.ptr[s] + r * in.pitch[s];
+                const float* src = in.ptr[s] + rj * in.pitch[s];
                 float* dst = dst0 + (s == 0 ? 0 : s == 1 ? off1 : off2);
                 const int len = in.len[s];
                 if (vec[s]) {
@@ -187,18 +208,22 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
     // fp16 hi/lo of 1024 q v in the swizzled K-major tile layout the fused kernel's loader streams.
     // Only the diff_pitch / 8 threads that own a 16-byte chunk of the operand tile take part: each reads its eight values
     // once and writes both forms (the fp32 row and the split tile) with 16-byte stores.
-    const int tile_stage_off = (static_cast<int>(threadIdx.x) >> 2) * 16384, tile_kchunk = static_cast<int>(threadIdx.x) & 3;
+    // The R rows of a group are dealt to the R halves of the block (thread t: row t / 128, chunk t % 128), so that no warp
+    // carries more than one row's write-out while the others wait at the barrier.
+    static_assert(PLIK_BIN_THREADS % PLIK_R == 0, "rows of a group are dealt to equal parts of the block");
+    constexpr int WT = PLIK_BIN_THREADS / PLIK_R;
+    const int w_row = static_cast<int>(threadIdx.x) / WT, w_ch = static_cast<int>(threadIdx.x) % WT;
+    const int tile_stage_off = (w_ch >> 2) * 16384, tile_kchunk = w_ch & 3;
     const long long tile_bytes = static_cast<long long>(diff_pitch / 32) * 16384;
     auto write_row = [&](long long rr, const float* vrow) {
-        if (static_cast<int>(threadIdx.x) >= diff_pitch / 8) return;
         const float4 m0 = *reinterpret_cast<const float4*>(vrow + diff_pitch), m1 = *reinterpret_cast<const float4*>(vrow + diff_pitch + 4);
         const float m = fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w)));
         // q = 2^-ex with m = f 2^ex, f in [0.5, 1): the exponent field alone (zero, subnormal, inf / NaN maxima keep q = 1)
         const uint32_t be = (__float_as_uint(m) >> 23) & 0xffu;
         const float q = (be >= 1u && be <= 253u) ? __uint_as_float((253u - be) << 23) : 1.f;
-        const float4 a = *reinterpret_cast<const float4*>(vrow + 8 * threadIdx.x), b = *reinterpret_cast<const float4*>(vrow + 8 * threadIdx.x + 4);
+        const float4 a = *reinterpret_cast<const float4*>(vrow + 8 * w_ch), b = *reinterpret_cast<const float4*>(vrow + 8 * w_ch + 4);
         const float x[8] = {a.x * q, a.y * q, a.z * q, a.w * q, b.x * q, b.y * q, b.z * q, b.w * q};
-        float* drow = diff + rr * diff_pitch + 8 * threadIdx.x;
+        float* drow = diff + rr * diff_pitch + 8 * w_ch;
         *reinterpret_cast<float4*>(drow) = make_float4(x[0], x[1], x[2], x[3]);
         *reinterpret_cast<float4*>(drow + 4) = make_float4(x[4], x[5], x[6], x[7]);
         const int rt = static_cast<int>(rr & 127);
@@ -208,48 +233,35 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
         uint8_t* t = tiles + (rr >> 7) * tile_bytes + tile_stage_off + rt * 64 + ((tile_kchunk ^ (rt >> 1)) & 3) * 16;
         *reinterpret_cast<uint4*>(t) = hi;
         *reinterpret_cast<uint4*>(t + 8192) = lo;
-        if (threadIdx.x == 0) row_scale[rr] = q;
+        if (w_ch == 0) row_scale[rr] = q;
+    };
+    // rows rr, rr + stride, ... binned in the previous iteration (their copies of the differences: parity `pv`)
+    auto write_group = [&](long long rr, int pv) {
+        if (w_ch >= diff_pitch / 8 || diff_pitch / 8 > WT) return;
+        const long long rj = rr + w_row * stride;
+        if (rj < n_rows) write_row(rj, vrow0 + (pv * R + w_row) * vstride);
     };
 
-    const long long stride = gridDim.x;
     long long r = blockIdx.x;
 #pragma unroll
-    for (int i = 0; i < PLIK_RING - 1; ++i) fetch(r + i * stride, i);
+    for (int i = 0; i < G - 1; ++i) fetch(r + i * R * stride, i);
     uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring)), vrow0_s = static_cast<uint32_t>(__cvta_generic_to_shared(vrow0));
     uint32_t buf_bytes = 4u * buf_floats, vstride_bytes = 4u * vstride;
     asm volatile("" : "+r"(ring_s), "+r"(vrow0_s), "+r"(buf_bytes), "+r"(vstride_bytes));      // pinned in registers
 #pragma unroll
     for (int p = 0; p < PLIK_MAX_PASSES; ++p) { my[p].off *= 4; asm volatile("" : "+r"(my[p].off), "+r"(my[p].bin)); }
-    int buf = 0, par = 0;
-    float c_next = r < n_rows ? cal[r] : 1.f;
-    long long r_prev = -1;                                       // binned in the previous iteration, not yet written out
-    uint32_t phases = 0;                                         // one parity bit per ring buffer
-    for (; r < n_rows; r += stride) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(PLIK_RING - 2) : "memory");    // this thread's 4-byte copies of row r have landed
-        while (!mbar_try_wait(bar0 + 8u * buf, (phases >> buf) & 1u)) { }          // ... and the row's bulk copies
-        phases ^= 1u << buf;
-        const float c = c_next;                                  // loaded one iteration ahead: a dependent global load per row
-        if (r + stride < n_rows) c_next = cal[r + stride];       // would sit on the critical path (9 % of the stall samples)
+
+    // one row: the thread's slots (loads of all passes first, then the arithmetic - the passes are independent chains; a pass
+    // that does not exist has off = 0, weights 0 and bin = -1: it costs its instructions but keeps the code branch-free)
+    auto bin_row = [&](long long rr, float c, uint32_t row_s, uint32_t vrow_s) {
         const float scale = units_factor / (c * c);
-        float vmax = 0.f;
-        __syncthreads();                                         // row r is complete for every thread; every thread has binned the
-                                                                 // previous row (its ring buffer is free, its differences and maxima are
-                                                                 // complete) and written out the row before that (its copy is free)
-        fetch(r + (PLIK_RING - 1) * stride, buf == 0 ? PLIK_RING - 1 : buf - 1);     // refill the buffer of the previous row
-        // shared-memory addresses as 32-bit integers behind explicit ld / st.shared: left to itself the compiler re-derives
-        // `ring + buf * buf_floats + off` from the kernel parameters in every pass (a dozen instructions each time)
-        const uint32_t row_s = ring_s + static_cast<uint32_t>(buf) * buf_bytes;
-        const uint32_t vrow_s = vrow0_s + static_cast<uint32_t>(par) * vstride_bytes;
-        float* vrow = vrow0 + par * vstride;
-        float* brow = binned ? binned + r * binned_pitch : nullptr;          // (optional) band powers of this row
-        float* drow = TILES ? nullptr : diff + r * diff_pitch;
+        float* brow = binned ? binned + rr * binned_pitch : nullptr;         // (optional) band powers of this row
+        float* drow = TILES ? nullptr : diff + rr * diff_pitch;
         asm volatile("" : "+l"(brow), "+l"(drow));
-        // all passes' loads first, then the arithmetic: the passes are independent chains, and a pass that does not exist
-        // (p >= n_passes) has off = 0, weights 0 and bin = -1 - it costs its instructions but keeps the code branch-free
         float v[PLIK_MAX_PASSES][PLIK_SEG];
 #pragma unroll
         for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
-            const uint32_t qa = row_s + static_cast<uint32_t>(my[p].off);              // byte offset (scaled before the loop)
+            const uint32_t qa = row_s + static_cast<uint32_t>(my[p].off);              // byte offset (scaled above)
 #pragma unroll
             for (int j = 0; j < PLIK_SEG; ++j)                   // beyond the slot's end: neighbouring data or zero pad, weight 0
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[p][j]) : "r"(qa + 4u * j));
@@ -266,6 +278,7 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
             }
             acc[p] = (a0 + a1) + a2;
         }
+        float vmax = 0.f;
 #pragma unroll
         for (int p = 0; p < PLIK_MAX_PASSES; ++p) {
             float sum = acc[p];
@@ -290,16 +303,47 @@ plik_bin_kernel(PlikInputs in, const float* __restrict__ cal, long long n_rows,
             // warp maximum in one instruction: non-negative floats order like their bit patterns (a NaN sorts above inf and
             // leaves q = 1 in write_row, like inf)
             const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-            if ((threadIdx.x & 31) == 0) vrow[diff_pitch + (threadIdx.x >> 5)] = __uint_as_float(wm);
-            if (r_prev >= 0) write_row(r_prev, vrow0 + (par ^ 1) * vstride);
+            if ((threadIdx.x & 31) == 0)
+                asm volatile("st.shared.b32 [%0], %1;" :: "r"(vrow_s + 4u * static_cast<uint32_t>(diff_pitch) + 4u * (threadIdx.x >> 5)), "r"(wm) : "memory");
+        }
+    };
+
+    int g = 0, par = 0;
+    float c_next[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) c_next[j] = r + j * stride < n_rows ? cal[r + j * stride] : 1.f;
+    long long r_prev = -1;                                       // first row of the group binned in the previous iteration, not yet written out
+    uint32_t phases = 0;                                         // one parity bit per group
+    for (; r < n_rows; r += R * stride) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(G - 2) : "memory");            // this thread's 4-byte copies of the group have landed
+        while (!mbar_try_wait(bar0 + 8u * g, (phases >> g) & 1u)) { }              // ... and its bulk copies
+        phases ^= 1u << g;
+        float c[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {                            // loaded one iteration ahead: a dependent global load per row
+            c[j] = c_next[j];                                    // would sit on the critical path (9 % of the stall samples)
+            const long long rn = r + (R + j) * stride;
+            if (rn < n_rows) c_next[j] = cal[rn];
+        }
+        __syncthreads();                                         // the group is complete for every thread; every thread has binned the
+                                                                 // previous group (its buffers are free, its differences and maxima are
+                                                                 // complete) and written out the group before that (its copies are free)
+        fetch(r + (G - 1) * R * stride, g == 0 ? G - 1 : g - 1);                   // refill the buffers of the previous group
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (r + j * stride < n_rows)                          // uniform across the block
+                bin_row(r + j * stride, c[j], ring_s + static_cast<uint32_t>(g * R + j) * buf_bytes,
+                        vrow0_s + static_cast<uint32_t>(par * R + j) * vstride_bytes);
+        if (TILES) {
+            if (r_prev >= 0) write_group(r_prev, par ^ 1);
             r_prev = r;
             par ^= 1;
         }
-        buf = buf + 1 == PLIK_RING ? 0 : buf + 1;
+        g = g + 1 == G ? 0 : g + 1;
     }
     if (TILES && r_prev >= 0) {
         __syncthreads();
-        write_row(r_prev, vrow0 + (par ^ 1) * vstride);
+        write_group(r_prev, par ^ 1);
     }
 }
 
