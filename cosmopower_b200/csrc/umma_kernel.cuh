@@ -913,6 +913,10 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             /* rows beyond n_rows are padding (computed, never stored) */                              \
             const long long pidx = is_next ? it : it - 1;      /* this cluster's running pair number */  \
             const long long pair = (pg_first + pidx * pg_step) * UM_CLUSTER + cta_rank;                \
+            /* a pair-group whose second tiles hold no row at all (the leader's tile 1 starts beyond the batch, so  \
+               the peer's tiles do too): every role skips the t = 1 jobs - a batch of up to 128 rows, a sampler's   \
+               single point, then walks one tile through the network instead of two (it is a cluster's last group) */ \
+            if (t == 1 && ((pg_first + pidx * pg_step) * UM_CLUSTER * 2 + 1) * UM_TILE_M >= P.n_rows) continue; \
             const int ppar = is_next ? it_par : it_par ^ 1;            /* parity and residue mod 3 of the pair number */ \
             const int pm3 = is_next ? it_m3 : (it_m3 + 2) % 3;                                         \
             const int ts = 2 * ppar + t;                                                               \
