@@ -7,14 +7,19 @@
 
 #include <pthread.h>
 #include <sched.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -120,6 +125,7 @@ struct cpb200_engine {
     long long* d_counters = nullptr;    // debug counters, UM_CNT_SLOTS per CTA (allocated on demand)
     // host pipeline
     cudaStream_t hstream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_piece[16] = {};       // mid-size pageable results: one event per piece of the device->host transfer
     float* h_in[2] = {nullptr, nullptr};
     float* h_out[2] = {nullptr, nullptr};
     float* d_in[2] = {nullptr, nullptr};
@@ -981,6 +987,7 @@ int cpb200_destroy(cpb200_engine* e) {
         if (e->h_out[i]) cudaFreeHost(e->h_out[i]);
         cudaFree(e->d_in[i]); cudaFree(e->d_out[i]);
     }
+    for (cudaEvent_t ev : e->ev_piece) if (ev) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     cudaGetLastError();
@@ -1057,11 +1064,114 @@ int host_threads() {
     return n;
 }
 
+// A small persistent pool of host threads for the copy-out below.  Spawning threads per call is slow on this pool's guests
+// (~100 us apiece), and so is waking a sleeping one (tools/latency_breakdown.py, CPB200_HOST_THREADS = 1 / 4 / 16 on a 10 MB
+// result: 1.12 / 1.02 / 1.53 ms).  Hence SESSIONS: a host call that will copy out a few megabytes or more opens one before it
+// launches - the workers wake while the kernel and the transfer run and then poll a generation counter instead of sleeping,
+// so each piece of the result finds them ready - and closes it when it returns (RAII), which sends them back to sleep.  One
+// session at a time: a caller that finds the pool taken (another device's host thread) copies on its own.
+class HostPool {
+public:
+    static HostPool* get() {
+        static std::mutex guard;
+        static HostPool* pool = nullptr;
+        static pid_t owner = 0;
+        std::lock_guard<std::mutex> lk(guard);
+        if (!pool || owner != getpid()) {          // (a forked child has no workers: it gets a pool of its own; the old object leaks)
+            pool = new HostPool(std::max(0, host_threads() - 1));
+            owner = getpid();
+        }
+        return pool;
+    }
+    class Session {
+    public:
+        explicit Session(bool wanted) {
+            if (!wanted) return;
+            HostPool* p = HostPool::get();
+            if (p->workers_ == 0 || !p->use_.try_lock()) return;
+            pool_ = p;
+            p->hot_.store(true, std::memory_order_release);
+            { std::lock_guard<std::mutex> lk(p->m_); }
+            p->cv_work_.notify_all();
+        }
+        ~Session() {
+            if (!pool_) return;
+            pool_->hot_.store(false, std::memory_order_release);
+            pool_->use_.unlock();
+        }
+        Session(const Session&) = delete;
+        Session& operator=(const Session&) = delete;
+        bool active() const { return pool_ != nullptr; }
+        int threads() const { return pool_ ? pool_->workers_ + 1 : 1; }
+        // f(i) for i in [0, n) on the workers and the calling thread; returns when all are done
+        void run(int n, const std::function<void(int)>& f) {
+            HostPool* p = pool_;
+            {
+                std::lock_guard<std::mutex> lk(p->m_);
+                p->job_ = &f; p->n_ = n; p->next_ = 0;
+                p->pending_.store(n, std::memory_order_relaxed);
+            }
+            p->gen_.fetch_add(1, std::memory_order_release);
+            p->work();
+            while (p->pending_.load(std::memory_order_acquire) != 0) cpu_relax();
+            std::lock_guard<std::mutex> lk(p->m_);
+            p->job_ = nullptr;
+        }
+    private:
+        HostPool* pool_ = nullptr;
+    };
+private:
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    explicit HostPool(int n_workers) : workers_(n_workers) {
+        for (int i = 0; i < n_workers; ++i) std::thread([this] { loop(); }).detach();      // they live as long as the process
+    }
+    // claim and run tasks of the current job until none is left (task claims go through the mutex: tasks are coarse)
+    void work() {
+        for (;;) {
+            int i;
+            const std::function<void(int)>* f;
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (!job_ || next_ >= n_) return;
+                i = next_++; f = job_;
+            }
+            (*f)(i);
+            pending_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    void loop() {
+        uint64_t seen = gen_.load(std::memory_order_acquire);
+        for (;;) {
+            if (!hot_.load(std::memory_order_acquire)) {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return hot_.load(std::memory_order_acquire); });
+            }
+            const uint64_t g = gen_.load(std::memory_order_acquire);
+            if (g != seen) { seen = g; work(); }
+            else cpu_relax();
+        }
+    }
+    const int workers_;
+    std::mutex m_, use_;
+    std::condition_variable cv_work_;
+    std::atomic<bool> hot_{false};
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int> pending_{0};
+    const std::function<void(int)>* job_ = nullptr;      // guarded by m_
+    int n_ = 0, next_ = 0;                                // guarded by m_
+};
+
 // rows of float32 in a pinned bounce buffer -> the caller's (pageable) rows of float32 or float64.  Fresh NumPy arrays are
 // untouched memory: the page faults of the first write dominate a single-threaded copy (3-4 GB/s), so the rows are split
-// over the host threads - at least 1 MB of input per thread.
+// over the session's threads - at least 256 KB of input per thread; without a session the calling thread copies alone.
 template <typename T>
-void copy_rows_out(T* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t rows, int cols) {
+void copy_rows_out(T* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t rows, int cols, HostPool::Session& sess) {
     auto work = [=](int64_t r0, int64_t r1) {
         for (int64_t r = r0; r < r1; ++r) {
             const float* s = src + r * src_pitch;
@@ -1070,7 +1180,15 @@ void copy_rows_out(T* dst, int64_t dst_pitch, const float* src, int64_t src_pitc
             else for (int j = 0; j < cols; ++j) d[j] = static_cast<T>(s[j]);
         }
     };
-    const int nt = static_cast<int>(std::min<int64_t>(host_threads(), rows * cols / (1 << 18)));
+    if (sess.active()) {
+        const int nt = static_cast<int>(std::min<int64_t>(sess.threads(), rows * cols / (1 << 16)));
+        if (nt <= 1) { work(0, rows); return; }
+        sess.run(nt, [&](int t) { work(rows * t / nt, rows * (t + 1) / nt); });
+        return;
+    }
+    // no session (the pool serves another device's host thread, or the result is small): threads of its own from 8 MB on,
+    // where their start-up cost is a small part of the copy
+    const int nt = rows * static_cast<int64_t>(cols) >= (2 << 20) ? static_cast<int>(std::min<int64_t>(host_threads(), rows * cols / (1 << 18))) : 1;
     if (nt <= 1) { work(0, rows); return; }
     std::vector<std::thread> pool;
     pool.reserve(nt);
@@ -1100,6 +1218,8 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
     if (!pin_out) R = std::min<int64_t>(R, std::max<int64_t>(2048, (n_rows + 7) / 8 + 255) / 256 * 256);
     const int64_t n_chunks = (n_rows + R - 1) / R;
     const size_t row_bytes = sizeof(float) * e->n_modes;
+    // helpers for the copy-out: woken now, ready when the first piece lands (4 MB of result or more; see HostPool)
+    HostPool::Session session(!pin_out && n_rows * static_cast<int64_t>(row_bytes) >= (4ll << 20));
     // Tight host rows (the NumPy layout, and the bounce buffers): the kernel then writes tight rows on the device too and the
     // chunk leaves as ONE contiguous copy - 56.9 GB/s on this pool's boxes against 52.4 GB/s for the pitched 2-D copy of
     // 10028-byte rows (tools/microbench/d2h_copy_bw.cu).  Unaligned rows cost the kernel its vector stores (cmb_TT: 2x the
@@ -1137,13 +1257,40 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
         g_err = msg;
         return rc;
     };
+    // Mid-size pageable result (one chunk, a megabyte or more): ONE launch, then the transfer in up to 16 pieces, each copied
+    // out of the bounce buffer by this thread while the next ones are still on the wire - the copy-out (a single thread
+    // moves ~17 GB/s here; from 4 MB on the session's helpers share it) hides the transfer instead of following it
+    // (1024 cmb_TT rows: 1.1-1.5 ms before; tools/latency_breakdown.py).
+    if (!pin_out && n_chunks == 1 && n_rows * static_cast<int64_t>(row_bytes) >= (1ll << 20)) {
+        const int n_pieces = static_cast<int>(std::min<int64_t>(16, std::max<int64_t>(1, n_rows * static_cast<int64_t>(row_bytes) / (1ll << 20))));
+        for (int i = 0; i < n_pieces; ++i) if (!e->ev_piece[i]) CU(cudaEventCreateWithFlags(&e->ev_piece[i], cudaEventDisableTiming));
+        const float* src = params_host;
+        if (!pin_in) { memcpy(e->h_in[0], src, sizeof(float) * n_rows * e->P); src = e->h_in[0]; }
+        CU(cudaMemcpyAsync(e->d_in[0], src, sizeof(float) * n_rows * e->P, cudaMemcpyHostToDevice, e->hstream[0]));
+        if (int rc = forward_async(e, e->d_in[0], n_rows, e->d_out[0], dev_pitch, flags, e->hstream[0])) return bail(rc);
+        auto piece_lo = [&](int i) { return n_rows * i / n_pieces; };
+        for (int i = 0; i < n_pieces; ++i) {
+            const int64_t lo = piece_lo(i), m = piece_lo(i + 1) - lo;
+            const cudaError_t err = cudaMemcpy2DAsync(e->h_out[0] + lo * e->n_modes, row_bytes, e->d_out[0] + lo * dev_pitch, sizeof(float) * dev_pitch,
+                                                      row_bytes, m, cudaMemcpyDeviceToHost, e->hstream[0]);
+            if (err != cudaSuccess || cudaEventRecord(e->ev_piece[i], e->hstream[0]) != cudaSuccess)
+                return bail(fail(CPB200_E_CUDA, "device->host piece %d failed: %s", i, cudaGetErrorString(cudaGetLastError())));
+        }
+        for (int i = 0; i < n_pieces; ++i) {
+            const cudaError_t err = cudaEventSynchronize(e->ev_piece[i]);
+            if (err != cudaSuccess) return bail(fail_sync(e, err, "cudaEventSynchronize"));
+            const int64_t lo = piece_lo(i), m = piece_lo(i + 1) - lo;
+            copy_rows_out(out_host + lo * out_pitch, out_pitch, e->h_out[0] + lo * e->n_modes, e->n_modes, m, e->n_modes, session);
+        }
+        return check_range(e);
+    }
     for (int64_t c = 0; c < n_chunks + 2; ++c) {
         const int slot = static_cast<int>(c & 1);
         if (c >= 2) {   // retire chunk c-2 of this slot
             const cudaError_t err = cudaStreamSynchronize(e->hstream[slot]);
             if (err != cudaSuccess) return bail(fail_sync(e, err, "cudaStreamSynchronize"));
             const int64_t r0 = (c - 2) * R, m = std::min<int64_t>(R, n_rows - r0);
-            if (!pin_out) copy_rows_out(out_host + r0 * out_pitch, out_pitch, e->h_out[slot], e->n_modes, m, e->n_modes);
+            if (!pin_out) copy_rows_out(out_host + r0 * out_pitch, out_pitch, e->h_out[slot], e->n_modes, m, e->n_modes, session);
         }
         if (c < n_chunks) if (int rc = submit(c, slot)) return bail(rc);
     }
