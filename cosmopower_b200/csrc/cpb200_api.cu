@@ -1058,7 +1058,12 @@ namespace {
 int host_threads() {
     static const int n = [] {
         const char* s = getenv("CPB200_HOST_THREADS");
-        const int v = s ? atoi(s) : static_cast<int>(std::thread::hardware_concurrency());
+        int v = s ? atoi(s) : static_cast<int>(std::thread::hardware_concurrency());
+        if (!s) {   // no more than the CPUs this process may run on (taskset, cpusets, a rank pinned next to its GPU)
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) v = std::min(v, CPU_COUNT(&set));
+        }
         return std::max(1, std::min(v, 32));
     }();
     return n;
@@ -1147,14 +1152,16 @@ private:
     }
     void loop() {
         uint64_t seen = gen_.load(std::memory_order_acquire);
+        unsigned idle = 0;
         for (;;) {
             if (!hot_.load(std::memory_order_acquire)) {
                 std::unique_lock<std::mutex> lk(m_);
                 cv_work_.wait(lk, [&] { return hot_.load(std::memory_order_acquire); });
             }
             const uint64_t g = gen_.load(std::memory_order_acquire);
-            if (g != seen) { seen = g; work(); }
-            else cpu_relax();
+            if (g != seen) { seen = g; work(); idle = 0; }
+            else if (++idle < 4096) cpu_relax();
+            else std::this_thread::yield();          // an oversubscribed host (CPU quota, many ranks): give the caller the core
         }
     }
     const int workers_;
