@@ -483,7 +483,7 @@ def test_fused_pk_pair_is_one_launch_and_equals_the_two_launch_path():
     import torch
     lin, a_lin = get_model("PKLIN_NN")
     nl, a_nl = get_model("PKNLBOOST_NN")
-    for n in (257, 100000):
+    for n in (100, 257, 100000):               # 100: a lone tile - the launch skips the pair's empty second tile in every role
         x_nl = priors.sample_prior(nl.parameters, n, seed=321)
         cols = [nl.parameters.index(k) for k in lin.parameters]
         xb = torch.from_numpy(x_nl.astype(np.float32)).cuda()
