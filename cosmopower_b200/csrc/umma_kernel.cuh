@@ -435,12 +435,17 @@ __device__ __forceinline__ void split2n(uint64_t ab, uint32_t& hi, uint32_t& nlo
 #ifndef UM_RANGE_CHECK
 #define UM_RANGE_CHECK 1      // producers of split operands report values beyond the fp16 range (0: saturate silently)
 #endif
+#ifndef UM_ACCURATE_ACT
+#define UM_ACCURATE_ACT 0     // 1 (accuracy study only): exp2f / IEEE division instead of the MUFU approximations
+#endif
 __device__ __forceinline__ float ex2_approx(float x) {
+    if (UM_ACCURATE_ACT) return exp2f(x);
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ float rcp_approx(float x) {
+    if (UM_ACCURATE_ACT) return __frcp_rn(x);
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
