@@ -115,7 +115,10 @@ int cpb200_forward_device(cpb200_engine* e, const float* params_dev, int64_t n_r
  * (cosmopower_NN.py:354-425; cosmopower_PCAplusNN.py:351-421).  Host float32 in, host float32
  * out; the copies host->device and device->host are pipelined with the kernel in row chunks.
  * Buffers from cpb200_host_alloc (pinned) are DMA'd directly; pageable buffers go through the
- * engine's pinned bounce buffers.  Synchronous: returns when `out_host` is complete.
+ * engine's pinned bounce buffers (a result of up to 2048 rows leaves in pieces behind ONE launch, each copied out while
+ * the next are on the wire; larger ones in row chunks of an eighth of the batch).  The copy-out runs on a small pool of
+ * library threads that are woken for the duration of a call with 4 MB of result or more and sleep otherwise
+ * (CPB200_HOST_THREADS, default: the CPUs the process may run on, at most 32).  Synchronous: returns when `out_host` is complete.
  * Only the n_modes floats of each row are written: with out_pitch > n_modes the padding is left alone (pitched copy);
  * with out_pitch == n_modes a transfer of 256 MB or more leaves the device as one contiguous copy per chunk, which is
  * ~8 % faster over PCIe than the pitched copy - the layout to choose for bulk results.
@@ -127,7 +130,7 @@ int cpb200_forward_host(cpb200_engine* e, const float* params_host, int64_t n_ro
  * The same call with a float64 result: the reference computes in the dtype NumPy promotion gives its input
  * (cosmopower_NN.py:371-384, cosmopower_PCAplusNN.py:368-381: float64 for dicts of lists / float64 arrays), so
  * predictions_np returns float64 there.  The device result (float32) is widened while it is copied out of the pinned
- * bounce buffers, rows split over the host threads (CPB200_HOST_THREADS, default all, at most 32); out_pitch in doubles.
+ * bounce buffers, rows split over the library's host threads (see above); out_pitch in doubles.
  */
 int cpb200_forward_host_f64(cpb200_engine* e, const float* params_host, int64_t n_rows,
                             double* out_host, int64_t out_pitch, int flags);
