@@ -53,7 +53,8 @@ def test_seeded_batch_against_oracle(name):
     assert parity.model_error(name, y, y_ref) <= parity.model_tol(name)
 
 
-@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 255, 257, 300, 1025])
+# (37938 = one full wave of 74 clusters x 512 rows + 50: a cluster's SECOND pair-group is a lone tile, whose empty partner is skipped)
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 255, 257, 300, 1025, 37938])
 def test_ragged_row_counts(n):
     name = "PKLIN_NN"
     m, attrs = get_model(name)
