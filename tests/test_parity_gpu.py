@@ -297,7 +297,10 @@ def test_small_batch_output_split_is_bit_identical(name, n, monkeypatch):
     assert err <= parity.model_tol(name), (name, n, err)
 
 
-@pytest.mark.parametrize("name,n", [("cmb_TT_NN", 1), ("cmb_TT_NN", 5000), ("PKLIN_NN", 20000), ("cmb_PP_PCAplusNN", 20011)])
+# (200 / 1500 cmb_TT rows and 2048 PKLIN rows: one-chunk results of 2 / 15 / 3.4 MB, which leave in pieces behind ONE launch - the
+# 15 MB one copied out by the session's pool threads; the larger sizes go through the two-slot chunk pipeline)
+@pytest.mark.parametrize("name,n", [("cmb_TT_NN", 1), ("cmb_TT_NN", 200), ("cmb_TT_NN", 1500), ("PKLIN_NN", 2048), ("cmb_TT_NN", 5000),
+                                    ("PKLIN_NN", 20000), ("cmb_PP_PCAplusNN", 20011)])
 def test_float64_host_path_is_the_widened_float32_result(name, n):
     """cpb200_forward_host_f64 (what predictions_np returns for float64 / list inputs) widens the device's float32 result
     with the host threads while copying it out, in smaller pipeline chunks than the float32 call: same values exactly,
@@ -308,6 +311,8 @@ def test_float64_host_path_is_the_widened_float32_result(name, n):
     y32 = eng.forward_host(x, ten_to=True)
     y64 = eng.forward_host(x, ten_to=True, dtype=np.float64)
     assert y64.dtype == np.float64 and np.array_equal(y64, y32.astype(np.float64))
+    import torch
+    assert np.array_equal(y32, m.ten_to_predictions_tf(torch.from_numpy(x).cuda()).cpu().numpy())      # the device-tensor call's bits
     wide = np.full((n, m.n_modes + 5), -1.0, dtype=np.float64)
     eng.forward_host(x, out=wide[:, :m.n_modes], ten_to=True)
     assert np.array_equal(wide[:, :m.n_modes], y64) and (wide[:, m.n_modes:] == -1.0).all()
