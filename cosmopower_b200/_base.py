@@ -55,8 +55,27 @@ class _EmulatorBase:
             except Exception:
                 pass
         if dev not in self._engines:
-            self._engines[dev] = _engine.Engine(self._attrs(), device=dev, precision=self._precision)
+            if self._precision not in ("f16x3", "fp32", "auto"):
+                raise ValueError("precision must be \"f16x3\", \"fp32\" or \"auto\", got %r" % (self._precision,))
+            self._engines[dev] = _engine.Engine(self._attrs(), device=dev, precision="f16x3" if self._precision == "auto" else self._precision)
         return self._engines[dev]
+
+    # precision="auto" (extension): batches of up to SMALL_ROWS rows - a sampler's single point - run on the fp32 CUDA-core
+    # kernels, whose column-per-warp form takes 35-50 us per call against 100-120 us for the tensor path (one tile walks the
+    # whole network whatever the batch); larger batches use the tensor path.  Both are inside the tolerance; they differ in
+    # the last bits, which is why the default ("f16x3") keeps every batch size on the same arithmetic.
+    SMALL_ROWS = 8
+
+    def _fp32_engine(self, dev):
+        if dev not in self._engines_fp32:
+            self._engines_fp32[dev] = _engine.Engine(self._attrs(), device=dev, precision="fp32")
+        return self._engines_fp32[dev]
+
+    def _engine_for(self, n_rows, device=None):
+        eng = self.engine(device)
+        if self._precision == "auto" and n_rows <= self.SMALL_ROWS:
+            return self._fp32_engine(eng.device)
+        return eng
 
     def close(self):
         for e in list(self._engines.values()) + list(self._engines_fp32.values()):
@@ -102,16 +121,14 @@ class _EmulatorBase:
         try:
             if devices is not None and len(devices) > 1:
                 return _engine.forward_host_multi([self.engine(d) for d in devices], x32, ten_to=ten_to, dtype=out_dtype)
-            return self.engine(devices[0] if devices else None).forward_host(x32, ten_to=ten_to, dtype=out_dtype)
+            return self._engine_for(x32.shape[0], devices[0] if devices else None).forward_host(x32, ten_to=ten_to, dtype=out_dtype)
         except _engine.Cpb200Error as err:
             if err.code != _engine.E_RANGE:
                 raise
         # a row beyond the fp16 split range (|z| >= 64 sigma, a huge activation, NaN): the reference evaluates those
         # without complaint (cosmopower_NN.py:371-384), so the batch is redone on the fp32 CUDA-core kernels
         eng = self.engine(devices[0] if devices else None)
-        if eng.device not in self._engines_fp32:
-            self._engines_fp32[eng.device] = _engine.Engine(self._attrs(), device=eng.device, precision="fp32")
-        return self._engines_fp32[eng.device].forward_host(x32, ten_to=ten_to, dtype=out_dtype)
+        return self._fp32_engine(eng.device).forward_host(x32, ten_to=ten_to, dtype=out_dtype)
 
     def predictions_np(self, parameters_dict, devices=None):
         """reference cosmopower_NN.py:388-405 / cosmopower_PCAplusNN.py:384-401 (`devices`: see forward_pass_np)."""
@@ -125,11 +142,11 @@ class _EmulatorBase:
     def predictions_tf(self, parameters_tensor):
         """Array-in/array-out twin (reference cosmopower_NN.py:160-190 / cosmopower_PCAplusNN.py:197-218):
         takes an already ordered CUDA float32 torch tensor (N, n_parameters), returns a CUDA tensor."""
-        return self.engine(parameters_tensor.device.index).forward_torch(parameters_tensor, ten_to=False)
+        return self._engine_for(parameters_tensor.shape[0], parameters_tensor.device.index).forward_torch(parameters_tensor, ten_to=False)
 
     def ten_to_predictions_tf(self, parameters_tensor):
         """reference cosmopower_NN.py:194-211 / cosmopower_PCAplusNN.py:222-239."""
-        return self.engine(parameters_tensor.device.index).forward_torch(parameters_tensor, ten_to=True)
+        return self._engine_for(parameters_tensor.shape[0], parameters_tensor.device.index).forward_torch(parameters_tensor, ten_to=True)
 
     predictions_device = predictions_tf
     ten_to_predictions_device = ten_to_predictions_tf

@@ -66,6 +66,8 @@ struct Gemm {
     std::vector<float> p0, p1, p2; // epilogue constants (see build_gemms)
     // device, SIMT path
     float *dW = nullptr, *dp0 = nullptr, *dp1 = nullptr, *dp2 = nullptr;
+    float* dWt = nullptr;          // fp32 path, tiny batches: the weights transposed, [N][Kp] with Kp = K rounded up to 4 (0 = none: K too deep)
+    int Kp = 0;
     // device, UMMA path
     int k_pad = 0, k_stages = 0, nc = 0, n_chunks = 0;
     int max_nc = cpb::UM_MAX_NC;   // widest chunk the schedule wants for this contraction (256 = two TMEM slots, 128 = one)
@@ -631,6 +633,34 @@ int check_range(cpb200_engine* e) {
 int launch_simt(cpb200_engine* e, const float* params, int64_t n, float* out, int64_t pitch, int flags,
                 cudaStream_t st) {
     const int G = static_cast<int>(e->gemms.size());
+    bool small = n <= cpb::SMALL_M;
+    for (const Gemm& g : e->gemms) small = small && g.dWt != nullptr;
+    if (small) {       // a sampler's single point: one warp per output column, the whole device on every layer (simt_kernels.cuh)
+        const float* A = params;
+        int64_t lda = e->P;
+        const int m = static_cast<int>(n);
+        for (int gi = 0; gi < G; ++gi) {
+            const Gemm& g = e->gemms[gi];
+            const bool last = gi == G - 1;
+            float* C = last ? out : e->simt_buf[gi & 1];
+            const int64_t ldc = last ? pitch : e->simt_width;
+            const unsigned grid = static_cast<unsigned>((g.N + cpb::SMALL_WARPS - 1) / cpb::SMALL_WARPS);
+            const float* im = gi == 0 ? e->d_pmean : nullptr;
+            const float* is = gi == 0 ? e->d_pstd : nullptr;
+            const int ten = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
+            if (g.epi == cpb::EPI_ACT)
+                cpb::dense_small_kernel<cpb::EPI_ACT><<<grid, 32 * cpb::SMALL_WARPS, 0, st>>>(A, lda, g.dWt, g.K, g.Kp, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, 0, im, is);
+            else if (g.epi == cpb::EPI_AFFINE)
+                cpb::dense_small_kernel<cpb::EPI_AFFINE><<<grid, 32 * cpb::SMALL_WARPS, 0, st>>>(A, lda, g.dWt, g.K, g.Kp, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, 0, im, is);
+            else
+                cpb::dense_small_kernel<cpb::EPI_OUT><<<grid, 32 * cpb::SMALL_WARPS, 0, st>>>(A, lda, g.dWt, g.K, g.Kp, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, ten, (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0, im, is);
+            ++e->launches;
+            A = C;
+            lda = ldc;
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
     for (int64_t r0 = 0; r0 < n; r0 += e->simt_rows) {
         const int64_t m = std::min<int64_t>(e->simt_rows, n - r0);
         const float* A = params + r0 * e->P;
@@ -907,6 +937,13 @@ static int create_impl(const cpb200_model_desc* const* descs, int n_models, int 
         int width = 1;
         for (auto& g : e->gemms) {
             if ((rc = upload(&g.dW, g.W.data(), g.W.size()))) return bail(rc);
+            if (round_up(g.K, 4) <= cpb::SMALL_KP_MAX) {      // transposed copy for dense_small_kernel
+                g.Kp = round_up(g.K, 4);
+                std::vector<float> wt(static_cast<size_t>(g.N) * g.Kp, 0.f);
+                for (int k = 0; k < g.K; ++k)
+                    for (int n = 0; n < g.N; ++n) wt[static_cast<size_t>(n) * g.Kp + k] = g.W[static_cast<size_t>(k) * g.N + n];
+                if ((rc = upload(&g.dWt, wt.data(), wt.size()))) return bail(rc);
+            }
             if ((rc = upload(&g.dp0, g.p0.data(), g.p0.size()))) return bail(rc);
             if ((rc = upload(&g.dp1, g.p1.data(), g.p1.size()))) return bail(rc);
             if ((rc = upload(&g.dp2, g.p2.data(), g.p2.size()))) return bail(rc);
@@ -973,7 +1010,7 @@ int cpb200_destroy(cpb200_engine* e) {
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
     for (auto& g : e->gemms) {
-        cudaFree(g.dW); cudaFree(g.dp0); cudaFree(g.dp1); cudaFree(g.dp2);
+        cudaFree(g.dW); cudaFree(g.dWt); cudaFree(g.dp0); cudaFree(g.dp1); cudaFree(g.dp2);
         cudaFree(g.dwpack); cudaFree(g.depi); cudaFree(g.depi_b);
     }
     for (int m = 0; m < cpb::UM_MAX_MODELS; ++m) { cudaFree(e->md_pmean[m]); cudaFree(e->md_pstd[m]); }
@@ -1090,11 +1127,13 @@ public:
     }
     class Session {
     public:
-        explicit Session(bool wanted) {
-            if (!wanted) return;
+        // `helpers`: how many workers to wake (0 = no session) - only as many as the result can feed, the others stay asleep
+        explicit Session(int helpers) {
+            if (helpers <= 0) return;
             HostPool* p = HostPool::get();
             if (p->workers_ == 0 || !p->use_.try_lock()) return;
             pool_ = p;
+            p->awake_.store(std::min(helpers, p->workers_), std::memory_order_release);
             p->hot_.store(true, std::memory_order_release);
             { std::lock_guard<std::mutex> lk(p->m_); }
             p->cv_work_.notify_all();
@@ -1107,7 +1146,7 @@ public:
         Session(const Session&) = delete;
         Session& operator=(const Session&) = delete;
         bool active() const { return pool_ != nullptr; }
-        int threads() const { return pool_ ? pool_->workers_ + 1 : 1; }
+        int threads() const { return pool_ ? pool_->awake_.load(std::memory_order_relaxed) + 1 : 1; }
         // f(i) for i in [0, n) on the workers and the calling thread; returns when all are done
         void run(int n, const std::function<void(int)>& f) {
             HostPool* p = pool_;
@@ -1134,7 +1173,7 @@ private:
 #endif
     }
     explicit HostPool(int n_workers) : workers_(n_workers) {
-        for (int i = 0; i < n_workers; ++i) std::thread([this] { loop(); }).detach();      // they live as long as the process
+        for (int i = 0; i < n_workers; ++i) std::thread([this, i] { loop(i); }).detach();      // they live as long as the process
     }
     // claim and run tasks of the current job until none is left (task claims go through the mutex: tasks are coarse)
     void work() {
@@ -1150,13 +1189,14 @@ private:
             pending_.fetch_sub(1, std::memory_order_release);
         }
     }
-    void loop() {
+    void loop(int index) {
         uint64_t seen = gen_.load(std::memory_order_acquire);
         unsigned idle = 0;
+        auto wanted = [&] { return hot_.load(std::memory_order_acquire) && index < awake_.load(std::memory_order_acquire); };
         for (;;) {
-            if (!hot_.load(std::memory_order_acquire)) {
+            if (!wanted()) {
                 std::unique_lock<std::mutex> lk(m_);
-                cv_work_.wait(lk, [&] { return hot_.load(std::memory_order_acquire); });
+                cv_work_.wait(lk, wanted);
             }
             const uint64_t g = gen_.load(std::memory_order_acquire);
             if (g != seen) { seen = g; work(); idle = 0; }
@@ -1168,6 +1208,7 @@ private:
     std::mutex m_, use_;
     std::condition_variable cv_work_;
     std::atomic<bool> hot_{false};
+    std::atomic<int> awake_{0};                           // workers 0 .. awake_ - 1 take part in the current session
     std::atomic<uint64_t> gen_{0};
     std::atomic<int> pending_{0};
     const std::function<void(int)>* job_ = nullptr;      // guarded by m_
@@ -1226,7 +1267,9 @@ int forward_host_impl(cpb200_engine* e, const float* params_host, int64_t n_rows
     const int64_t n_chunks = (n_rows + R - 1) / R;
     const size_t row_bytes = sizeof(float) * e->n_modes;
     // helpers for the copy-out: woken now, ready when the first piece lands (4 MB of result or more; see HostPool)
-    HostPool::Session session(!pin_out && n_rows * static_cast<int64_t>(row_bytes) >= (4ll << 20));
+    // (one helper per 2 MB of result: a pool that wakes wider than the copy can use only competes with the caller's other threads)
+    const int64_t result_bytes = n_rows * static_cast<int64_t>(sizeof(T)) * e->n_modes;
+    HostPool::Session session(!pin_out && result_bytes >= (4ll << 20) ? static_cast<int>(std::min<int64_t>(64, result_bytes >> 21)) : 0);
     // Tight host rows (the NumPy layout, and the bounce buffers): the kernel then writes tight rows on the device too and the
     // chunk leaves as ONE contiguous copy - 56.9 GB/s on this pool's boxes against 52.4 GB/s for the pitched 2-D copy of
     // 10028-byte rows (tools/microbench/d2h_copy_bw.cu).  Unaligned rows cost the kernel its vector stores (cmb_TT: 2x the

@@ -106,4 +106,71 @@ dense_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
     }
 }
 
+// Tiny batches (a sampler's single point, up to SMALL_M rows): the layer is a handful of dot products per output column, so
+// the tile kernel above - 8 blocks for a 512-wide layer, each walking K in 16-deep steps of dependent global loads - spends
+// 30+ us per layer waiting.  Here a warp owns one output column: it streams that column's K weights once (TRANSPOSED copy
+// Wt[N][Kp], Kp = K padded to a multiple of 4 with zeros: 16-byte coalesced loads), every lane accumulates its share for
+// all rows from the activations in shared memory, five shuffles per row finish the sums, and lane r applies the epilogue
+// of row r.  N / 4 blocks per layer: the whole device reads the layer's weights at once (L2-resident after the first call).
+constexpr int SMALL_M = 8, SMALL_KP_MAX = 1024, SMALL_WARPS = 4;
+
+template <int EPI>
+__global__ void __launch_bounds__(32 * SMALL_WARPS)
+dense_small_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ Wt, int K, int Kp, int N,
+                   float* __restrict__ C, int64_t ldc, int M,
+                   const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2,
+                   int ten_to, int accumulate, const float* __restrict__ in_mean, const float* __restrict__ in_std)
+{
+    __shared__ __align__(16) float As[SMALL_M][SMALL_KP_MAX];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < M * Kp; i += 32 * SMALL_WARPS) {
+        const int r = i / Kp, k = i - r * Kp;
+        float v = 0.f;
+        if (k < K) {
+            v = A[r * lda + k];
+            if (in_mean != nullptr) v = (v - in_mean[k]) / in_std[k];
+        }
+        As[r][k] = v;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * SMALL_WARPS + warp;
+    if (j >= N) return;
+    float acc[SMALL_M];
+#pragma unroll
+    for (int r = 0; r < SMALL_M; ++r) acc[r] = 0.f;
+    const float4* w4 = reinterpret_cast<const float4*>(Wt + static_cast<int64_t>(j) * Kp);
+    for (int k4 = lane; k4 < Kp / 4; k4 += 32) {
+        const float4 w = w4[k4];
+#pragma unroll
+        for (int r = 0; r < SMALL_M; ++r) {
+            if (r < M) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * k4]);
+                acc[r] = fmaf(a.x, w.x, acc[r]); acc[r] = fmaf(a.y, w.y, acc[r]);
+                acc[r] = fmaf(a.z, w.z, acc[r]); acc[r] = fmaf(a.w, w.w, acc[r]);
+            }
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int r = 0; r < SMALL_M; ++r) {
+        float s = acc[r];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == r) mine = s;
+    }
+    if (lane >= M) return;
+    float v = mine;
+    if (EPI == EPI_ACT) {
+        const float a = v + p0[j];
+        const float alpha = p1[j], beta = p2[j];
+        const float s = 1.f / (1.f + expf(-alpha * a));      // exp(+big)=inf -> s=0, as numpy
+        v = (beta + (1.f - beta) * s) * a;
+    } else {
+        v = fmaf(v, p0[j], p1[j]);
+        if (EPI == EPI_OUT && accumulate) v += C[lane * ldc + j];      // fused sum of log-spectra
+        if (EPI == EPI_OUT && ten_to) v = exp10f(v);
+    }
+    C[lane * ldc + j] = v;
+}
+
 }  // namespace cpb

@@ -598,3 +598,44 @@ def test_stand_in_head_scaled_to_unit_rms_outputs_against_the_float32_reference_
     assert np.percentile(e_gpu, 99.9) <= parity.TOL_LOG
     assert e_gpu.max() <= max(parity.TOL_LOG, 3.0 * e_f32.max())
     m.close()
+
+
+@pytest.mark.parametrize("name", ["cmb_TT_NN", "cmb_TE_PCAplusNN", "cmb_PP_PCAplusNN", "PKNLBOOST_NN"])
+def test_fp32_path_tiny_batches_use_the_column_per_warp_kernels(name):
+    """precision="fp32", up to 8 rows (a sampler's single point): dense_small_kernel - a warp per output column over transposed
+    weights - instead of the tile kernel.  Same float32 arithmetic in another summation order: the rows must agree with the same
+    rows evaluated inside a larger batch to float32 rounding, and with the float64 oracle inside the tolerance."""
+    import torch
+    m, attrs = get_model(name, "fp32")
+    x = priors.sample_prior(m.parameters, 64, seed=4711)
+    big = m.forward_pass_np(x)                                        # 64 rows: the tile kernel
+    ref = oracle_np.forward_pass(attrs, x)
+    for n in (1, 3, 8):
+        launches = m.engine().launch_count()
+        small = m.forward_pass_np(x[:n])
+        assert m.engine().launch_count() - launches == len(m.W_) + (1 if "PCA" in name else 0)      # one launch per contraction
+        assert parity.model_error(name, small, ref[:n]) <= parity.model_tol(name)
+        scale = np.abs(ref[:n]).max(axis=1, keepdims=True) if name in parity.LINEAR_MODELS else np.maximum(np.abs(ref[:n]), 1.0)
+        assert (np.abs(small - big[:n]) / scale).max() <= 5e-6
+    xt = torch.from_numpy(x[:1].astype(np.float32)).cuda()
+    assert torch.isfinite(m.ten_to_predictions_tf(xt)).all() or name in parity.LINEAR_MODELS
+
+
+def test_precision_auto_routes_tiny_batches_to_the_fp32_kernels():
+    """precision="auto" (extension): up to 8 rows on the fp32 column-per-warp kernels, larger batches on the tensor path - the
+    same results as the two single-precision models give for those sizes, through the dict API and the device-tensor API."""
+    import torch
+    kind, path = standins.model_path("PKLIN_NN")
+    auto = cp.cosmopower_NN(restore=True, restore_filename=path, device=0, precision="auto")
+    tens, _ = get_model("PKLIN_NN")
+    simt, attrs = get_model("PKLIN_NN", "fp32")
+    x = priors.sample_prior(auto.parameters, 40, seed=99)
+    for n, want in ((1, simt), (8, simt), (9, tens), (40, tens)):
+        d = {k: x[:n, i] for i, k in enumerate(auto.parameters)}
+        assert np.array_equal(auto.ten_to_predictions_np(d), want.ten_to_predictions_np(d)), n
+        xt = torch.from_numpy(x[:n].astype(np.float32)).cuda()
+        assert torch.equal(auto.predictions_tf(xt), want.predictions_tf(xt)), n
+        assert parity.model_error("PKLIN_NN", auto.predictions_np(d), oracle_np.forward_pass(attrs, x[:n])) <= parity.TOL_LOG
+    with pytest.raises(ValueError):
+        cp.cosmopower_NN(restore=True, restore_filename=path, device=0, precision="fp8").engine()
+    auto.close()
