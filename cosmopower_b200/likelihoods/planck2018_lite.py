@@ -186,12 +186,13 @@ class tf_planck2018_lite:
         if fold_te and hasattr(te_emu_model, "_attrs") and "pca_transform_matrix_" in te_emu_model._attrs():
             folded = fold_binning_into_pca_emulator(te_emu_model._attrs(), first, start, self.window_ttteee.reshape(-1),
                                                     self.nbintt, self.nbinte, n_ell)
-            self._te_binned = _engine.Engine(folded, device=self.device, precision=getattr(te_emu_model, "_precision", "f16x3"))
+            te_prec = getattr(te_emu_model, "_precision", "f16x3")
+            self._te_binned = _engine.Engine(folded, device=self.device, precision="f16x3" if te_prec == "auto" else te_prec)
         # fuse_binning=True (the default when TT and EE are tensor-core NN emulators): the window weights are applied and the
         # multipoles summed into per-4-multipole partial band powers inside the emulators' output epilogues
         # (cpb200_engine_set_binning): 5 KB per spectrum row leave the SM instead of 10 KB and the tail adds partials.
         self._binned = False
-        if fuse_binning and all(hasattr(m, "engine") and getattr(m, "_precision", "") == "f16x3" and not hasattr(m, "pca_transform_matrix_")
+        if fuse_binning and all(hasattr(m, "engine") and getattr(m, "_precision", "") in ("f16x3", "auto") and not hasattr(m, "pca_transform_matrix_")
                                 for m in (tt_emu_model, ee_emu_model)):
             w = self.window_ttteee.reshape(-1)
             for m, b0, nb, off in ((tt_emu_model, 0, self.nbintt, 0), (ee_emu_model, self.nbintt + self.nbinte, self.nbinee, 2 * n_ell)):
@@ -204,6 +205,14 @@ class tf_planck2018_lite:
             self._binned = True
         self._engine = _engine.PlikEngine(n_ell, start, first, self.window_ttteee.reshape(-1), x_data, self.fisher,
                                           units_factor, device=self.device, te_binned=self._te_binned is not None, partials=self._binned)
+        # Emulators built with precision="auto": batches of up to SMALL_ROWS rows (a sampler's single point) go through the
+        # emulators' fp32 column-per-warp kernels (35-50 us per call instead of 100-120 us) and a tail of their own (spectra
+        # in, no partials): with cuda_graphs=True one log-likelihood takes 70 us instead of 160 us.
+        self._small = None
+        if all(getattr(m, "_precision", "") == "auto" for m in (tt_emu_model, te_emu_model, ee_emu_model)):
+            te_small = _engine.Engine(folded, device=self.device, precision="fp32") if self._te_binned is not None else None
+            self._small = (te_small, _engine.PlikEngine(n_ell, start, first, self.window_ttteee.reshape(-1), x_data, self.fisher, units_factor,
+                                                        device=self.device, te_binned=te_small is not None, partials=False))
 
     # ===== INVERSE COVARIANCE ======  (:206-230)
     def get_inverse_covmat(self, cov):
@@ -225,7 +234,12 @@ class tf_planck2018_lite:
         small-batch mode), so the three launches go to three streams and share the device instead of queueing."""
         import torch
         te = (lambda: self._te_binned.forward_torch(x, ten_to=False)) if self._te_binned is not None else (lambda: self.te_emu_model.predictions_tf(x))
-        if self._binned:
+        if self._use_small(x.shape[0]):
+            if self._small[0] is not None:
+                te = lambda: self._small[0].forward_torch(x, ten_to=False)
+            tt = lambda: self.tt_emu_model.ten_to_predictions_tf(x)          # precision="auto": the fp32 kernels at this size
+            ee = lambda: self.ee_emu_model.ten_to_predictions_tf(x)
+        elif self._binned:
             tt = lambda: self.tt_emu_model.engine(self.device).forward_torch(x, ten_to=True, binned=True)
             ee = lambda: self.ee_emu_model.engine(self.device).forward_torch(x, ten_to=True, binned=True)
         else:
@@ -252,6 +266,9 @@ class tf_planck2018_lite:
             x.record_stream(s1)
             x.record_stream(s2)
         return cl_tt, cl_te, cl_ee
+
+    def _use_small(self, n_rows):
+        return self._small is not None and n_rows <= type(self.tt_emu_model).SMALL_ROWS
 
     def get_loglkl(self, parameters):
         """(N, len(parameter_keys)) -> (N, 1) log-likelihood, as the reference's get_loglkl (:257-304)."""
@@ -296,7 +313,8 @@ class tf_planck2018_lite:
         for r0 in range(0, n, self.chunk_rows):
             x = cosmo[r0:r0 + self.chunk_rows]
             cl_tt, cl_te, cl_ee = self._emulate(x)
-            out[r0:r0 + x.shape[0], 0] = self._engine.loglike_torch(cl_tt, cl_te, cl_ee, cal[r0:r0 + x.shape[0]])
+            tail = self._small[1] if self._use_small(x.shape[0]) else self._engine
+            out[r0:r0 + x.shape[0], 0] = tail.loglike_torch(cl_tt, cl_te, cl_ee, cal[r0:r0 + x.shape[0]])
         return out
 
     def loglkl(self, parameters, prodpri):
@@ -320,6 +338,11 @@ class tf_planck2018_lite:
         self._engine.close()
         if self._te_binned is not None:
             self._te_binned.close()
+        if self._small is not None:
+            if self._small[0] is not None:
+                self._small[0].close()
+            self._small[1].close()
+            self._small = None
 
 
 

@@ -300,3 +300,39 @@ def test_binning_fused_into_the_emulators_matches_the_unfused_path_and_the_oracl
     fused.close(); plain.close()
     for m in models.values():
         m.close()
+
+
+def test_single_points_through_auto_precision_emulators():
+    """Emulators built with precision="auto": batches of up to 8 rows go through the fp32 column-per-warp kernels and a tail of
+    their own, larger ones through the tensor path with fused binning - both inside the end-to-end tolerance of the oracle
+    pipeline, the small path also as a CUDA-graph replay."""
+    import torch
+    import cosmopower_b200 as cp
+    from cosmopower_b200 import priors, standins
+    from cosmopower_b200.likelihoods import tf_planck2018_lite
+    models, attrs = {}, {}
+    for key, name in (("tt", "cmb_TT_NN"), ("te", "cmb_TE_PCAplusNN"), ("ee", "cmb_EE_NN")):
+        kind, path = standins.model_path(name)
+        models[key] = getattr(cp, kind)(restore=True, restore_filename=path, device=0, precision="auto")
+        attrs[key] = standins.load_attrs(kind, path)
+    params = list(models["tt"].parameters)
+    o = planck_lite_np.PlanckLiteOracle()
+    for graphs in (False, True):
+        like = tf_planck2018_lite(parameters=None, tt_emu_model=models["tt"], te_emu_model=models["te"], ee_emu_model=models["ee"],
+                                  cuda_graphs=graphs)
+        assert like._small is not None and like._binned
+        for n in (1, 8, 9, 300):
+            x = priors.sample_prior(params, n, seed=50 + n)
+            cal = 1 + 0.0025 * np.random.default_rng(n).standard_normal(n)
+            full = np.concatenate([x, cal[:, None]], axis=1).astype(np.float32)
+            x64 = full[:, :len(params)].astype(np.float64)
+            with np.errstate(over="ignore"):
+                ref = o.loglike_from_spectra(10.0 ** oracle_np.forward_pass(attrs["tt"], x64), oracle_np.forward_pass(attrs["te"], x64),
+                                             10.0 ** oracle_np.forward_pass(attrs["ee"], x64), full[:, -1].astype(np.float64))
+            ll = like.get_loglkl(torch.from_numpy(full).cuda()).cpu().numpy()
+            assert ll.shape == (n, 1)
+            rel = np.abs(ll - ref) / np.abs(ref)
+            assert rel.max() <= 1e-3, (graphs, n, rel.max())
+        like.close()
+    for m in models.values():
+        m.close()
