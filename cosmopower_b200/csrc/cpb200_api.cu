@@ -831,6 +831,9 @@ int setup_umma(cpb200_engine* e) {
         }
     }
     e->um_scratch_cta = 2ull * e->n_models * e->um_a0_bytes + static_cast<unsigned long long>(cpb::UM_ACT_BUFS) * e->um_abuf_bytes + 4ull * e->um_pbuf_bytes;
+#ifdef CPB200_PROFILING_BUILD
+    if (const char* pad = getenv("CPB200_SCRATCH_PAD")) e->um_scratch_cta += static_cast<unsigned long long>(atoll(pad)) / 128 * 128;   // L2 set-aliasing probe
+#endif
     if (e->gemms.size() == 1 && e->gemms[0].epi == cpb::EPI_QUADFORM) e->um_scratch_cta = 1024;   // operand tiles are prebuilt elsewhere
     const size_t total = static_cast<size_t>(e->um_scratch_cta) * e->num_sms;
     if (cudaMalloc(reinterpret_cast<void**>(&e->um_scratch), total) != cudaSuccess)

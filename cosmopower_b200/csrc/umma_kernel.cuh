@@ -121,7 +121,7 @@ struct UmmaParams {
     int n_models;
     UmmaModel m[UM_MAX_MODELS];
     int discard_ok;            // every operand-producing contraction has a chunk width that is a multiple of 64 (see the epilogue's discard)
-    int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM, 64 = no MMAs, 128 = no operand copies, 256 = no discards (results are garbage)
+    int debug_flags;           // profiling instantiation only: 1 = epilogues skip all work, 2 = epilogues only read TMEM, 64 = no MMAs, 128 = no operand copies, 256 = no discards, 512 = the OUTPUT epilogues store nothing (results are garbage)
     long long n_rows;
     long long n_pairs;         // ceil(n_tiles / 2)
     long long n_pairgroups;    // ceil(n_pairs / UM_CLUSTER): one pair per CTA of a cluster, processed in lockstep
@@ -631,7 +631,7 @@ __device__ __forceinline__ void epi_output_half(const uint32_t (&v)[16], const f
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = ex2_approx(y[j]);
         }
-        if (dbg & 4) {
+        if (dbg & (4 | 512)) {
             if (y[0] == 1.2345e-30f && y[5] == 3.4e29f) stg_cs_v8(dst, y);
         } else if (mode == OUT_VEC32) {
             stg_cs_v8(dst, y);                 // 8 rows x 128 B per warp instruction: full lines
@@ -671,7 +671,7 @@ __device__ __forceinline__ void epi_output_half_fast(const uint32_t (&v)[16], co
 #pragma unroll
         for (int j = 0; j < 8; ++j) y1[j] = ex2_approx(y1[j]);
     }
-    if (dbg & 4) {
+    if (dbg & (4 | 512)) {
         if (y0[0] == 1.2345e-30f && y1[5] == 3.4e29f) stg_cs_v8(d0, y0);
     } else {
         stg_cs_v8(d0, y0);                     // 8 rows x 128 B per warp instruction: full lines
