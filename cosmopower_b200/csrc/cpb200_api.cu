@@ -648,12 +648,23 @@ int launch_simt(cpb200_engine* e, const float* params, int64_t n, float* out, in
             const float* im = gi == 0 ? e->d_pmean : nullptr;
             const float* is = gi == 0 ? e->d_pstd : nullptr;
             const int ten = (flags & CPB200_FLAG_TEN_TO) ? 1 : 0;
+            // programmatic dependent launch: layer l + 1 may start (and fetch its weights) while layer l drains
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * cpb::SMALL_WARPS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = gi > 0 ? 1 : 0;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            const int acc_flag = (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0, zero = 0, m_i = m, K_i = g.K, Kp_i = g.Kp, N_i = g.N;
+            const float* Wt = g.dWt; const float* q0 = g.dp0; const float* q1 = g.dp1; const float* q2 = g.dp2;
+            cudaError_t lerr;
             if (g.epi == cpb::EPI_ACT)
-                cpb::dense_small_kernel<cpb::EPI_ACT><<<grid, 32 * cpb::SMALL_WARPS, 0, st>>>(A, lda, g.dWt, g.K, g.Kp, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, 0, im, is);
+                lerr = cudaLaunchKernelEx(&cfg, cpb::dense_small_kernel<cpb::EPI_ACT>, A, lda, Wt, K_i, Kp_i, N_i, C, ldc, m_i, q0, q1, q2, zero, zero, im, is);
             else if (g.epi == cpb::EPI_AFFINE)
-                cpb::dense_small_kernel<cpb::EPI_AFFINE><<<grid, 32 * cpb::SMALL_WARPS, 0, st>>>(A, lda, g.dWt, g.K, g.Kp, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, 0, 0, im, is);
+                lerr = cudaLaunchKernelEx(&cfg, cpb::dense_small_kernel<cpb::EPI_AFFINE>, A, lda, Wt, K_i, Kp_i, N_i, C, ldc, m_i, q0, q1, q2, zero, zero, im, is);
             else
-                cpb::dense_small_kernel<cpb::EPI_OUT><<<grid, 32 * cpb::SMALL_WARPS, 0, st>>>(A, lda, g.dWt, g.K, g.Kp, g.N, C, ldc, m, g.dp0, g.dp1, g.dp2, ten, (flags & CPB200_FLAG_ACCUMULATE) ? 1 : 0, im, is);
+                lerr = cudaLaunchKernelEx(&cfg, cpb::dense_small_kernel<cpb::EPI_OUT>, A, lda, Wt, K_i, Kp_i, N_i, C, ldc, m_i, q0, q1, q2, ten, acc_flag, im, is);
+            if (lerr != cudaSuccess) return fail(CPB200_E_CUDA, "tiny-batch layer launch failed: %s", cudaGetErrorString(lerr));
             ++e->launches;
             A = C;
             lda = ldc;

@@ -123,6 +123,24 @@ dense_small_kernel(const float* __restrict__ A, int64_t lda, const float* __rest
 {
     __shared__ __align__(16) float As[SMALL_M][SMALL_KP_MAX];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Programmatic dependent launch: the layers of a forward pass are launched back to back with the "programmatic stream
+    // serialization" attribute, so this grid may start while the previous layer's is still draining.  Everything that does not
+    // depend on that layer's output - this warp's weight column, the largest read of the kernel - is fetched first; then
+    // griddepcontrol.wait blocks until the previous grid has completed and its writes are visible.  (Without the attribute
+    // both instructions are no-ops.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int j = blockIdx.x * SMALL_WARPS + warp;
+    constexpr int WREG = SMALL_KP_MAX / 4 / 32;
+    float4 wreg[WREG];
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(Wt + static_cast<int64_t>(j < N ? j : 0) * Kp);
+#pragma unroll
+        for (int u = 0; u < WREG; ++u) {
+            const int k4 = lane + 32 * u;
+            wreg[u] = k4 < Kp / 4 ? w4[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int i = tid; i < M * Kp; i += 32 * SMALL_WARPS) {
         const int r = i / Kp, k = i - r * Kp;
         float v = 0.f;
@@ -133,20 +151,22 @@ dense_small_kernel(const float* __restrict__ A, int64_t lda, const float* __rest
         As[r][k] = v;
     }
     __syncthreads();
-    const int j = blockIdx.x * SMALL_WARPS + warp;
     if (j >= N) return;
     float acc[SMALL_M];
 #pragma unroll
     for (int r = 0; r < SMALL_M; ++r) acc[r] = 0.f;
-    const float4* w4 = reinterpret_cast<const float4*>(Wt + static_cast<int64_t>(j) * Kp);
-    for (int k4 = lane; k4 < Kp / 4; k4 += 32) {
-        const float4 w = w4[k4];
 #pragma unroll
-        for (int r = 0; r < SMALL_M; ++r) {
-            if (r < M) {
-                const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * k4]);
-                acc[r] = fmaf(a.x, w.x, acc[r]); acc[r] = fmaf(a.y, w.y, acc[r]);
-                acc[r] = fmaf(a.z, w.z, acc[r]); acc[r] = fmaf(a.w, w.w, acc[r]);
+    for (int u = 0; u < WREG; ++u) {
+        const int k4 = lane + 32 * u;
+        if (k4 < Kp / 4) {
+            const float4 w = wreg[u];
+#pragma unroll
+            for (int r = 0; r < SMALL_M; ++r) {
+                if (r < M) {
+                    const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * k4]);
+                    acc[r] = fmaf(a.x, w.x, acc[r]); acc[r] = fmaf(a.y, w.y, acc[r]);
+                    acc[r] = fmaf(a.z, w.z, acc[r]); acc[r] = fmaf(a.w, w.w, acc[r]);
+                }
             }
         }
     }
