@@ -639,3 +639,33 @@ def test_precision_auto_routes_tiny_batches_to_the_fp32_kernels():
     with pytest.raises(ValueError):
         cp.cosmopower_NN(restore=True, restore_filename=path, device=0, precision="fp8").engine()
     auto.close()
+
+
+def test_fp32_tiny_batches_odd_shapes_and_the_fused_sum():
+    """dense_small_kernel on widths that are not multiples of four, a layer deeper than its shared-memory rows allow (falls back
+    to the tile kernel), and the fused P(k) sum (the second emulator's output layer adds what the first one wrote)."""
+    rng = np.random.default_rng(5)
+    for n_hidden, n_params, n_modes in (([37, 101], 7, 333), ([1100], 5, 70), ([], 3, 9)):
+        dims = [n_params] + list(n_hidden) + [n_modes]
+        W = [(rng.standard_normal((a, b)) / np.sqrt(a)).astype(np.float32) for a, b in zip(dims[:-1], dims[1:])]
+        b = [(0.1 * rng.standard_normal(d)).astype(np.float32) for d in dims[1:]]
+        kw = dict(parameters=["p%d" % i for i in range(n_params)], modes=np.arange(n_modes), n_hidden=list(n_hidden),
+                  parameters_mean=rng.standard_normal(n_params), parameters_std=0.5 + rng.random(n_params),
+                  features_mean=rng.standard_normal(n_modes), features_std=0.5 + rng.random(n_modes),
+                  weights=dict(W_=W, b_=b, alphas_=[(1.0 + rng.standard_normal(d)).astype(np.float32) for d in n_hidden],
+                               betas_=[(0.5 * rng.standard_normal(d)).astype(np.float32) for d in n_hidden]))
+        m = cp.cosmopower_NN(device=0, precision="fp32", **kw)
+        attrs = {k: getattr(m, k) for k in ("W_", "b_", "alphas_", "betas_", "parameters_mean_", "parameters_std_",
+                                            "features_mean_", "features_std_", "n_layers", "parameters", "n_modes")}
+        x = rng.standard_normal((5, n_params))
+        for n in (1, 5):
+            assert parity.log_error(m.forward_pass_np(x[:n]), oracle_np.forward_pass(attrs, x[:n])) <= parity.TOL_LOG, (n_hidden, n)
+        m.close()
+    lin, a_lin = get_model("PKLIN_NN", "fp32")
+    nl, a_nl = get_model("PKNLBOOST_NN", "fp32")
+    x_nl = priors.sample_prior(nl.parameters, 3, seed=12)
+    d_nl = {k: x_nl[:, i] for i, k in enumerate(nl.parameters)}
+    d_lin = {k: d_nl[k] for k in lin.parameters}
+    y = cp.ten_to_sum_predictions_np([lin, nl], [d_lin, d_nl])
+    total_log = oracle_np.predictions_np(a_lin, d_lin) + oracle_np.predictions_np(a_nl, d_nl)
+    assert y.shape == (3, 420) and parity.ten_to_error(y, total_log) <= 2 * parity.TOL_LOG
