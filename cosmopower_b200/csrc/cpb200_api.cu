@@ -754,6 +754,13 @@ int launch_umma(cpb200_engine* e, const float* const* params, int64_t n, float* 
     p.ext_a0 = e->qf_ext_a0; p.qf_d = e->qf_d; p.qf_pitch = e->qf_pitch; p.qf_cols = e->qf_cols; p.qf_partial = e->qf_partial;
     if (p.max_cycles) cudaMemsetAsync(e->d_max_cycles, 0, sizeof(unsigned long long), st);
     p.counters = e->d_counters;
+#ifdef CPB200_PROFILING_BUILD
+    if (e->d_counters) if (const char* al = getenv("CPB200_ALIGN_EVERY")) {      // phase-alignment probe (see UmmaParams::align_every)
+        static unsigned* d_align = nullptr;
+        if (!d_align) cudaMalloc(reinterpret_cast<void**>(&d_align), sizeof(unsigned));
+        if (d_align) { cudaMemsetAsync(d_align, 0, sizeof(unsigned), st); p.align_every = atoi(al); p.align_counter = d_align; }
+    }
+#endif
     int max_clusters = e->num_sms / cpb::UM_CLUSTER;
     if (const char* cap = getenv("CPB200_DEBUG_MAX_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(cap)));  // tuning aid
     // Small batches leave most SMs idle: deal the output contraction's chunks (57 % of a cmb_TT pair's cycles) out to

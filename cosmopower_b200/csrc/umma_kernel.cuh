@@ -153,6 +153,10 @@ struct UmmaParams {
     int qf_cols;
     float* qf_partial;   // every launch: max over CTAs of the SM cycles between kernel entry and exit
     long long* counters;       // optional debug counters, 16 per CTA (nullptr = off); see UM_CNT_*
+    // profiling probe (CPB200_ALIGN_EVERY, PROF instantiation only): every `align_every` pairs the MMA issuers of all clusters
+    // meet at a counter in global memory, so that the clusters walk their trunks and their output phases at the same time
+    int align_every;
+    unsigned* align_counter;
 };
 
 // job-table entry, word 0: which part of which job, and where its accumulator lives
@@ -1024,7 +1028,21 @@ fused_mlp_umma_kernel(const __grid_constant__ UmmaParams P)
             const uint64_t a_hi0 = umma_desc_a(base + UM_SMEM_STAGES);
             const uint64_t a_lo0 = umma_desc_a(base + UM_SMEM_STAGES + UM_A_HALF_BYTES);
             const uint64_t b_hi0 = umma_desc(base + UM_SMEM_STAGES + UM_A_STAGE_BYTES);
+            long long aligned_it = 0;
+            const long long align_last = P.align_every > 0 ? (P.n_pairgroups / (gridDim.x / UM_CLUSTER)) : 0;   // iterations every cluster runs
             UM_FOR_EACH_ENTRY({
+                if (PROF && P.align_every > 0 && P.align_counter && it != aligned_it && it % P.align_every == 0 && it <= align_last && out_split == 1) {
+                    aligned_it = it;
+                    if (lane == 0) {
+                        const unsigned target = static_cast<unsigned>((it / P.align_every) * (gridDim.x / UM_CLUSTER));
+                        atomicAdd(P.align_counter, 1u);
+                        const long long t0 = clock64();
+                        while (*reinterpret_cast<volatile unsigned*>(P.align_counter) < target) {
+                            if (clock64() - t0 > CPB_WATCHDOG_CYCLES) { if (P.error_flag) atomicExch(P.error_flag, 210); __threadfence_system(); __trap(); }
+                        }
+                    }
+                    __syncwarp();
+                }
                 const UmmaGemm& L = P.g[g];
                 const uint32_t idesc = umma_idesc(L.nc);
                 const uint64_t b_lo_off = static_cast<uint64_t>((static_cast<uint32_t>(L.nc / 2) * UM_KS * 2u) >> 4);   // (hi -> lo half tile) >> 4
